@@ -1,0 +1,61 @@
+// common.cuh — shared types of the engine (host + device).
+// Stand-in engine for the "reassignment method" of /root/reference/README.md:3,11;
+// conventions are SURVEY.md §7 / oracle/reassign_oracle.py header.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ems {
+
+// Fixed-point scale of the deterministic accumulator: energy * 2^44 as u64.
+// Integer adds are associative, so the grid is bit-exact in any deposit order.
+// Range per cell 2^20 (a full-scale sine is 1.0), resolution 5.7e-14 (-132 dB).
+constexpr float  kFixScale    = 17592186044416.0f;        // 2^44
+constexpr double kFixScaleInv = 1.0 / 17592186044416.0;
+
+enum DepositMode : int {
+    kStorePoints = 0,   // write (dt_cols, dk_bins, energy) triples
+    kDepositU64  = 1,   // red.global.add.u64 into the fixed-point accumulator
+    kDepositF32  = 2    // red.global.add.f32 fast mode
+};
+
+// Arguments of the fused frame-gather + 3-window STFT + reassignment kernels.
+struct StftArgs {
+    const float*  pcm;        // planar [channels][S]
+    long long     S;          // samples per channel
+    long long     F;          // frames per channel
+    long long     f_begin;    // frame range of this launch (per channel)
+    long long     f_end;
+    int           channels;
+    int           hop;
+    const float4* win;        // [N] {h, th*(2/N), dh*(N/pi), 0}
+    const float2* tw;         // [N] W_N^j = (cos, -sin)(2 pi j / N)
+    float*        dt_cols;    // [channels][F][B] or null
+    float*        dk_bins;
+    float*        energy;
+    void*         acc;        // [channels][F][B] u64 or f32 accumulator, or null
+    float         gate_lin;   // drop points with energy <= gate
+    float         inv_hop;
+    int           mode;       // DepositMode
+    int           reassign;   // 0: plain spectrogram columns
+};
+
+struct PostArgs {
+    const void*   acc;        // u64 or f32 [channels][F][B]
+    int           acc_is_u64;
+    float*        grid;       // fp32 [channels][F][B] or null
+    uint8_t*      index;      // u8   [channels][F][B] or null
+    const float*  weight;     // [B] gain^2 * w_low(k)
+    float*        carry;      // [channels][B] EMA state entering col_begin (updated)
+    long long     F;
+    long long     col_begin;
+    long long     col_end;
+    int           B;
+    int           channels;
+    float         smoothing;
+    float         db_floor;   // TOP_DB - range
+    float         inv_range;  // 255 / range
+    float         gate_db;
+};
+
+}  // namespace ems

@@ -1,0 +1,530 @@
+// engine.cu — host side of the engine and the C-ABI of include/emspec.h.
+// C++ host, no torch types; one handle = one CUDA stream.
+#include "../../include/emspec.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "common.cuh"
+#include "scatter_post.cuh"
+#include "stft_generic.cuh"
+
+namespace ems {
+
+constexpr double kPi = 3.14159265358979323846;
+constexpr double kLowEndCornerHz = 200.0;   // oracle/reassign_oracle.py LOW_END_CORNER_HZ
+constexpr double kTopDb = 0.0;
+
+struct DevBuf {
+    void*  p = nullptr;
+    size_t bytes = 0;
+};
+
+}  // namespace ems
+
+struct ems_handle {
+    ems_params prm{};
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;      // the stream calls run on
+    cudaStream_t copy_in = nullptr, copy_out = nullptr;
+    float4* win = nullptr;              // [N]
+    float2* tw = nullptr;               // [N]
+    float*  weight = nullptr;           // [B]
+    ems::DevBuf acc, carry, ema_local, ema_carry, host_pcm, host_idx, host_grid;
+    cudaEvent_t ev[EMS_STAGE_COUNT][2]{};
+    bool ev_valid[EMS_STAGE_COUNT]{};
+    uint64_t launches = 0;
+    char err[256] = "";
+};
+
+namespace ems {
+
+static ems_status fail(ems_handle* h, ems_status s, const char* fmt, ...) {
+    if (h) {
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(h->err, sizeof(h->err), fmt, ap);
+        va_end(ap);
+    }
+    return s;
+}
+
+#define EMS_CUDA(h, call)                                                              \
+    do {                                                                               \
+        cudaError_t e_ = (call);                                                       \
+        if (e_ != cudaSuccess)                                                         \
+            return ems::fail((h), e_ == cudaErrorMemoryAllocation ? EMS_ERR_NOMEM      \
+                                                                  : EMS_ERR_CUDA,     \
+                             "%s: %s", #call, cudaGetErrorString(e_));                 \
+    } while (0)
+
+static ems_status ensure(ems_handle* h, DevBuf& b, size_t bytes) {
+    if (b.bytes >= bytes) return EMS_OK;
+    if (b.p) { EMS_CUDA(h, cudaStreamSynchronize(h->stream)); EMS_CUDA(h, cudaFree(b.p)); b = DevBuf{}; }
+    EMS_CUDA(h, cudaMalloc(&b.p, bytes));
+    b.bytes = bytes;
+    return EMS_OK;
+}
+
+static bool valid_params(const ems_params& p) {
+    if (p.n_fft < 256 || p.n_fft > 32768 || (p.n_fft & (p.n_fft - 1))) return false;
+    if (p.hop < 1 || p.hop > p.n_fft) return false;
+    if (!(p.sample_rate > 0.f) || p.channels < 1 || p.channels > 64) return false;
+    if (!(p.db_range > 0.f) || !(p.gain >= 0.f) || !(p.low_end_boost > 0.f)) return false;
+    if (!(p.smoothing >= 0.f) || !(p.smoothing < 1.f)) return false;
+    if (!std::isfinite(p.noise_gate_db)) return false;
+    return true;
+}
+
+static int ilog2(int n) { int l = 0; while ((1 << l) < n) ++l; return l; }
+
+static ems_status upload_display(ems_handle* h) {
+    const int B = h->prm.n_fft / 2 + 1;
+    std::vector<float> w(B);
+    const double g2 = (double)h->prm.gain * (double)h->prm.gain;
+    for (int k = 0; k < B; ++k) {
+        const double f = (double)k * (double)h->prm.sample_rate / (double)h->prm.n_fft;
+        const double r = f / kLowEndCornerHz;
+        w[k] = (float)(g2 * (1.0 + ((double)h->prm.low_end_boost - 1.0) / (1.0 + r * r)));
+    }
+    EMS_CUDA(h, cudaMemcpyAsync(h->weight, w.data(), B * sizeof(float), cudaMemcpyHostToDevice,
+                                h->stream));
+    EMS_CUDA(h, cudaStreamSynchronize(h->stream));
+    return EMS_OK;
+}
+
+static long long frames_of(const ems_params& p, size_t S) {
+    return S < (size_t)p.n_fft ? 0 : 1 + (long long)((S - (size_t)p.n_fft) / (size_t)p.hop);
+}
+
+// ---------------------------------------------------------------- kernel dispatch
+template <int LOG2N>
+static ems_status launch_generic(ems_handle* h, const StftArgs& a) {
+    constexpr int N = 1 << LOG2N;
+    constexpr int THREADS = 256;
+    const size_t smem = (size_t)N * 12;
+    auto kern = stft_reassign_generic<LOG2N, THREADS>;
+    EMS_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    EMS_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, smem));
+    if (occ < 1) return fail(h, EMS_ERR_UNSUPPORTED, "n_fft=%d does not fit shared memory", N);
+    const long long total = (a.f_end - a.f_begin) * a.channels;
+    long long grid = (long long)h->sm_count * occ;
+    if (grid > total) grid = total;
+    if (grid < 1) return EMS_OK;
+    kern<<<(unsigned)grid, THREADS, smem, h->stream>>>(a);
+    ++h->launches;
+    EMS_CUDA(h, cudaGetLastError());
+    return EMS_OK;
+}
+
+static ems_status launch_stft(ems_handle* h, const StftArgs& a) {
+    switch (ilog2(h->prm.n_fft)) {
+        case 8:  return launch_generic<8>(h, a);
+        case 9:  return launch_generic<9>(h, a);
+        case 10: return launch_generic<10>(h, a);
+        case 11: return launch_generic<11>(h, a);
+        case 12: return launch_generic<12>(h, a);
+        case 13: return launch_generic<13>(h, a);
+        case 14: return launch_generic<14>(h, a);
+        default: return fail(h, EMS_ERR_UNSUPPORTED, "n_fft=%d has no kernel in this build",
+                             h->prm.n_fft);
+    }
+}
+
+static StftArgs make_args(ems_handle* h, const float* pcm, size_t S, long long F) {
+    StftArgs a{};
+    a.pcm = pcm; a.S = (long long)S; a.F = F; a.f_begin = 0; a.f_end = F;
+    a.channels = h->prm.channels; a.hop = h->prm.hop;
+    a.win = h->win; a.tw = h->tw;
+    a.gate_lin = (float)std::pow(10.0, (double)h->prm.noise_gate_db / 10.0);
+    a.inv_hop = 1.0f / (float)h->prm.hop;
+    a.reassign = (h->prm.flags & EMS_FLAG_REASSIGN) ? 1 : 0;
+    return a;
+}
+
+static PostArgs make_post(ems_handle* h, long long F, float* grid, uint8_t* index) {
+    PostArgs p{};
+    p.acc = h->acc.p;
+    p.acc_is_u64 = (h->prm.flags & EMS_FLAG_DETERMINISTIC) ? 1 : 0;
+    p.grid = grid; p.index = index; p.weight = h->weight;
+    p.carry = (float*)h->carry.p;
+    p.F = F; p.col_begin = 0; p.col_end = F;
+    p.B = h->prm.n_fft / 2 + 1; p.channels = h->prm.channels;
+    p.smoothing = h->prm.smoothing;
+    p.db_floor = (float)(kTopDb - (double)h->prm.db_range);
+    p.inv_range = 255.0f / h->prm.db_range;
+    p.gate_db = h->prm.noise_gate_db;
+    return p;
+}
+
+// Post-pass over columns [col_begin, col_end) of every channel; h->carry holds the EMA
+// state entering col_begin and leaves with the state after col_end - 1.
+static ems_status run_post(ems_handle* h, PostArgs p) {
+    const long long ncols = p.col_end - p.col_begin;
+    if (ncols <= 0) return EMS_OK;
+    const int n_chunks = (int)((ncols + kPostChunk - 1) / kPostChunk);
+    const dim3 blk(128);
+    const dim3 grd((p.B + 127) / 128, n_chunks, p.channels);
+    const float* carry_in = nullptr;
+    if (p.smoothing > 0.f && p.index) {
+        const size_t bytes = (size_t)p.channels * n_chunks * p.B * sizeof(float);
+        ems_status s;
+        if ((s = ensure(h, h->ema_local, bytes)) != EMS_OK) return s;
+        if ((s = ensure(h, h->ema_carry, bytes)) != EMS_OK) return s;
+        p.carry = (float*)h->carry.p;
+        post_ema_local_kernel<<<grd, blk, 0, h->stream>>>(p, (float*)h->ema_local.p, n_chunks);
+        const long long last = ncols - (long long)(n_chunks - 1) * kPostChunk;
+        post_ema_carry_kernel<<<dim3((p.B + 127) / 128, p.channels), blk, 0, h->stream>>>(
+            p, (const float*)h->ema_local.p, (float*)h->ema_carry.p, n_chunks,
+            (float)std::pow((double)p.smoothing, (double)kPostChunk),
+            (float)std::pow((double)p.smoothing, (double)last));
+        h->launches += 2;
+        carry_in = (const float*)h->ema_carry.p;
+    }
+    post_emit_kernel<<<grd, blk, 0, h->stream>>>(p, carry_in, n_chunks);
+    ++h->launches;
+    EMS_CUDA(h, cudaGetLastError());
+    return EMS_OK;
+}
+
+static ems_status reset_carry(ems_handle* h) {
+    const size_t bytes = (size_t)h->prm.channels * (h->prm.n_fft / 2 + 1) * sizeof(float);
+    ems_status s = ensure(h, h->carry, bytes);
+    if (s != EMS_OK) return s;
+    EMS_CUDA(h, cudaMemsetAsync(h->carry.p, 0, bytes, h->stream));
+    return EMS_OK;
+}
+
+static void stage_begin(ems_handle* h, int st) { cudaEventRecord(h->ev[st][0], h->stream); }
+static void stage_end(ems_handle* h, int st) {
+    cudaEventRecord(h->ev[st][1], h->stream);
+    h->ev_valid[st] = true;
+}
+
+static ems_status finish(ems_handle* h) {
+    if (h->prm.flags & EMS_FLAG_SYNC) EMS_CUDA(h, cudaStreamSynchronize(h->stream));
+    return EMS_OK;
+}
+
+}  // namespace ems
+
+using namespace ems;
+
+// ============================================================================ C-ABI
+extern "C" {
+
+int ems_abi_version(void) { return EMS_ABI_VERSION; }
+
+const char* ems_status_str(ems_status s) {
+    switch (s) {
+        case EMS_OK: return "ok";
+        case EMS_ERR_INVALID_ARG: return "invalid argument";
+        case EMS_ERR_UNSUPPORTED: return "unsupported";
+        case EMS_ERR_CUDA: return "CUDA error";
+        case EMS_ERR_NOMEM: return "out of memory";
+        case EMS_ERR_STATE: return "invalid state";
+    }
+    return "unknown status";
+}
+
+const char* ems_last_error(const ems_handle* h) { return h ? h->err : "null handle"; }
+
+ems_status ems_default_params(ems_params* p) {
+    if (!p) return EMS_ERR_INVALID_ARG;
+    p->n_fft = 4096; p->hop = 128; p->sample_rate = 48000.f; p->channels = 1;
+    p->db_range = 58.f; p->gain = 3.5f; p->low_end_boost = 3.9f; p->smoothing = 0.f;
+    p->noise_gate_db = -65.f;
+    p->flags = EMS_FLAG_REASSIGN | EMS_FLAG_DETERMINISTIC;
+    return EMS_OK;
+}
+
+ems_status ems_create(const ems_params* params, ems_handle** out) {
+    if (!params || !out) return EMS_ERR_INVALID_ARG;
+    *out = nullptr;
+    if (!valid_params(*params)) return EMS_ERR_INVALID_ARG;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) return EMS_ERR_CUDA;  // no CPU fallback
+    ems_handle* h = new (std::nothrow) ems_handle();
+    if (!h) return EMS_ERR_NOMEM;
+    h->prm = *params;
+    auto bail = [&](ems_status s) { ems_destroy(h); return s; };
+    if (cudaGetDevice(&h->device) != cudaSuccess) return bail(EMS_ERR_CUDA);
+    cudaDeviceProp prop{};
+    if (cudaGetDeviceProperties(&prop, h->device) != cudaSuccess) return bail(EMS_ERR_CUDA);
+    h->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&h->copy_in, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&h->copy_out, cudaStreamNonBlocking) != cudaSuccess)
+        return bail(EMS_ERR_CUDA);
+    h->stream = h->own_stream;
+    for (auto& e : h->ev)
+        for (auto& x : e)
+            if (cudaEventCreate(&x) != cudaSuccess) return bail(EMS_ERR_CUDA);
+
+    const int N = params->n_fft, B = N / 2 + 1;
+    if (cudaMalloc(&h->win, sizeof(float4) * N) != cudaSuccess ||
+        cudaMalloc(&h->tw, sizeof(float2) * N) != cudaSuccess ||
+        cudaMalloc(&h->weight, sizeof(float) * B) != cudaSuccess)
+        return bail(EMS_ERR_NOMEM);
+    std::vector<float4> win(N);
+    std::vector<float2> tw(N);
+    for (int n = 0; n < N; ++n) {
+        const double ang = 2.0 * kPi * (double)n / (double)N;
+        const double c = std::cos(ang), s = std::sin(ang);
+        const double hn = 0.5 - 0.5 * c;
+        win[n] = make_float4((float)hn, (float)(((double)n - N / 2) * hn * (2.0 / N)), (float)s, 0.f);
+        tw[n] = make_float2((float)c, (float)(-s));
+    }
+    if (cudaMemcpy(h->win, win.data(), sizeof(float4) * N, cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(h->tw, tw.data(), sizeof(float2) * N, cudaMemcpyHostToDevice) != cudaSuccess)
+        return bail(EMS_ERR_CUDA);
+    ems_status s = upload_display(h);
+    if (s != EMS_OK) return bail(s);
+    *out = h;
+    return EMS_OK;
+}
+
+ems_status ems_destroy(ems_handle* h) {
+    if (!h) return EMS_ERR_INVALID_ARG;
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    for (DevBuf* b : {&h->acc, &h->carry, &h->ema_local, &h->ema_carry, &h->host_pcm,
+                      &h->host_idx, &h->host_grid})
+        if (b->p) cudaFree(b->p);
+    if (h->win) cudaFree(h->win);
+    if (h->tw) cudaFree(h->tw);
+    if (h->weight) cudaFree(h->weight);
+    for (auto& e : h->ev)
+        for (auto& x : e)
+            if (x) cudaEventDestroy(x);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    if (h->copy_in) cudaStreamDestroy(h->copy_in);
+    if (h->copy_out) cudaStreamDestroy(h->copy_out);
+    delete h;
+    return EMS_OK;
+}
+
+ems_status ems_update_display(ems_handle* h, const ems_params* p) {
+    if (!h || !p) return EMS_ERR_INVALID_ARG;
+    if (!valid_params(*p) || p->n_fft != h->prm.n_fft || p->hop != h->prm.hop ||
+        p->channels != h->prm.channels || p->sample_rate != h->prm.sample_rate)
+        return fail(h, EMS_ERR_INVALID_ARG, "n_fft/hop/channels/sample_rate need a new handle");
+    h->prm = *p;
+    return upload_display(h);
+}
+
+ems_status ems_set_stream(ems_handle* h, void* s) {
+    if (!h) return EMS_ERR_INVALID_ARG;
+    h->stream = s ? (cudaStream_t)s : h->own_stream;
+    return EMS_OK;
+}
+
+ems_status ems_get_stream(ems_handle* h, void** s) {
+    if (!h || !s) return EMS_ERR_INVALID_ARG;
+    *s = (void*)h->stream;
+    return EMS_OK;
+}
+
+ems_status ems_synchronize(ems_handle* h) {
+    if (!h) return EMS_ERR_INVALID_ARG;
+    EMS_CUDA(h, cudaStreamSynchronize(h->stream));
+    return EMS_OK;
+}
+
+ems_status ems_frame_count(const ems_handle* h, size_t S, size_t* F) {
+    if (!h || !F) return EMS_ERR_INVALID_ARG;
+    *F = (size_t)frames_of(h->prm, S);
+    return EMS_OK;
+}
+
+ems_status ems_process_points(ems_handle* h, const float* pcm, size_t S, float* dt_cols,
+                              float* dk_bins, float* energy, size_t* n_frames) {
+    if (!h) return EMS_ERR_INVALID_ARG;
+    const long long F = frames_of(h->prm, S);
+    if (n_frames) *n_frames = (size_t)F;
+    for (bool& v : h->ev_valid) v = false;
+    if (F == 0) return EMS_OK;
+    if (!pcm || !dt_cols || !dk_bins || !energy) return fail(h, EMS_ERR_INVALID_ARG, "null buffer");
+    StftArgs a = make_args(h, pcm, S, F);
+    a.dt_cols = dt_cols; a.dk_bins = dk_bins; a.energy = energy; a.mode = kStorePoints;
+    stage_begin(h, EMS_STAGE_POINTS);
+    ems_status s = launch_stft(h, a);
+    if (s != EMS_OK) return s;
+    stage_end(h, EMS_STAGE_POINTS);
+    return finish(h);
+}
+
+ems_status ems_scatter_points(ems_handle* h, const float* dt_cols, const float* dk_bins,
+                              const float* energy, size_t n_frames, float* grid, uint8_t* index) {
+    if (!h) return EMS_ERR_INVALID_ARG;
+    for (bool& v : h->ev_valid) v = false;
+    if (n_frames == 0) return EMS_OK;
+    if (!dt_cols || !dk_bins || !energy || (!grid && !index))
+        return fail(h, EMS_ERR_INVALID_ARG, "null buffer");
+    const long long F = (long long)n_frames;
+    const int B = h->prm.n_fft / 2 + 1, C = h->prm.channels;
+    const bool det = h->prm.flags & EMS_FLAG_DETERMINISTIC;
+    const size_t cells = (size_t)C * F * B;
+    ems_status s = ensure(h, h->acc, cells * (det ? 8 : 4));
+    if (s != EMS_OK) return s;
+    if ((s = reset_carry(h)) != EMS_OK) return s;
+    stage_begin(h, EMS_STAGE_SCATTER);
+    EMS_CUDA(h, cudaMemsetAsync(h->acc.p, 0, cells * (det ? 8 : 4), h->stream));
+    long long blocks = (long long)((cells + 255) / 256);
+    const long long cap = (long long)h->sm_count * 32;
+    if (blocks > cap) blocks = cap;
+    scatter_points_kernel<<<(unsigned)blocks, 256, 0, h->stream>>>(dt_cols, dk_bins, energy,
+                                                                  h->acc.p, det, F, B, C);
+    ++h->launches;
+    EMS_CUDA(h, cudaGetLastError());
+    stage_end(h, EMS_STAGE_SCATTER);
+    stage_begin(h, EMS_STAGE_POST);
+    if ((s = run_post(h, make_post(h, F, grid, index))) != EMS_OK) return s;
+    stage_end(h, EMS_STAGE_POST);
+    return finish(h);
+}
+
+ems_status ems_process_grid(ems_handle* h, const float* pcm, size_t S, float* grid,
+                            uint8_t* index, size_t* n_frames) {
+    if (!h) return EMS_ERR_INVALID_ARG;
+    const long long F = frames_of(h->prm, S);
+    if (n_frames) *n_frames = (size_t)F;
+    for (bool& v : h->ev_valid) v = false;
+    if (F == 0) return EMS_OK;
+    if (!pcm || (!grid && !index)) return fail(h, EMS_ERR_INVALID_ARG, "null buffer");
+    const int B = h->prm.n_fft / 2 + 1, C = h->prm.channels;
+    const bool det = h->prm.flags & EMS_FLAG_DETERMINISTIC;
+    const size_t cells = (size_t)C * F * B;
+    ems_status s = ensure(h, h->acc, cells * (det ? 8 : 4));
+    if (s != EMS_OK) return s;
+    if ((s = reset_carry(h)) != EMS_OK) return s;
+    StftArgs a = make_args(h, pcm, S, F);
+    a.acc = h->acc.p; a.mode = det ? kDepositU64 : kDepositF32;
+    stage_begin(h, EMS_STAGE_POINTS);
+    EMS_CUDA(h, cudaMemsetAsync(h->acc.p, 0, cells * (det ? 8 : 4), h->stream));
+    if ((s = launch_stft(h, a)) != EMS_OK) return s;
+    stage_end(h, EMS_STAGE_POINTS);
+    stage_begin(h, EMS_STAGE_POST);
+    if ((s = run_post(h, make_post(h, F, grid, index))) != EMS_OK) return s;
+    stage_end(h, EMS_STAGE_POST);
+    return finish(h);
+}
+
+ems_status ems_process_host(ems_handle* h, const float* pcm_host, size_t S, float* grid_host,
+                            uint8_t* index_host, size_t* n_frames) {
+    if (!h) return EMS_ERR_INVALID_ARG;
+    const long long F = frames_of(h->prm, S);
+    if (n_frames) *n_frames = (size_t)F;
+    for (bool& v : h->ev_valid) v = false;
+    if (F == 0) return EMS_OK;
+    if (!pcm_host || (!grid_host && !index_host)) return fail(h, EMS_ERR_INVALID_ARG, "null buffer");
+    const int N = h->prm.n_fft, H = h->prm.hop, B = N / 2 + 1, C = h->prm.channels;
+    const bool det = h->prm.flags & EMS_FLAG_DETERMINISTIC;
+    const size_t cells = (size_t)C * F * B;
+    ems_status s;
+    if ((s = ensure(h, h->host_pcm, (size_t)C * S * sizeof(float))) != EMS_OK) return s;
+    if ((s = ensure(h, h->acc, cells * (det ? 8 : 4))) != EMS_OK) return s;
+    if (index_host && (s = ensure(h, h->host_idx, cells)) != EMS_OK) return s;
+    if (grid_host && (s = ensure(h, h->host_grid, cells * sizeof(float))) != EMS_OK) return s;
+    if ((s = reset_carry(h)) != EMS_OK) return s;
+    float* pcm_dev = (float*)h->host_pcm.p;
+    uint8_t* idx_dev = index_host ? (uint8_t*)h->host_idx.p : nullptr;
+    float* grid_dev = grid_host ? (float*)h->host_grid.p : nullptr;
+    EMS_CUDA(h, cudaMemsetAsync(h->acc.p, 0, cells * (det ? 8 : 4), h->stream));
+
+    // Frame chunks: H2D of chunk c+1 overlaps the kernels of chunk c, whose finished
+    // columns (those no later frame can reach: col < f_end - R) go back while c+1 runs.
+    const long long R = (N / 2 + H - 1) / H;
+    long long chunk = (long long)(((size_t)64 << 20) / ((size_t)H * sizeof(float)));  // ~64 MiB of new samples
+    if (chunk < 4 * R + 1024) chunk = 4 * R + 1024;
+    const int n_chunks = (int)((F + chunk - 1) / chunk);
+    std::vector<cudaEvent_t> ev_in(n_chunks), ev_done(n_chunks);
+    for (int c = 0; c < n_chunks; ++c) {
+        cudaEventCreateWithFlags(&ev_in[c], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&ev_done[c], cudaEventDisableTiming);
+    }
+    auto cleanup = [&]() {
+        for (int c = 0; c < n_chunks; ++c) { cudaEventDestroy(ev_in[c]); cudaEventDestroy(ev_done[c]); }
+    };
+    cudaEvent_t ev_start;
+    cudaEventCreateWithFlags(&ev_start, cudaEventDisableTiming);
+    cudaEventRecord(ev_start, h->stream);
+    cudaStreamWaitEvent(h->copy_in, ev_start, 0);     // the memset and earlier work come first
+    cudaStreamWaitEvent(h->copy_out, ev_start, 0);
+    cudaEventDestroy(ev_start);
+    long long sent = 0;        // samples per channel already on the device
+    long long cols_done = 0;   // columns already post-processed
+    ems_status rs = EMS_OK;
+    for (int c = 0; c < n_chunks && rs == EMS_OK; ++c) {
+        const long long f0 = (long long)c * chunk, f1 = std::min(F, f0 + chunk);
+        const long long need = (f1 == F) ? (long long)S : (f1 - 1) * H + N;   // samples needed
+        for (int ch = 0; ch < C; ++ch)
+            cudaMemcpyAsync(pcm_dev + (size_t)ch * S + sent, pcm_host + (size_t)ch * S + sent,
+                            (size_t)(need - sent) * sizeof(float), cudaMemcpyHostToDevice,
+                            h->copy_in);
+        sent = need;
+        cudaEventRecord(ev_in[c], h->copy_in);
+        cudaStreamWaitEvent(h->stream, ev_in[c], 0);
+        StftArgs a = make_args(h, pcm_dev, S, F);
+        a.f_begin = f0; a.f_end = f1;
+        a.acc = h->acc.p; a.mode = det ? kDepositU64 : kDepositF32;
+        if ((rs = launch_stft(h, a)) != EMS_OK) break;
+        const long long col_end = (f1 == F) ? F : std::max(cols_done, f1 - R);
+        PostArgs p = make_post(h, F, grid_dev, idx_dev);
+        p.col_begin = cols_done; p.col_end = col_end;
+        if ((rs = run_post(h, p)) != EMS_OK) break;
+        cudaEventRecord(ev_done[c], h->stream);
+        cudaStreamWaitEvent(h->copy_out, ev_done[c], 0);
+        if (col_end > cols_done) {
+            for (int ch = 0; ch < C; ++ch) {
+                const size_t off = ((size_t)ch * F + cols_done) * B, cnt = (size_t)(col_end - cols_done) * B;
+                if (index_host)
+                    cudaMemcpyAsync(index_host + off, idx_dev + off, cnt, cudaMemcpyDeviceToHost, h->copy_out);
+                if (grid_host)
+                    cudaMemcpyAsync(grid_host + off, grid_dev + off, cnt * sizeof(float),
+                                    cudaMemcpyDeviceToHost, h->copy_out);
+            }
+        }
+        cols_done = col_end;
+    }
+    cudaError_t e1 = cudaStreamSynchronize(h->copy_out);
+    cudaError_t e2 = cudaStreamSynchronize(h->stream);
+    cudaError_t e3 = cudaStreamSynchronize(h->copy_in);
+    cleanup();
+    if (rs != EMS_OK) return rs;
+    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess)
+        return fail(h, EMS_ERR_CUDA, "process_host: %s",
+                    cudaGetErrorString(e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3)));
+    return EMS_OK;
+}
+
+ems_status ems_stage_ms(ems_handle* h, int stage, float* ms) {
+    if (!h || !ms || stage < 0 || stage >= EMS_STAGE_COUNT) return EMS_ERR_INVALID_ARG;
+    if (!h->ev_valid[stage]) return fail(h, EMS_ERR_STATE, "stage %d did not run", stage);
+    EMS_CUDA(h, cudaEventSynchronize(h->ev[stage][1]));
+    EMS_CUDA(h, cudaEventElapsedTime(ms, h->ev[stage][0], h->ev[stage][1]));
+    return EMS_OK;
+}
+
+ems_status ems_launch_count(const ems_handle* h, uint64_t* n) {
+    if (!h || !n) return EMS_ERR_INVALID_ARG;
+    *n = h->launches;
+    return EMS_OK;
+}
+
+ems_status ems_stream_push(ems_handle* h, const float*, uint8_t*, int*, int64_t*) {
+    return fail(h, EMS_ERR_UNSUPPORTED, "streaming mode not built yet");
+}
+
+ems_status ems_stream_reset(ems_handle* h) {
+    return fail(h, EMS_ERR_UNSUPPORTED, "streaming mode not built yet");
+}
+
+}  // extern "C"

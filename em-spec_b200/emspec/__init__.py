@@ -1,0 +1,238 @@
+"""ctypes binding of include/emspec.h — used by the parity tests and bench.py.
+
+The product is libemspec.so (C-ABI, hand-written CUDA for sm_100a).  This module only
+marshals pointers: torch is used for device memory and streams, never for compute.
+There is no CPU path: if the library is missing or no CUDA device is present every
+entry point raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libemspec.so")
+
+FLAG_REASSIGN = 1
+FLAG_DETERMINISTIC = 2
+FLAG_SYNC = 4
+STAGE_POINTS, STAGE_SCATTER, STAGE_POST = 0, 1, 2
+
+OK, ERR_INVALID_ARG, ERR_UNSUPPORTED, ERR_CUDA, ERR_NOMEM, ERR_STATE = range(6)
+
+
+class EmspecError(RuntimeError):
+    def __init__(self, status: int, msg: str):
+        super().__init__(f"emspec status {status}: {msg}")
+        self.status = status
+
+
+class Params(C.Structure):
+    """ems_params (include/emspec.h); defaults = assets/settings.png "Default" preset."""
+    _fields_ = [
+        ("n_fft", C.c_int32), ("hop", C.c_int32), ("sample_rate", C.c_float),
+        ("channels", C.c_int32), ("db_range", C.c_float), ("gain", C.c_float),
+        ("low_end_boost", C.c_float), ("smoothing", C.c_float),
+        ("noise_gate_db", C.c_float), ("flags", C.c_uint32),
+    ]
+
+
+# name -> (restype, argtypes); every symbol include/emspec.h declares.
+_VP, _FP, _U8P = C.c_void_p, C.c_void_p, C.c_void_p
+_SIG = {
+    "ems_abi_version": (C.c_int, []),
+    "ems_status_str": (C.c_char_p, [C.c_int]),
+    "ems_last_error": (C.c_char_p, [_VP]),
+    "ems_default_params": (C.c_int, [C.POINTER(Params)]),
+    "ems_create": (C.c_int, [C.POINTER(Params), C.POINTER(_VP)]),
+    "ems_destroy": (C.c_int, [_VP]),
+    "ems_update_display": (C.c_int, [_VP, C.POINTER(Params)]),
+    "ems_set_stream": (C.c_int, [_VP, _VP]),
+    "ems_get_stream": (C.c_int, [_VP, C.POINTER(_VP)]),
+    "ems_synchronize": (C.c_int, [_VP]),
+    "ems_frame_count": (C.c_int, [_VP, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "ems_process_points": (C.c_int, [_VP, _FP, C.c_size_t, _FP, _FP, _FP, C.POINTER(C.c_size_t)]),
+    "ems_process_grid": (C.c_int, [_VP, _FP, C.c_size_t, _FP, _U8P, C.POINTER(C.c_size_t)]),
+    "ems_scatter_points": (C.c_int, [_VP, _FP, _FP, _FP, C.c_size_t, _FP, _U8P]),
+    "ems_process_host": (C.c_int, [_VP, _FP, C.c_size_t, _FP, _U8P, C.POINTER(C.c_size_t)]),
+    "ems_stage_ms": (C.c_int, [_VP, C.c_int, C.POINTER(C.c_float)]),
+    "ems_launch_count": (C.c_int, [_VP, C.POINTER(C.c_uint64)]),
+    "ems_stream_push": (C.c_int, [_VP, _FP, _U8P, C.POINTER(C.c_int), C.POINTER(C.c_int64)]),
+    "ems_stream_reset": (C.c_int, [_VP]),
+}
+SYMBOLS = tuple(_SIG)
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Loads libemspec.so; raises (loudly) when the CUDA extension has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing: build it with `python em-spec_b200/build_emspec.py` "
+                "(there is no CPU fallback)")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIG.items():
+            fn = getattr(lib, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = lib
+    return _lib
+
+
+def default_params() -> Params:
+    p = Params()
+    load().ems_default_params(C.byref(p))
+    return p
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class Engine:
+    """One ems_handle.  Tensors in / out are torch CUDA tensors (device memory only)."""
+
+    def __init__(self, **kw):
+        self.lib = load()
+        self.params = default_params()
+        for k, v in kw.items():
+            if not hasattr(self.params, k):
+                raise TypeError(f"unknown parameter {k}")
+            setattr(self.params, k, v)
+        self.h = C.c_void_p()
+        st = self.lib.ems_create(C.byref(self.params), C.byref(self.h))
+        if st != OK:
+            self.h = C.c_void_p()
+            raise EmspecError(st, self.lib.ems_status_str(st).decode())
+
+    # ------------------------------------------------------------------ plumbing
+    def _check(self, st: int):
+        if st != OK:
+            raise EmspecError(st, f"{self.lib.ems_status_str(st).decode()}: "
+                                  f"{self.lib.ems_last_error(self.h).decode()}")
+
+    def close(self):
+        if getattr(self, "h", None) and self.h.value:
+            self.lib.ems_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def n_bins(self) -> int:
+        return self.params.n_fft // 2 + 1
+
+    def frame_count(self, n_samples: int) -> int:
+        n = C.c_size_t()
+        self._check(self.lib.ems_frame_count(self.h, n_samples, C.byref(n)))
+        return n.value
+
+    def use_torch_stream(self):
+        """Run on torch's current stream so torch.cuda.Event timing and ordering apply."""
+        import torch
+        self._check(self.lib.ems_set_stream(self.h, C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+
+    def synchronize(self):
+        self._check(self.lib.ems_synchronize(self.h))
+
+    def update_display(self, **kw):
+        for k, v in kw.items():
+            setattr(self.params, k, v)
+        self._check(self.lib.ems_update_display(self.h, C.byref(self.params)))
+
+    def stage_ms(self, stage: int) -> float:
+        ms = C.c_float()
+        self._check(self.lib.ems_stage_ms(self.h, stage, C.byref(ms)))
+        return ms.value
+
+    def launch_count(self) -> int:
+        n = C.c_uint64()
+        self._check(self.lib.ems_launch_count(self.h, C.byref(n)))
+        return n.value
+
+    def _pcm(self, pcm):
+        import torch
+        if pcm.dim() == 1:
+            pcm = pcm[None, :]
+        assert pcm.is_cuda and pcm.dtype == torch.float32 and pcm.is_contiguous()
+        assert pcm.shape[0] == self.params.channels
+        return pcm
+
+    # ------------------------------------------------------------------ offline
+    def process_points(self, pcm, out=None):
+        """-> (dt_cols, dk_bins, energy) fp32 CUDA tensors [channels][F][B]."""
+        import torch
+        pcm = self._pcm(pcm)
+        S = pcm.shape[1]
+        F = self.frame_count(S)
+        shape = (self.params.channels, F, self.n_bins)
+        if out is None:
+            out = tuple(torch.empty(shape, dtype=torch.float32, device=pcm.device) for _ in range(3))
+        n = C.c_size_t()
+        self._check(self.lib.ems_process_points(self.h, _ptr(pcm), S, _ptr(out[0]), _ptr(out[1]),
+                                                _ptr(out[2]), C.byref(n)))
+        assert n.value == F
+        return out
+
+    def process_grid(self, pcm, want_grid=True, want_index=True, out=None):
+        """-> (grid fp32 | None, index u8 | None), CUDA tensors [channels][F][B]."""
+        import torch
+        pcm = self._pcm(pcm)
+        S = pcm.shape[1]
+        F = self.frame_count(S)
+        shape = (self.params.channels, F, self.n_bins)
+        if out is None:
+            grid = torch.empty(shape, dtype=torch.float32, device=pcm.device) if want_grid else None
+            idx = torch.empty(shape, dtype=torch.uint8, device=pcm.device) if want_index else None
+        else:
+            grid, idx = out
+        n = C.c_size_t()
+        self._check(self.lib.ems_process_grid(self.h, _ptr(pcm), S, _ptr(grid), _ptr(idx), C.byref(n)))
+        return grid, idx
+
+    def scatter_points(self, dt, dk, en, want_grid=True, want_index=True):
+        import torch
+        F = en.shape[-2]
+        shape = (self.params.channels, F, self.n_bins)
+        grid = torch.empty(shape, dtype=torch.float32, device=en.device) if want_grid else None
+        idx = torch.empty(shape, dtype=torch.uint8, device=en.device) if want_index else None
+        self._check(self.lib.ems_scatter_points(self.h, _ptr(dt), _ptr(dk), _ptr(en), F,
+                                                _ptr(grid), _ptr(idx)))
+        return grid, idx
+
+    def process_host(self, pcm_host, want_grid=False, index_out=None, grid_out=None):
+        """Host (CPU, ideally pinned) fp32 tensor [channels][S] -> (grid | None, index) CPU tensors."""
+        import torch
+        if pcm_host.dim() == 1:
+            pcm_host = pcm_host[None, :]
+        assert (not pcm_host.is_cuda) and pcm_host.dtype == torch.float32 and pcm_host.is_contiguous()
+        S = pcm_host.shape[1]
+        F = self.frame_count(S)
+        shape = (self.params.channels, F, self.n_bins)
+        pin = torch.cuda.is_available()
+        if index_out is None:
+            index_out = torch.empty(shape, dtype=torch.uint8, pin_memory=pin)
+        if want_grid and grid_out is None:
+            grid_out = torch.empty(shape, dtype=torch.float32, pin_memory=pin)
+        n = C.c_size_t()
+        self._check(self.lib.ems_process_host(self.h, _ptr(pcm_host), S, _ptr(grid_out),
+                                              _ptr(index_out), C.byref(n)))
+        return grid_out, index_out
+
+    # ------------------------------------------------------------------ streaming
+    def stream_reset(self):
+        self._check(self.lib.ems_stream_reset(self.h))
+
+    def stream_push(self, pcm_host, column_host):
+        """pcm_host: CPU fp32 [hop*channels] interleaved; column_host: CPU u8 [channels][B].
+        -> (ready: bool, column_index: int)"""
+        ready, idx = C.c_int(0), C.c_int64(-1)
+        self._check(self.lib.ems_stream_push(self.h, _ptr(pcm_host), _ptr(column_host),
+                                             C.byref(ready), C.byref(idx)))
+        return bool(ready.value), idx.value

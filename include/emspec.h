@@ -1,0 +1,149 @@
+/*
+ * emspec.h — C-ABI of the B200-native reassigned-spectrogram engine.
+ *
+ * STAND-IN BOUNDARY.  effree/EM-Spec exposes no plugin / operator / FFI interface:
+ * it is a GUI application whose source is private (/root/reference/README.md:73) and
+ * whose only documented control surface is the settings panel
+ * (/root/reference/README.md:41-51).  Each entry point below therefore cites the
+ * README control or feature it stands in for, not a reference function.
+ * SURVEY.md §8b is the contract this header implements.
+ *
+ * Conventions
+ *   - plain C symbols, POD structs, caller owns every buffer it passes in;
+ *   - every call returns ems_status (0 = OK); nothing throws or aborts across the ABI;
+ *   - one handle = one CUDA stream; a handle is not thread-safe, handles are independent;
+ *   - offline calls are asynchronous on the handle's stream unless EMS_FLAG_SYNC is set;
+ *   - "dev" pointers are CUDA device pointers on the handle's device, "host" pointers
+ *     are host memory (pinned memory makes the copies asynchronous);
+ *   - there is no CPU fallback: without a CUDA device ems_create fails with
+ *     EMS_ERR_CUDA.
+ *
+ * Geometry: N = n_fft, H = hop, B = N/2+1 bins,
+ *   F = 0 if S < N else 1 + (S-N)/H frames per channel for S samples per channel.
+ *   Frame f covers samples [f*H, f*H+N); column f of every output is centred there.
+ */
+#ifndef EMSPEC_H_
+#define EMSPEC_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EMS_ABI_VERSION 1
+
+typedef enum ems_status {
+    EMS_OK = 0,
+    EMS_ERR_INVALID_ARG = 1, /* null pointer, n_fft not a power of two in range, hop <= 0, ... */
+    EMS_ERR_UNSUPPORTED = 2, /* valid request this build cannot serve */
+    EMS_ERR_CUDA = 3,        /* CUDA runtime error (ems_last_error has the text) */
+    EMS_ERR_NOMEM = 4,       /* device or host allocation failed */
+    EMS_ERR_STATE = 5        /* call not valid in the handle's current state */
+} ems_status;
+
+/* flags */
+#define EMS_FLAG_REASSIGN      1u /* 1: reassigned ("Enhanced"), 0: plain |X_h|^2 columns ("Natural");
+                                     assets/settings.png buttons */
+#define EMS_FLAG_DETERMINISTIC 2u /* scatter accumulates in 64-bit fixed point: order-independent,
+                                     bit-exact across runs; 0: fp32 red.global.add fast mode */
+#define EMS_FLAG_SYNC          4u /* offline calls synchronise the stream before returning */
+
+/* Parameter surface = the README settings glossary (/root/reference/README.md:41-51);
+ * defaults in comments are the "Default" preset of assets/settings.png. */
+typedef struct ems_params {
+    int32_t  n_fft;         /* "FFT Size" README.md:43; power of two, 256..32768      (4096) */
+    int32_t  hop;           /* "Scroll Speed" README.md:44 maps to hop, 1..n_fft      (128)  */
+    float    sample_rate;   /* Hz                                                     (48000)*/
+    int32_t  channels;      /* planar channels per call, >= 1                         (1)    */
+    float    db_range;      /* "dB Range" README.md:46; floor = 0 dB - range          (58)   */
+    float    gain;          /* "Gain" README.md:47; linear amplitude                  (3.5)  */
+    float    low_end_boost; /* "Low-End Boost" README.md:49; weight at DC             (3.9)  */
+    float    smoothing;     /* "Smoothing" README.md:50; EMA coefficient in [0,1)     (0.0)  */
+    float    noise_gate_db; /* "Noise Gate" README.md:51; dB re full-scale sine       (-65)  */
+    uint32_t flags;         /* EMS_FLAG_*                                                     */
+} ems_params;
+
+typedef struct ems_handle ems_handle;
+
+/* Stage ids for ems_stage_ms (device time of the last offline call, CUDA events). */
+#define EMS_STAGE_POINTS  0 /* fused frame gather + 3-window STFT + reassignment (a1-a3) */
+#define EMS_STAGE_SCATTER 1 /* energy scatter onto the grid (a4) */
+#define EMS_STAGE_POST    2 /* dB / gate / boost / smoothing / colour index (a5) */
+#define EMS_STAGE_COUNT   3
+
+int         ems_abi_version(void);
+const char* ems_status_str(ems_status s);
+/* Text of the last error on this handle (never NULL). */
+const char* ems_last_error(const ems_handle* h);
+
+/* Fills *p with the settings.png "Default" preset. */
+ems_status ems_default_params(ems_params* p);
+
+/* Creates an engine on the current CUDA device.  Stands in for launching the app
+ * with a preset (/root/reference/README.md:35-38). */
+ems_status ems_create(const ems_params* params, ems_handle** out);
+ems_status ems_destroy(ems_handle* h);
+
+/* Live display controls (README.md:41 "changes are applied in real-time"): updates
+ * db_range, gain, low_end_boost, smoothing, noise_gate_db and flags; n_fft / hop /
+ * channels changes require a new handle (EMS_ERR_INVALID_ARG). */
+ems_status ems_update_display(ems_handle* h, const ems_params* params);
+
+/* Run on a caller-provided cudaStream_t instead of the handle's own stream. */
+ems_status ems_set_stream(ems_handle* h, void* cuda_stream);
+ems_status ems_get_stream(ems_handle* h, void** cuda_stream);
+ems_status ems_synchronize(ems_handle* h);
+
+/* F for n_samples_per_ch samples with this handle's n_fft / hop. */
+ems_status ems_frame_count(const ems_handle* h, size_t n_samples_per_ch, size_t* n_frames);
+
+/* a1-a3, "reassignment method" (/root/reference/README.md:3,11).
+ * pcm_dev: fp32 planar [channels][n_samples_per_ch].
+ * dt_cols, dk_bins, energy: fp32 [channels][F][B] each (device).  A point of frame f,
+ * bin k sits at column f + dt_cols, bin k + dk_bins with energy |X_h|^2 (4/N)^2.
+ * Dropped points (SURVEY.md §7 "Out-of-support points") carry energy 0, dt = dk = 0. */
+ems_status ems_process_points(ems_handle* h, const float* pcm_dev, size_t n_samples_per_ch,
+                              float* dt_cols, float* dk_bins, float* energy,
+                              size_t* n_frames);
+
+/* a1-a5: the picture the app draws (/root/reference/assets/spectrogram.png).
+ * grid_dev : fp32 [channels][F][B] accumulated energy, or NULL;
+ * index_dev: u8   [channels][F][B] colour index 0..255, or NULL (not both NULL). */
+ems_status ems_process_grid(ems_handle* h, const float* pcm_dev, size_t n_samples_per_ch,
+                            float* grid_dev, uint8_t* index_dev, size_t* n_frames);
+
+/* a4 + a5 from caller-held points (as written by ems_process_points, possibly edited):
+ * deposits energy > 0 points at (f + rint(dt_cols), k + rint(dk_bins)), then the
+ * post-pass.  All pointers are device pointers; grid_dev / index_dev as above. */
+ems_status ems_scatter_points(ems_handle* h, const float* dt_cols, const float* dk_bins,
+                              const float* energy, size_t n_frames,
+                              float* grid_dev, uint8_t* index_dev);
+
+/* Same as ems_process_grid with HOST buffers: chunks the stream, overlaps H2D, compute
+ * and D2H on two streams, and returns when index_host (and grid_host if not NULL) are
+ * complete.  Pinned buffers recommended.  This is the call an application makes. */
+ems_status ems_process_host(ems_handle* h, const float* pcm_host, size_t n_samples_per_ch,
+                            float* grid_host, uint8_t* index_host, size_t* n_frames);
+
+/* Device milliseconds of a stage of the last offline call on this handle (after the
+ * stream has been synchronised); EMS_ERR_STATE if that stage did not run. */
+ems_status ems_stage_ms(ems_handle* h, int stage, float* ms);
+/* Kernel launches issued by this handle since creation. */
+ems_status ems_launch_count(const ems_handle* h, uint64_t* launches);
+
+/* Streaming mode ("start visualizing your system audio", /root/reference/README.md:36).
+ * pcm_host: hop*channels fp32 samples, interleaved.  Once the ring holds n_fft samples
+ * every push analyses one new frame per channel.  A column is final R = ceil(n_fft/(2 hop))
+ * pushes after its own frame; then *column_ready = 1, column_host (u8 [channels][B], pinned
+ * recommended) holds it and *column_index (nullable) its frame index.  Synchronous. */
+ems_status ems_stream_push(ems_handle* h, const float* pcm_host, uint8_t* column_host,
+                           int* column_ready, int64_t* column_index);
+/* Clears the ring, the rolling grid and the smoothing state. */
+ems_status ems_stream_reset(ems_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EMSPEC_H_ */

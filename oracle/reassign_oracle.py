@@ -1,0 +1,226 @@
+"""STAND-IN ORACLE — float64 NumPy reassigned spectrogram.  TEST INFRASTRUCTURE ONLY.
+
+PARITY UNPINNED: effree/EM-Spec ships no source, no tests, no golden vectors
+(/root/reference/README.md:73 "The source code is maintained in a private
+repository").  Nothing here is EM-Spec's own output.  This file
+restates the *published* time-frequency reassignment method the README names
+(/root/reference/README.md:3,11 "reassignment method") from the literature:
+
+  * F. Auger, P. Flandrin, "Improving the readability of time-frequency and
+    time-scale representations by the reassignment method", IEEE TSP 43(5), 1995
+    (the operators  t^ = t - Re(X_th X_h*)/|X_h|^2,  w^ = w + Im(X_dh X_h*)/|X_h|^2);
+  * S. Fulop, K. Fitz, JASA 119(1), 2006 (discrete form).
+
+It is pinned instead by analytic known-answer tests (tests/test_oracle_kats.py:
+off-bin tone, unit impulse, linear chirp, energy conservation) — SURVEY.md §4.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+legs may import this module; the product path (em-spec_b200/) never does.
+
+Conventions (SURVEY.md §7 "Sign conventions", §8c):
+  frame m covers samples [m*H, m*H+N), centre m*H + N/2, no padding;
+  periodic Hann h[n] = 0.5 - 0.5 cos(2 pi n / N); th[n] = (n - N/2) h[n];
+  dh[n] = (pi/N) sin(2 pi n / N) (analytic derivative);
+  X_w[k] = sum_n x[mH+n] w[n] exp(-2 pi i k n / N), k = 0..N/2;
+  energy e = |X_h|^2 (4/N)^2   (a full-scale sine gives 0 dB);
+  dt [samples] = +Re(X_th conj X_h)/|X_h|^2   -> t^ [columns] = m + dt/H;
+  dk [bins]    = -Im(X_dh conj X_h)/|X_h|^2 * N/(2 pi) -> w^ [bins] = k + dk;
+  points are reported as displacements (dt/H columns, dk bins) from (m, k) so that
+  fp32 keeps full precision on hour-long streams;
+  a point is dropped (energy 0, zero displacement) when e <= gate, |dt| > N/2,
+  w^ outside [0, N/2], or m + rint(dt/H) outside [0, F-1];
+  nearest-cell deposit at (m + rint(dt/H), k + rint(dk)), round-half-even (np.rint / rintf).
+Display shaping (/root/reference/README.md:46-51): gain, low-end boost, smoothing,
+noise gate, dB range -> u8 colour index.  Semantics are stand-ins.
+"""
+from __future__ import annotations
+
+import dataclasses
+import math
+
+import numpy as np
+import scipy.fft
+
+LOW_END_CORNER_HZ = 200.0  # stand-in shape constant of the low-end boost weight
+TOP_DB = 0.0               # display ceiling; floor = TOP_DB - db_range
+
+FLAG_REASSIGN = 1          # 0: plain |X_h|^2 columns ("Natural"), 1: reassigned ("Enhanced")
+FLAG_DETERMINISTIC = 2     # no effect in the oracle (float64 sums in index order)
+FLAG_SYNC = 4              # no effect in the oracle
+
+
+@dataclasses.dataclass
+class Params:
+    """Mirror of `ems_params` (include/emspec.h).  Defaults = settings.png "Default" preset."""
+    n_fft: int = 4096            # README.md:43 "FFT Size"
+    hop: int = 128               # README.md:44 "Scroll Speed" maps to hop
+    sample_rate: float = 48000.0
+    channels: int = 1
+    db_range: float = 58.0       # README.md:46
+    gain: float = 3.5            # README.md:47 (linear amplitude)
+    low_end_boost: float = 3.9   # README.md:49
+    smoothing: float = 0.0       # README.md:50
+    noise_gate_db: float = -65.0 # README.md:51
+    flags: int = FLAG_REASSIGN | FLAG_DETERMINISTIC
+
+    @property
+    def n_bins(self) -> int:
+        return self.n_fft // 2 + 1
+
+    @property
+    def gate_lin(self) -> float:
+        return 10.0 ** (self.noise_gate_db / 10.0)
+
+
+def frame_count(n_samples: int, n_fft: int, hop: int) -> int:
+    """F = 1 + floor((S - N)/H), 0 when the stream is shorter than one frame."""
+    return 0 if n_samples < n_fft else 1 + (n_samples - n_fft) // hop
+
+
+def windows(n_fft: int):
+    """(h, th, dh) in float64, frame-local index n = 0..N-1."""
+    n = np.arange(n_fft, dtype=np.float64)
+    ang = 2.0 * np.pi * n / n_fft
+    h = 0.5 - 0.5 * np.cos(ang)
+    th = (n - n_fft / 2) * h
+    dh = (np.pi / n_fft) * np.sin(ang)
+    return h, th, dh
+
+
+def stft3(x: np.ndarray, n_fft: int, hop: int, m0: int, m1: int, workers: int = 1):
+    """X_h, X_th, X_dh for frames [m0, m1) -> three complex128 arrays [m1-m0, N/2+1]."""
+    h, th, dh = windows(n_fft)
+    idx = (np.arange(m0, m1)[:, None] * hop) + np.arange(n_fft)[None, :]
+    fr = np.asarray(x, dtype=np.float64)[idx]
+    Xh = scipy.fft.rfft(fr * h, axis=1, workers=workers)
+    Xth = scipy.fft.rfft(fr * th, axis=1, workers=workers)
+    Xdh = scipy.fft.rfft(fr * dh, axis=1, workers=workers)
+    return Xh, Xth, Xdh
+
+
+def reassign_operators(Xh, Xth, Xdh, n_fft: int):
+    """(energy, dt_samples, dk_bins) from the three STFTs; zero where |X_h| = 0."""
+    p = Xh.real * Xh.real + Xh.imag * Xh.imag
+    safe = np.where(p > 0.0, p, 1.0)
+    dt = (Xth.real * Xh.real + Xth.imag * Xh.imag) / safe
+    dk = -(Xdh.imag * Xh.real - Xdh.real * Xh.imag) / safe * (n_fft / (2.0 * np.pi))
+    e = p * (4.0 / n_fft) ** 2
+    dt = np.where(p > 0.0, dt, 0.0)
+    dk = np.where(p > 0.0, dk, 0.0)
+    return e, dt, dk
+
+
+def reassign_points(x: np.ndarray, prm: Params, chunk: int = 256, workers: int = 1,
+                    return_raw: bool = False):
+    """The a1..a3 path: fp64 points as [F][B] arrays (dt_cols, dk_bins, energy).
+
+    Same meaning as ems_process_points (include/emspec.h): the point of frame f, bin k
+    sits at column f + dt_cols, bin k + dk_bins.  Dropped points carry energy 0 and
+    zero displacement.  With return_raw=True also returns the un-gated energy (used
+    by the tests to band the coordinate tolerance by level).
+    """
+    N, H = prm.n_fft, prm.hop
+    x = np.asarray(x)
+    F = frame_count(x.shape[-1], N, H)
+    B = prm.n_bins
+    dcol = np.zeros((F, B), np.float64)
+    dbin = np.zeros((F, B), np.float64)
+    en = np.zeros((F, B), np.float64)
+    raw = np.empty((F, B), np.float64) if return_raw else None
+    k = np.arange(B, dtype=np.float64)[None, :]
+    gate = prm.gate_lin
+    for m0 in range(0, F, chunk):
+        m1 = min(F, m0 + chunk)
+        Xh, Xth, Xdh = stft3(x, N, H, m0, m1, workers)
+        e, dt, dk = reassign_operators(Xh, Xth, Xdh, N)
+        m = np.arange(m0, m1, dtype=np.float64)[:, None]
+        if raw is not None:
+            raw[m0:m1] = e
+        if prm.flags & FLAG_REASSIGN:
+            dc = dt / H
+            col = m + np.rint(dc)
+            wh = k + dk
+            ok = (e > gate) & (np.abs(dt) <= N / 2) & (wh >= 0.0) & (wh <= N / 2) \
+                 & (col >= 0) & (col <= F - 1)
+            dcol[m0:m1] = np.where(ok, dc, 0.0)
+            dbin[m0:m1] = np.where(ok, dk, 0.0)
+        else:
+            ok = e > gate
+        en[m0:m1] = np.where(ok, e, 0.0)
+    if return_raw:
+        return dcol, dbin, en, raw
+    return dcol, dbin, en
+
+
+def scatter_grid(dcol, dbin, energy) -> np.ndarray:
+    """a4: G[f + rint(dt_cols), k + rint(dk_bins)] += e over kept (e > 0) points; fp64 [F][B]."""
+    F, B = energy.shape
+    f, k = np.nonzero(energy > 0.0)
+    col = f + np.rint(dcol[f, k]).astype(np.int64)
+    row = k + np.rint(dbin[f, k]).astype(np.int64)
+    flat = np.bincount(col * B + row, weights=energy[f, k], minlength=F * B)
+    return flat.reshape(F, B)
+
+
+def low_end_weight(prm: Params) -> np.ndarray:
+    """w_low(k) = 1 + (boost-1)/(1 + (f_k/200 Hz)^2): `boost` at DC, -> 1 at high f."""
+    f = np.arange(prm.n_bins, dtype=np.float64) * prm.sample_rate / prm.n_fft
+    return 1.0 + (prm.low_end_boost - 1.0) / (1.0 + (f / LOW_END_CORNER_HZ) ** 2)
+
+
+def shaped_energy(grid: np.ndarray, prm: Params) -> np.ndarray:
+    """E = G gain^2 w_low(k), then the temporal EMA y[m] = s y[m-1] + (1-s) E[m], y[-1] = 0."""
+    E = grid * (prm.gain ** 2) * low_end_weight(prm)[None, :]
+    s = prm.smoothing
+    if s > 0.0:
+        y = np.empty_like(E)
+        acc = np.zeros(E.shape[1])
+        for m in range(E.shape[0]):
+            acc = s * acc + (1.0 - s) * E[m]
+            y[m] = acc
+        E = y
+    return E
+
+
+def postpass(grid: np.ndarray, prm: Params) -> np.ndarray:
+    """a5: shaped energy -> dB -> gate -> u8 colour index [F][B]."""
+    E = shaped_energy(grid, prm)
+    with np.errstate(divide="ignore"):
+        db = 10.0 * np.log10(E)
+    floor = TOP_DB - prm.db_range
+    v = np.rint(255.0 * (db - floor) / prm.db_range)
+    v = np.clip(v, 0.0, 255.0)
+    v = np.where((E > 0.0) & (db >= prm.noise_gate_db), v, 0.0)
+    return v.astype(np.uint8)
+
+
+def process(x: np.ndarray, prm: Params, workers: int = 1):
+    """Whole path for one channel: (grid fp64 [F][B], index u8 [F][B])."""
+    dcol, dbin, en = reassign_points(x, prm, workers=workers)
+    grid = scatter_grid(dcol, dbin, en)
+    return grid, postpass(grid, prm)
+
+
+# ---------------------------------------------------------------------------
+# Synthetic input: chirp + two tones + noise, float32 samples.
+# ---------------------------------------------------------------------------
+def synth_signal(n_samples: int, sample_rate: float = 48000.0, seed: int = 0,
+                 clip_index: int | None = None) -> np.ndarray:
+    """0.5*logchirp(20 Hz -> 20 kHz over the clip) + 0.25*sin(2 pi f1 t)
+    + 0.125*sin(2 pi f2 t) + 1e-3*N(0,1), cast to float32.
+    Single stream: f1 = 440, f2 = 3000.5.  Batch clips: f1 = 440 + 7*(i mod 64),
+    f2 = 3000.5 + 11*(i mod 128), seed = clip index."""
+    t = np.arange(n_samples, dtype=np.float64) / sample_rate
+    T = n_samples / sample_rate
+    f0, f1c = 20.0, 20000.0
+    r = math.log(f1c / f0)
+    phase = 2.0 * np.pi * f0 * T / r * np.expm1(r * t / T)
+    fa, fb = 440.0, 3000.5
+    if clip_index is not None:
+        fa += 7.0 * (clip_index % 64)
+        fb += 11.0 * (clip_index % 128)
+        seed = clip_index
+    rng = np.random.default_rng(seed)
+    x = 0.5 * np.sin(phase) + 0.25 * np.sin(2 * np.pi * fa * t) \
+        + 0.125 * np.sin(2 * np.pi * fb * t) + 1e-3 * rng.standard_normal(n_samples)
+    return x.astype(np.float32)

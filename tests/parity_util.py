@@ -1,0 +1,97 @@
+"""Shared parity checks: CUDA path (through the C-ABI) vs the float64 stand-in oracle.
+
+Tolerances are north_star's, made measurable as in SURVEY.md §8c:
+  coordinates: max error <= 1e-3 (columns / bins) over bins within 40 dB of the peak,
+               p99 error <= 1e-3 over bins above the noise gate;
+  energy     : <= 1e-4 relative L2 on the accumulated grid (and on the point energies);
+  validity   : kept/dropped decisions may differ only for points sitting on a threshold.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+import reassign_oracle as orc
+
+COORD_TOL = 1e-3
+ENERGY_TOL = 1e-4
+
+
+def rel_l2(a, b) -> float:
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    den = np.linalg.norm(b.ravel())
+    return float(np.linalg.norm((a - b).ravel()) / den) if den > 0 else float(np.linalg.norm(a.ravel()))
+
+
+def check_points(gpu_pts, x: np.ndarray, prm: orc.Params, hop_for_msg=None):
+    """gpu_pts: (dt, dk, e) numpy arrays [F][B] from the CUDA path for the same float32 x."""
+    dt_g, dk_g, e_g = (np.asarray(a, np.float64) for a in gpu_pts)
+    dt_o, dk_o, e_o, raw = orc.reassign_points(x, prm, return_raw=True)
+    assert dt_g.shape == dt_o.shape, (dt_g.shape, dt_o.shape)
+    assert np.isfinite(dt_g).all() and np.isfinite(dk_g).all() and np.isfinite(e_g).all()
+    both = (e_g > 0) & (e_o > 0)
+    n_valid = int((e_o > 0).sum())
+    # validity decisions: tolerate flips only on points hugging a threshold
+    flips = (e_g > 0) != (e_o > 0)
+    if flips.any():
+        gate = prm.gate_lin
+        N, H = prm.n_fft, prm.hop
+        Xh, Xth, Xdh = None, None, None
+        near_gate = np.abs(raw - gate) <= 1e-3 * gate
+        # displacement thresholds: recompute oracle's un-masked displacements where needed
+        f_idx, k_idx = np.nonzero(flips & ~near_gate)
+        bad = 0
+        for f, k in zip(f_idx, k_idx):
+            Xh, Xth, Xdh = orc.stft3(x, N, H, f, f + 1)
+            e, dts, dkb = orc.reassign_operators(Xh, Xth, Xdh, N)
+            dts, dkb = dts[0, k], dkb[0, k]
+            wh = k + dkb
+            dc = dts / H
+            edge = (abs(abs(dts) - N / 2) < 1e-2 or abs(wh) < 1e-3 or abs(wh - N / 2) < 1e-3
+                    or abs(dc - np.rint(dc)) > 0.5 - 2e-3)   # column rounding decides in/out of stream
+            bad += 0 if edge else 1
+        assert bad == 0, f"{bad} kept/dropped mismatches away from any threshold"
+        assert flips.sum() <= max(4, 1e-3 * n_valid), f"{flips.sum()} validity flips of {n_valid}"
+    if not both.any():
+        return dict(n_valid=n_valid)
+    peak = raw.max()
+    strong = both & (raw >= peak * 1e-4)          # within 40 dB of the peak
+    err_t = np.abs(dt_g - dt_o)
+    err_k = np.abs(dk_g - dk_o)
+    stats = dict(
+        n_valid=n_valid,
+        max_dt_strong=float(err_t[strong].max()) if strong.any() else 0.0,
+        max_dk_strong=float(err_k[strong].max()) if strong.any() else 0.0,
+        p99_dt=float(np.percentile(err_t[both], 99)),
+        p99_dk=float(np.percentile(err_k[both], 99)),
+        e_rel_l2=rel_l2(e_g[both], e_o[both]),
+    )
+    assert stats["max_dt_strong"] <= COORD_TOL, stats
+    assert stats["max_dk_strong"] <= COORD_TOL, stats
+    assert stats["p99_dt"] <= COORD_TOL, stats
+    assert stats["p99_dk"] <= COORD_TOL, stats
+    assert stats["e_rel_l2"] <= ENERGY_TOL, stats
+    return stats
+
+
+def check_grid(grid_gpu, x: np.ndarray, prm: orc.Params):
+    grid_o, idx_o = orc.process(x, prm)
+    err = rel_l2(grid_gpu, grid_o)
+    assert err <= ENERGY_TOL, f"grid rel-L2 {err}"
+    return err, grid_o, idx_o
+
+
+def check_index(idx_gpu, grid_o: np.ndarray, prm: orc.Params):
+    """u8 colour index: a quantised float -> +-1 at rounding boundaries, flips allowed only
+    for cells whose level sits on the gate."""
+    idx_o = orc.postpass(grid_o, prm)
+    E = orc.shaped_energy(grid_o, prm)
+    with np.errstate(divide="ignore"):
+        db = 10 * np.log10(E)
+    on_gate = np.abs(db - prm.noise_gate_db) < 1e-3
+    d = np.abs(idx_gpu.astype(np.int32) - idx_o.astype(np.int32))
+    d = np.where(on_gate, 0, d)
+    assert d.max() <= 1, f"colour index differs by {d.max()}"
+    frac = float((d > 0).mean())
+    assert frac <= 1e-3, f"{frac} of cells off by one"
+    return frac

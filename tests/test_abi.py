@@ -1,0 +1,80 @@
+"""CPU tests of the drop-in boundary: the C-ABI library builds for sm_100a, loads, and
+exports every symbol include/emspec.h declares.  No compute calls without a GPU."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "emspec.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(ems_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_header_symbols_all_exported(lib_built):
+    import emspec
+    lib = emspec.load()
+    syms = header_symbols()
+    assert len(syms) >= 18
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/emspec.h but not exported"
+    assert sorted(emspec.SYMBOLS) == syms, "binding and header disagree"
+
+
+def test_abi_version_and_status_strings(lib_built):
+    import emspec
+    lib = emspec.load()
+    assert lib.ems_abi_version() == 1
+    assert lib.ems_status_str(0) == b"ok"
+    for s in range(1, 6):
+        assert len(lib.ems_status_str(s)) > 0
+
+
+def test_default_params_are_the_settings_png_preset(lib_built):
+    import emspec
+    p = emspec.default_params()
+    assert (p.n_fft, p.hop, p.channels) == (4096, 128, 1)
+    assert abs(p.db_range - 58) < 1e-6 and abs(p.gain - 3.5) < 1e-6
+    assert abs(p.low_end_boost - 3.9) < 1e-6 and p.smoothing == 0 and p.noise_gate_db == -65
+    assert p.flags & emspec.FLAG_REASSIGN and p.flags & emspec.FLAG_DETERMINISTIC
+
+
+def test_invalid_arguments_rejected_before_any_cuda_call(lib_built):
+    import emspec
+    lib = emspec.load()
+    h = ctypes.c_void_p()
+    assert lib.ems_create(None, ctypes.byref(h)) == emspec.ERR_INVALID_ARG
+    for bad in (dict(n_fft=1000), dict(n_fft=128), dict(n_fft=65536), dict(hop=0),
+                dict(hop=8192), dict(channels=0), dict(smoothing=1.0), dict(db_range=0.0)):
+        p = emspec.default_params()
+        for k, v in bad.items():
+            setattr(p, k, v)
+        assert lib.ems_create(ctypes.byref(p), ctypes.byref(h)) == emspec.ERR_INVALID_ARG, bad
+    assert lib.ems_destroy(None) == emspec.ERR_INVALID_ARG
+    assert lib.ems_process_points(None, None, 0, None, None, None, None) == emspec.ERR_INVALID_ARG
+
+
+def test_no_cpu_fallback(lib_built):
+    """Without a CUDA device the engine refuses to exist; with one it must be created."""
+    import torch
+    import emspec
+    if torch.cuda.is_available():
+        emspec.Engine().close()
+    else:
+        with pytest.raises(emspec.EmspecError) as ei:
+            emspec.Engine()
+        assert ei.value.status == emspec.ERR_CUDA
+
+
+def test_product_never_imports_oracle():
+    """The oracle is test infrastructure: nothing under em-spec_b200/ may reference it."""
+    for dp, _, fs in os.walk(os.path.join(ROOT, "em-spec_b200")):
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                txt = open(os.path.join(dp, f)).read()
+                assert "import reassign_oracle" not in txt and "from reassign_oracle" not in txt, f
+                assert "oracle/" not in txt.replace("oracle/reassign_oracle.py", "").replace("oracle/reassign_oracle.py::", ""), f

@@ -1,0 +1,240 @@
+"""GPU parity tests: the CUDA path, called through the C-ABI (ctypes), against the float64
+stand-in oracle on the same float32 samples.  STAND-IN PARITY — not EM-Spec output
+(/root/reference/README.md:73)."""
+import os
+
+import numpy as np
+import pytest
+
+import reassign_oracle as orc
+from parity_util import check_grid, check_index, check_points, rel_l2
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+SR = 48000
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(scope="module")
+def emspec(lib_built):
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import emspec as m
+    m.load()
+    return m
+
+
+def run_points(m, x, prm, **kw):
+    eng = m.Engine(n_fft=prm.n_fft, hop=prm.hop, noise_gate_db=prm.noise_gate_db,
+                   flags=prm.flags | m.FLAG_SYNC, **kw)
+    pts = eng.process_points(torch.from_numpy(x).cuda())
+    out = tuple(p[0].cpu().numpy() for p in pts)
+    eng.close()
+    return out
+
+
+def run_grid(m, x, prm, want_grid=True):
+    eng = m.Engine(n_fft=prm.n_fft, hop=prm.hop, noise_gate_db=prm.noise_gate_db,
+                   db_range=prm.db_range, gain=prm.gain, low_end_boost=prm.low_end_boost,
+                   smoothing=prm.smoothing, sample_rate=prm.sample_rate,
+                   flags=prm.flags | m.FLAG_SYNC)
+    g, i = eng.process_grid(torch.from_numpy(x).cuda(), want_grid=want_grid)
+    eng.close()
+    return (g[0].cpu().numpy() if g is not None else None), i[0].cpu().numpy()
+
+
+@pytest.mark.parametrize("n_fft,hop,secs", [
+    (256, 64, 0.25), (512, 128, 0.5), (1024, 256, 0.5), (2048, 512, 2.0),   # configs[0] geometry
+    (4096, 128, 1.0), (4096, 256, 1.0), (8192, 256, 1.0), (16384, 4096, 2.0),
+    (4096, 1000, 0.5), (2048, 2048, 0.5),                                   # odd hop, hop = n_fft
+])
+def test_points_vs_oracle(emspec, n_fft, hop, secs):
+    x = orc.synth_signal(int(secs * SR), SR, seed=1)
+    prm = orc.Params(n_fft=n_fft, hop=hop)
+    stats = check_points(run_points(emspec, x, prm), x, prm)
+    assert stats["n_valid"] > 0
+
+
+def test_points_low_gate_many_valid(emspec):
+    """Gate at -120 dB keeps almost every bin: the p99 criterion over a dense point set."""
+    x = orc.synth_signal(SR // 2, SR, seed=2)
+    prm = orc.Params(n_fft=4096, hop=128, noise_gate_db=-100.0)
+    stats = check_points(run_points(emspec, x, prm), x, prm)
+    assert stats["n_valid"] > 100000
+
+
+def test_kat_tone_impulse_chirp(emspec):
+    """The analytic KATs of SURVEY.md §4 through the CUDA path."""
+    t = np.arange(SR) / SR
+    prm = orc.Params(n_fft=2048, hop=512, noise_gate_db=-200.0)
+    x = np.sin(2 * np.pi * 1000.37 * t).astype(np.float32)
+    dt, dk, e = run_points(emspec, x, prm)
+    k = int(np.argmax(e[10]))
+    assert abs((k + dk[10, k]) * SR / 2048 - 1000.37) < 2e-3          # wrong sign gives 1015.26
+    x = np.zeros(SR, np.float32)
+    m, pos = 5, 5 * 512 + 1024 + 300
+    x[pos] = 1.0
+    dt, dk, e = run_points(emspec, x, prm)
+    that = (m + dt[m, 100:900]) * 512 + 1024
+    assert np.abs(that - pos).max() < 0.05                             # wrong sign gives pos - 600
+    prm = orc.Params(n_fft=4096, hop=128, noise_gate_db=-200.0)
+    f0, f1 = 500.0, 8000.0
+    x = np.sin(2 * np.pi * (f0 * t + 0.5 * (f1 - f0) * t * t)).astype(np.float32)
+    dt, dk, e = run_points(emspec, x, prm)
+    m = 150
+    k = int(np.argmax(e[m]))
+    for kk in range(k - 3, k + 4):
+        tt = ((m + dt[m, kk]) * 128 + 2048) / SR
+        assert abs((kk + dk[m, kk]) * SR / 4096 - (f0 + (f1 - f0) * tt)) < 0.05
+
+
+def test_silence_dc_square_short(emspec):
+    prm = orc.Params(n_fft=1024, hop=256)
+    for x in (np.zeros(8192, np.float32), np.ones(8192, np.float32),
+              np.sign(np.sin(2 * np.pi * 997.0 * np.arange(8192) / SR)).astype(np.float32)):
+        pts = run_points(emspec, x, prm)
+        assert all(np.isfinite(p).all() for p in pts)
+        check_points(pts, x, prm)
+    dt, dk, e = run_points(emspec, np.zeros(8192, np.float32), prm)
+    assert e.max() == 0.0 and np.abs(dt).max() == 0.0
+    g, idx = run_grid(emspec, np.zeros(8192, np.float32), prm)
+    assert g.max() == 0.0 and idx.max() == 0
+    # shorter than one frame -> zero frames, no launch, no error
+    eng = emspec.Engine(n_fft=1024, hop=256)
+    assert eng.frame_count(1023) == 0 and eng.frame_count(1024) == 1 and eng.frame_count(1279) == 1
+    pts = eng.process_points(torch.zeros(1000, device="cuda"))
+    assert pts[0].shape == (1, 0, 513)
+    eng.close()
+
+
+def test_plain_mode(emspec):
+    """EMS_FLAG_REASSIGN off: plain |X_h|^2 columns, zero displacement."""
+    x = orc.synth_signal(SR // 2, SR, seed=3)
+    prm = orc.Params(n_fft=2048, hop=256, flags=orc.FLAG_DETERMINISTIC)
+    dt, dk, e = run_points(emspec, x, prm)
+    assert np.abs(dt).max() == 0 and np.abs(dk).max() == 0
+    check_points((dt, dk, e), x, prm)
+    g, _ = run_grid(emspec, x, prm)
+    check_grid(g, x, prm)
+
+
+@pytest.mark.parametrize("n_fft,hop", [(2048, 512), (4096, 128), (1024, 64)])
+def test_grid_and_index_vs_oracle(emspec, n_fft, hop):
+    x = orc.synth_signal(SR, SR, seed=4)
+    prm = orc.Params(n_fft=n_fft, hop=hop)
+    g, idx = run_grid(emspec, x, prm)
+    err, grid_o, _ = check_grid(g, x, prm)
+    check_index(idx, grid_o, prm)
+    # energy conservation: the grid holds exactly the kept point energy
+    dt, dk, e = run_points(emspec, x, prm)
+    assert abs(g.sum(dtype=np.float64) - e.sum(dtype=np.float64)) <= 1e-5 * e.sum(dtype=np.float64)
+
+
+def test_display_controls(emspec):
+    """configs[4]: low-end boost + smoothing + noise gate enabled."""
+    x = orc.synth_signal(SR, SR, seed=5)
+    prm = orc.Params(n_fft=2048, hop=512, low_end_boost=3.9, smoothing=0.5,
+                     noise_gate_db=-50.0, db_range=70.0, gain=2.0)
+    g, idx = run_grid(emspec, x, prm)
+    err, grid_o, _ = check_grid(g, x, prm)
+    check_index(idx, grid_o, prm)
+    prm.smoothing = 0.9     # long memory: exercises the chunk carries (F > 256 columns)
+    prm.hop = 64
+    g, idx = run_grid(emspec, x, prm)
+    err, grid_o, _ = check_grid(g, x, prm)
+    check_index(idx, grid_o, prm)
+
+
+def test_deterministic_and_fast_mode(emspec):
+    x = torch.from_numpy(orc.synth_signal(2 * SR, SR, seed=6)).cuda()
+    eng = emspec.Engine(n_fft=4096, hop=128, flags=emspec.FLAG_REASSIGN | emspec.FLAG_DETERMINISTIC | emspec.FLAG_SYNC)
+    runs = [eng.process_grid(x) for _ in range(3)]
+    for g, i in runs[1:]:
+        assert torch.equal(g, runs[0][0]) and torch.equal(i, runs[0][1])     # bit-exact
+    pts = eng.process_points(x)
+    g2, i2 = eng.scatter_points(*pts)                                         # a4 from stored points
+    assert torch.equal(g2, runs[0][0]) and torch.equal(i2, runs[0][1])
+    eng.close()
+    fast = emspec.Engine(n_fft=4096, hop=128, flags=emspec.FLAG_REASSIGN | emspec.FLAG_SYNC)
+    gf, _ = fast.process_grid(x)
+    fast.close()
+    assert rel_l2(gf.cpu().numpy(), runs[0][0].cpu().numpy()) < 1e-5
+
+
+def test_stereo_planar(emspec):
+    xl = orc.synth_signal(SR // 2, SR, seed=7)
+    xr = orc.synth_signal(SR // 2, SR, seed=8)
+    prm = orc.Params(n_fft=2048, hop=256)
+    eng = emspec.Engine(n_fft=2048, hop=256, channels=2, flags=prm.flags | emspec.FLAG_SYNC)
+    pcm = torch.from_numpy(np.stack([xl, xr])).cuda()
+    pts = eng.process_points(pcm)
+    g, idx = eng.process_grid(pcm)
+    eng.close()
+    for c, x in enumerate((xl, xr)):
+        check_points(tuple(p[c].cpu().numpy() for p in pts), x, prm)
+        check_grid(g[c].cpu().numpy(), x, prm)
+
+
+def test_process_host_matches_device(emspec):
+    """The HOST-buffer call (chunked, overlapped copies) equals the device-buffer call."""
+    x = orc.synth_signal(3 * SR, SR, seed=9)
+    eng = emspec.Engine(n_fft=1024, hop=32, smoothing=0.3, flags=emspec.FLAG_REASSIGN | emspec.FLAG_DETERMINISTIC | emspec.FLAG_SYNC)
+    g_dev, i_dev = eng.process_grid(torch.from_numpy(x).cuda())
+    g_host, i_host = eng.process_host(torch.from_numpy(x).pin_memory(), want_grid=True)
+    assert torch.equal(g_host, g_dev.cpu()) and torch.equal(i_host, i_dev.cpu())
+    eng.close()
+
+
+def test_golden_fixture(emspec):
+    """Committed fixture (tests/golden/make_golden.py): CUDA path vs stored oracle output."""
+    z = np.load(os.path.join(GOLD, "reassign_n512_h128.npz"))
+    prm = orc.Params(n_fft=int(z["n_fft"]), hop=int(z["hop"]), noise_gate_db=float(z["gate_db"]))
+    dt, dk, e = run_points(emspec, z["x"], prm)
+    keep = (z["energy"] > 0) & (e > 0)
+    assert keep.sum() >= 0.999 * (z["energy"] > 0).sum()
+    strong = keep & (z["raw"] >= z["raw"].max() * 1e-4)
+    assert np.abs(dt - z["dt_cols"])[strong].max() <= 1e-3
+    assert np.abs(dk - z["dk_bins"])[strong].max() <= 1e-3
+    g, idx = run_grid(emspec, z["x"], prm)
+    assert rel_l2(g, z["grid"]) <= 1e-4
+    d = np.abs(idx.astype(int) - z["index"].astype(int))
+    assert d.max() <= 1 and (d > 0).mean() <= 1e-3
+
+
+def test_long_stream_properties(emspec):
+    """Full-size geometry (n_fft=4096, hop=128) on a 2-minute stream: properties that do not
+    need the oracle — energy conservation, determinism, late frames equal to a shifted run."""
+    S = 120 * SR
+    g = torch.Generator(device="cuda").manual_seed(0)
+    t = torch.arange(S, device="cuda", dtype=torch.float64) / SR
+    x = (0.4 * torch.sin(2 * np.pi * (200.0 * t + 30.0 * t * t)) + 0.2 * torch.sin(2 * np.pi * 997.0 * t)).float()
+    x += 1e-3 * torch.randn(S, device="cuda", generator=g)
+    eng = emspec.Engine(n_fft=4096, hop=128, flags=emspec.FLAG_REASSIGN | emspec.FLAG_DETERMINISTIC | emspec.FLAG_SYNC)
+    dt, dk, e = eng.process_points(x)
+    grid, idx = eng.process_grid(x)
+    assert torch.isfinite(dt).all() and torch.isfinite(dk).all() and torch.isfinite(e).all()
+    assert dt.abs().max() <= 16.0 + 1e-3                      # |dt| <= N/2 samples = R columns
+    tot_p, tot_g = e.double().sum().item(), grid.double().sum().item()
+    assert abs(tot_p - tot_g) <= 1e-6 * tot_p
+    # shift invariance: frames of x[off*hop:] equal frames off.. of x (same samples, same kernel)
+    off = 40000
+    dt2, dk2, e2 = eng.process_points(x[off * 128:].contiguous())
+    F2 = e2.shape[1]
+    inner = slice(20, F2 - 20)     # away from both stream ends (column-in-stream rule)
+    assert torch.equal(e2[0, inner], e[0, off:off + F2][inner])
+    assert torch.equal(dt2[0, inner], dt[0, off:off + F2][inner])
+    # oracle on a late slice (absolute frame index ~ 40000: fp32 displacement form keeps precision)
+    sl = x[off * 128: off * 128 + 4096 + 128 * 63].cpu().numpy()
+    prm = orc.Params(n_fft=4096, hop=128)
+    o = orc.reassign_points(sl, prm)
+    a = tuple(v[0, off:off + 64].cpu().numpy() for v in (dt, dk, e))
+    both = (o[2] > 0) & (a[2] > 0)
+    col_ok = np.ones_like(both)
+    col_ok[:17] = False
+    col_ok[-17:] = False            # the slice's own stream ends differ from the long stream's
+    both &= col_ok
+    assert both.sum() > 100
+    assert np.percentile(np.abs(a[0] - o[0])[both], 99) <= 1e-3
+    assert np.percentile(np.abs(a[1] - o[1])[both], 99) <= 1e-3
+    eng.close()

@@ -1,0 +1,136 @@
+"""CPU tests pinning the float64 stand-in oracle by analytic known answers.
+STAND-IN: EM-Spec publishes no vectors (/root/reference/README.md:73); the KATs are
+mathematics of the reassignment method the README names (README.md:3,11)."""
+import os
+
+import numpy as np
+import pytest
+
+import reassign_oracle as orc
+
+SR = 48000
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def test_frame_count_edges():
+    assert orc.frame_count(0, 1024, 256) == 0
+    assert orc.frame_count(1023, 1024, 256) == 0
+    assert orc.frame_count(1024, 1024, 256) == 1
+    assert orc.frame_count(1279, 1024, 256) == 1
+    assert orc.frame_count(1280, 1024, 256) == 2
+    assert orc.frame_count(480000, 2048, 512) == 934          # configs[0]
+    assert orc.frame_count(172800000, 4096, 128) == 1349969   # configs[2]
+    assert orc.frame_count(2880000, 4096, 256) == 11235       # one clip of configs[3]
+
+
+def test_windows_definition():
+    h, th, dh = orc.windows(1024)
+    n = np.arange(1024)
+    assert h[0] == 0 and abs(h[512] - 1) < 1e-15
+    assert np.allclose(th, (n - 512) * h)
+    # analytic derivative vs a centred finite difference of the continuous Hann
+    eps = 1e-5
+    fd = (-0.5 * np.cos(2 * np.pi * (n + eps) / 1024) + 0.5 * np.cos(2 * np.pi * (n - eps) / 1024)) / (2 * eps)
+    assert np.allclose(dh, fd, atol=1e-9)
+
+
+def test_kat_offbin_tone_frequency_sign():
+    z = np.load(os.path.join(GOLD, "kats.npz"))
+    t = np.arange(SR) / SR
+    x = np.sin(2 * np.pi * float(z["tone_hz"]) * t)
+    prm = orc.Params(n_fft=2048, hop=512, noise_gate_db=-200)
+    dt, dk, e = orc.reassign_points(x, prm)
+    k = int(np.argmax(e[10]))
+    f_hat = (k + dk[10, k]) * SR / 2048
+    assert abs(f_hat - float(z["tone_hz"])) < 2e-3
+    assert abs(f_hat - float(z["tone_wrong_sign_hz"])) > 10          # the wrong sign lands here
+    assert abs(e[10, k] - 1.0) < 0.2                                   # ~0 dB for a full-scale sine
+
+
+def test_kat_impulse_time_sign():
+    z = np.load(os.path.join(GOLD, "kats.npz"))
+    prm = orc.Params(n_fft=2048, hop=512, noise_gate_db=-200)
+    x = np.zeros(SR)
+    m = 5
+    pos = m * 512 + 1024 + 300
+    assert pos == int(z["impulse_pos"])
+    x[pos] = 1.0
+    dt, dk, e = orc.reassign_points(x, prm)
+    that = (m + dt[m, 1:-1]) * 512 + 1024
+    assert np.abs(that - pos).max() < 1e-6
+    assert np.abs(dk[m, 1:-1]).max() < 1e-6
+    assert abs(int(z["impulse_wrong_sign"]) - (pos - 600)) == 0
+
+
+def test_kat_linear_chirp_on_if_line():
+    z = np.load(os.path.join(GOLD, "kats.npz"))
+    f0, f1 = float(z["chirp_f0"]), float(z["chirp_f1"])
+    t = np.arange(SR) / SR
+    x = np.sin(2 * np.pi * (f0 * t + 0.5 * (f1 - f0) * t * t))
+    prm = orc.Params(n_fft=4096, hop=128, noise_gate_db=-200)
+    dt, dk, e = orc.reassign_points(x, prm)
+    for m in (100, 150, 250):
+        k = int(np.argmax(e[m]))
+        for kk in range(k - 3, k + 4):
+            tt = ((m + dt[m, kk]) * 128 + 2048) / SR
+            assert abs((kk + dk[m, kk]) * SR / 4096 - (f0 + (f1 - f0) * tt)) < 1e-3
+
+
+def test_energy_conservation_and_drop_rule():
+    x = orc.synth_signal(SR, SR, seed=0)
+    prm = orc.Params(n_fft=2048, hop=512)
+    dt, dk, e = orc.reassign_points(x, prm)
+    grid = orc.scatter_grid(dt, dk, e)
+    assert abs(grid.sum() - e.sum()) < 1e-9 * e.sum()
+    assert (np.abs(dt) <= 2048 / 2 / 512 + 1e-12).all()
+    k = np.arange(1025)[None, :]
+    assert ((k + dk) >= 0).all() and ((k + dk) <= 1024).all()
+    assert (e[e > 0] > prm.gate_lin).all()
+    # dropped points are zeroed, not NaN
+    assert np.isfinite(dt).all() and np.isfinite(dk).all()
+
+
+def test_silence_dc_square():
+    prm = orc.Params(n_fft=1024, hop=256)
+    g, idx = orc.process(np.zeros(8192), prm)
+    assert g.max() == 0 and idx.max() == 0
+    for x in (np.ones(8192), np.sign(np.sin(2 * np.pi * 997.0 * np.arange(8192) / SR))):
+        g, idx = orc.process(x, prm)
+        assert np.isfinite(g).all()
+
+
+def test_postpass_controls():
+    prm = orc.Params(n_fft=512, hop=128, gain=1.0, low_end_boost=1.0, db_range=60.0, noise_gate_db=-50.0)
+    grid = np.zeros((4, 257))
+    grid[:, 10] = 1.0          # 0 dB -> 255
+    grid[:, 20] = 1e-3         # -30 dB -> 127.5 -> 128 (half-even on .5 -> 128)
+    grid[:, 30] = 1e-5 * 0.99  # below the -50 dB gate -> 0
+    grid[:, 40] = 1e-7         # below the floor -> 0
+    idx = orc.postpass(grid, prm)
+    assert idx[0, 10] == 255 and idx[0, 20] in (127, 128) and idx[0, 30] == 0 and idx[0, 40] == 0
+    w = orc.low_end_weight(orc.Params(n_fft=512, low_end_boost=3.9))
+    assert abs(w[0] - 3.9) < 1e-12 and abs(w[-1] - 1.0) < 1e-3 and (np.diff(w) <= 0).all()
+    # smoothing: EMA step response
+    prm.smoothing = 0.5
+    E = orc.shaped_energy(grid, prm)
+    assert np.allclose(E[:, 10], [0.5, 0.75, 0.875, 0.9375])
+
+
+def test_oracle_matches_golden_fixture():
+    z = np.load(os.path.join(GOLD, "reassign_n512_h128.npz"))
+    prm = orc.Params(n_fft=int(z["n_fft"]), hop=int(z["hop"]), noise_gate_db=float(z["gate_db"]))
+    dt, dk, e = orc.reassign_points(z["x"], prm)
+    assert np.allclose(dt, z["dt_cols"], atol=1e-5) and np.allclose(dk, z["dk_bins"], atol=1e-5)
+    assert np.allclose(e, z["energy"], rtol=1e-6, atol=1e-12)
+    grid, index = orc.process(z["x"], prm)
+    assert np.allclose(grid, z["grid"], rtol=1e-6, atol=1e-12)
+    assert (index == z["index"]).all()
+
+
+def test_synth_signal_is_deterministic():
+    a = orc.synth_signal(4800, SR, seed=0)
+    b = orc.synth_signal(4800, SR, seed=0)
+    assert a.dtype == np.float32 and (a == b).all()
+    assert np.abs(a).max() < 1.0
+    c = orc.synth_signal(4800, SR, clip_index=3)
+    assert not (a == c).all()
