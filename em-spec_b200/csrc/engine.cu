@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -13,6 +14,7 @@
 #include "common.cuh"
 #include "scatter_post.cuh"
 #include "stft_generic.cuh"
+#include "stft_r16.cuh"
 
 namespace ems {
 
@@ -41,6 +43,7 @@ struct ems_handle {
     cudaEvent_t ev[EMS_STAGE_COUNT][2]{};
     bool ev_valid[EMS_STAGE_COUNT]{};
     uint64_t launches = 0;
+    bool force_generic = false;         // EMS_FORCE_GENERIC=1: bypass the tuned kernels (A/B tests)
     char err[256] = "";
 };
 
@@ -125,7 +128,27 @@ static ems_status launch_generic(ems_handle* h, const StftArgs& a) {
     return EMS_OK;
 }
 
+// Tuned n_fft = 4096 kernel: persistent, one CTA per SM, 3 workers x 128 threads.
+static ems_status launch_r16(ems_handle* h, const StftArgs& a, int tile_T) {
+    const size_t smem = (size_t)r16::kFixedBytes + ((size_t)(tile_T - 1) * a.hop + r16::N) * sizeof(float);
+    auto kern = r16::stft_reassign_r16;
+    EMS_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, r16::kMaxSmem));
+    const long long per_ch = a.f_end - a.f_begin;
+    const long long n_tiles = ((per_ch + tile_T - 1) / tile_T) * a.channels;
+    long long grid = h->sm_count;
+    if (grid > n_tiles) grid = n_tiles;
+    if (grid < 1) return EMS_OK;
+    kern<<<(unsigned)grid, r16::kThreads, smem, h->stream>>>(a, tile_T);
+    ++h->launches;
+    EMS_CUDA(h, cudaGetLastError());
+    return EMS_OK;
+}
+
 static ems_status launch_stft(ems_handle* h, const StftArgs& a) {
+    if (h->prm.n_fft == 4096 && !h->force_generic) {
+        const int tile_T = r16::tile_frames(a.hop);
+        if (tile_T >= r16::kWorkers) return launch_r16(h, a, tile_T);
+    }
     switch (ilog2(h->prm.n_fft)) {
         case 8:  return launch_generic<8>(h, a);
         case 9:  return launch_generic<9>(h, a);
@@ -255,6 +278,7 @@ ems_status ems_create(const ems_params* params, ems_handle** out) {
     ems_handle* h = new (std::nothrow) ems_handle();
     if (!h) return EMS_ERR_NOMEM;
     h->prm = *params;
+    { const char* fg = getenv("EMS_FORCE_GENERIC"); h->force_generic = fg && fg[0] == '1'; }
     auto bail = [&](ems_status s) { ems_destroy(h); return s; };
     if (cudaGetDevice(&h->device) != cudaSuccess) return bail(EMS_ERR_CUDA);
     cudaDeviceProp prop{};
@@ -322,7 +346,7 @@ ems_status ems_update_display(ems_handle* h, const ems_params* p) {
 
 ems_status ems_set_stream(ems_handle* h, void* s) {
     if (!h) return EMS_ERR_INVALID_ARG;
-    h->stream = s ? (cudaStream_t)s : h->own_stream;
+    h->stream = (cudaStream_t)s;   // NULL is the CUDA default stream, taken literally
     return EMS_OK;
 }
 

@@ -1,0 +1,333 @@
+// stft_r16.cuh — tuned fused frame gather + 3-window STFT + reassignment for n_fft = 4096.
+//
+// Layout of the work (DESIGN.md "K1-K3"):
+//   * persistent CTAs, one per SM, 3 workers x 128 threads; a CTA walks tiles of T
+//     consecutive frames whose samples ((T-1)*hop + 4096 floats) sit once in shared memory;
+//   * a worker analyses one frame at a time, entirely on-chip:
+//       Z = FFT_4096(x*h + j*x*th')   as 16 x 16 x 16   (two radix-16 butterflies / thread / pass)
+//       Y = FFT_2048(w[2n] + j*w[2n+1]), w = x*dh'  as 16 x 16 x 8
+//     in-place decimation-in-frequency in the worker's private buffers, one named barrier
+//     per exchange (3 per frame); every access pattern is bank-conflict-free through the
+//     paddings padZ(a) = a + (a >> 8), padY(a) = a + (a >> 7)  (tools/bank_sim.py);
+//   * windows are not stored: cos/sin of the sample angle come from the thread's base
+//     angle rotated by compile-time constants;
+//   * the last pass is arranged so that thread p owns output residues t = p and 256 - p:
+//     Z[k], Z[N-k], Y[k], Y[N/2-k] of its 16 bins are then all in its own registers and the
+//     untangle + Auger-Flandrin epilogue needs no further exchange; X_h, X_th, X_dh never
+//     exist outside registers.  Residues 0 and 128 (self-paired, 17 bins) go through a
+//     48-entry scratch handled by 17 lanes of warp 0.
+// Semantics are identical to stft_generic.cuh (same reassign_emit).
+#pragma once
+#include "common.cuh"
+#include "stft_generic.cuh"
+
+#include <type_traits>
+#include <utility>
+
+namespace ems {
+namespace r16 {
+
+constexpr int N = 4096;
+constexpr int kWorkers = 3;
+constexpr int kWorkerThreads = 128;
+constexpr int kThreads = kWorkers * kWorkerThreads;
+constexpr int kZBuf = 4112;            // float2, padZ(4095) = 4110
+constexpr int kYBuf = 2064;            // float2, padY(2047) = 2062
+constexpr int kZtab = 15 * 256;        // W_4096^{b i}, i = 1..15, b < 256
+constexpr int kYtab = 15 * 128;        // W_2048^{b i}, b < 128
+constexpr int kT2 = 15 * 16;           // W_256^{p2 i}
+constexpr int kT2Y = 15 * 8;           // W_128^{p2 i}
+constexpr int kScratch = 48;           // thread-0 self-paired residues
+constexpr int kTabFloat2 = kZtab + kYtab + kT2 + kT2Y;
+constexpr int kFixedBytes = (kWorkers * (kZBuf + kYBuf + kScratch) + kTabFloat2) * 8;
+constexpr int kMaxSmem = 232448;       // 227 KB
+constexpr int kTileFloats = (kMaxSmem - kFixedBytes) / 4;
+
+__host__ __device__ constexpr int tile_frames(int hop) {
+    int t = (kTileFloats - N) / hop + 1;
+    t -= t % kWorkers;
+    return t > 36 ? 36 : t;
+}
+
+template <int... Is, class Fn>
+__device__ __forceinline__ void static_for_impl(std::integer_sequence<int, Is...>, Fn&& fn) {
+    (fn(std::integral_constant<int, Is>{}), ...);
+}
+// fn(integral_constant<int, 0>) ... fn(integral_constant<int, Count - 1>): loop indices usable
+// as template arguments and constexpr table indices
+template <int Count, class Fn>
+__device__ __forceinline__ void static_for(Fn&& fn) {
+    static_for_impl(std::make_integer_sequence<int, Count>{}, fn);
+}
+
+__device__ __forceinline__ float2 operator+(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 operator-(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+
+// forward DFT-4 in place: (x0, x1, x2, x3) <- outputs 0..3
+__device__ __forceinline__ void dft4(float2& x0, float2& x1, float2& x2, float2& x3) {
+    const float2 s02 = x0 + x2, d02 = x0 - x2, s13 = x1 + x3, d13 = x1 - x3;
+    x0 = s02 + s13;
+    x2 = s02 - s13;
+    x1 = make_float2(d02.x + d13.y, d02.y - d13.x);
+    x3 = make_float2(d02.x - d13.y, d02.y + d13.x);
+}
+
+// multiply by W16^E = exp(-2 pi j E / 16), E compile-time
+template <int E>
+__device__ __forceinline__ float2 mul_w16(float2 v) {
+    constexpr float C1 = 0.92387953251128674f, S1 = 0.38268343236508977f, R = 0.70710678118654752f;
+    constexpr int e = E & 15;
+    if constexpr (e == 0) return v;
+    else if constexpr (e == 4) return make_float2(v.y, -v.x);
+    else if constexpr (e == 8) return make_float2(-v.x, -v.y);
+    else if constexpr (e == 12) return make_float2(-v.y, v.x);
+    else if constexpr (e == 2) return make_float2((v.x + v.y) * R, (v.y - v.x) * R);
+    else if constexpr (e == 6) return make_float2((v.y - v.x) * R, -(v.x + v.y) * R);
+    else if constexpr (e == 10) return make_float2(-(v.x + v.y) * R, (v.x - v.y) * R);
+    else if constexpr (e == 14) return make_float2((v.x - v.y) * R, (v.x + v.y) * R);
+    else {
+        // (c, -s) with c = cos(2 pi e/16), s = sin(2 pi e/16)
+        constexpr float c = (e == 1 || e == 15) ? C1 : (e == 3 || e == 13) ? S1
+                          : (e == 5 || e == 11) ? -S1 : -C1;               // e == 7, 9
+        constexpr float s = (e == 1 || e == 7) ? S1 : (e == 3 || e == 5) ? C1
+                          : (e == 9 || e == 15) ? -S1 : -C1;               // e == 11, 13
+        return make_float2(v.x * c + v.y * s, v.y * c - v.x * s);
+    }
+}
+
+// forward DFT-16 in registers.  Output i sits in a[o16(i)].
+__host__ __device__ constexpr int o16(int i) { return 4 * (i & 3) + (i >> 2); }
+
+__device__ __forceinline__ void dft16(float2 (&a)[16]) {
+#pragma unroll
+    for (int j0 = 0; j0 < 4; ++j0) dft4(a[j0], a[j0 + 4], a[j0 + 8], a[j0 + 12]);
+    // a[j0 + 4 i0] *= W16^{i0 j0}
+    a[5] = mul_w16<1>(a[5]);   a[9] = mul_w16<2>(a[9]);   a[13] = mul_w16<3>(a[13]);
+    a[6] = mul_w16<2>(a[6]);   a[10] = mul_w16<4>(a[10]); a[14] = mul_w16<6>(a[14]);
+    a[7] = mul_w16<3>(a[7]);   a[11] = mul_w16<6>(a[11]); a[15] = mul_w16<9>(a[15]);
+#pragma unroll
+    for (int i0 = 0; i0 < 4; ++i0) dft4(a[4 * i0], a[4 * i0 + 1], a[4 * i0 + 2], a[4 * i0 + 3]);
+}
+
+// forward DFT-8 in registers.  Output i sits in a[o8(i)].
+__host__ __device__ constexpr int o8(int i) { return 2 * (i & 3) + (i >> 2); }
+
+__device__ __forceinline__ void dft8(float2 (&a)[8]) {
+    dft4(a[0], a[2], a[4], a[6]);
+    dft4(a[1], a[3], a[5], a[7]);
+    // a[j0 + 2 i0]: the odd half takes W8^{i0} = W16^{2 i0}
+    a[3] = mul_w16<2>(a[3]); a[5] = mul_w16<4>(a[5]); a[7] = mul_w16<6>(a[7]);
+#pragma unroll
+    for (int i0 = 0; i0 < 4; ++i0) {
+        const float2 u0 = a[2 * i0], u1 = a[2 * i0 + 1];
+        a[2 * i0] = u0 + u1;
+        a[2 * i0 + 1] = u0 - u1;
+    }
+}
+
+__device__ __forceinline__ void worker_bar(int w) {
+    asm volatile("bar.sync %0, %1;" ::"r"(w + 1), "r"(kWorkerThreads) : "memory");
+}
+
+// cos(q pi/16), sin(q pi/16) for compile-time q
+__host__ __device__ constexpr float c32(int q) {
+    constexpr float t[32] = {
+        1.0f, 0.98078528040323043f, 0.92387953251128674f, 0.83146961230254524f, 0.70710678118654752f,
+        0.55557023301960218f, 0.38268343236508977f, 0.19509032201612825f, 0.0f, -0.19509032201612825f,
+        -0.38268343236508977f, -0.55557023301960218f, -0.70710678118654752f, -0.83146961230254524f,
+        -0.92387953251128674f, -0.98078528040323043f, -1.0f, -0.98078528040323043f,
+        -0.92387953251128674f, -0.83146961230254524f, -0.70710678118654752f, -0.55557023301960218f,
+        -0.38268343236508977f, -0.19509032201612825f, 0.0f, 0.19509032201612825f, 0.38268343236508977f,
+        0.55557023301960218f, 0.70710678118654752f, 0.83146961230254524f, 0.92387953251128674f,
+        0.98078528040323043f};
+    return t[q & 31];
+}
+__host__ __device__ constexpr float s32(int q) { return c32(q - 8); }   // sin(q pi/16) = cos(q pi/16 - pi/2)
+
+// One bin of the epilogue: untangle the packed spectra and emit.
+//   zk = Z[k], zn = Z[N-k], yk = Y[k mod N/2], yn = Y[(N/2-k) mod N/2], w = W_N^k
+__device__ __forceinline__ void bin_emit(const StftArgs& a, long long chan_off, long long f, int k,
+                                         float2 zk, float2 zn, float2 yk, float2 yn, float2 w) {
+    const float2 A2 = make_float2(zk.x + zn.x, zk.y - zn.y);
+    const float2 B2 = make_float2(zk.y + zn.y, zn.x - zk.x);
+    const float2 E2 = make_float2(yk.x + yn.x, yk.y - yn.y);
+    const float2 O2 = make_float2(yk.y + yn.y, yn.x - yk.x);
+    const float2 D2 = make_float2(E2.x + (w.x * O2.x - w.y * O2.y), E2.y + (w.x * O2.y + w.y * O2.x));
+    reassign_emit<N>(a, chan_off, f, k, A2, B2, D2);
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+stft_reassign_r16(const StftArgs a, const int tile_T) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* sm = reinterpret_cast<float2*>(smem_raw);
+    float2* Ztab = sm;                         // [15][256]
+    float2* Ytab = Ztab + kZtab;               // [15][128]
+    float2* T2 = Ytab + kYtab;                 // [15][16]
+    float2* T2Y = T2 + kT2;                    // [15][8]
+    float2* wbuf = T2Y + kT2Y;                 // per worker: Z, Y, scratch
+    float* tile = reinterpret_cast<float*>(wbuf + kWorkers * (kZBuf + kYBuf + kScratch));
+
+    const int tid = threadIdx.x;
+    const int w = tid >> 7;                    // worker
+    const int p = tid & 127;                   // thread in worker
+    float2* Zb = wbuf + w * (kZBuf + kYBuf + kScratch);
+    float2* Yb = Zb + kZBuf;
+    float2* Sc = Yb + kYBuf;
+
+    // ---- twiddle tables (once per CTA)
+    for (int e = tid; e < kZtab; e += kThreads) { const int i = e / 256 + 1, b = e % 256; Ztab[e] = __ldg(&a.tw[b * i]); }
+    for (int e = tid; e < kYtab; e += kThreads) { const int i = e / 128 + 1, b = e % 128; Ytab[e] = __ldg(&a.tw[2 * b * i]); }
+    for (int e = tid; e < kT2; e += kThreads) { const int i = e / 16 + 1, q = e % 16; T2[e] = __ldg(&a.tw[16 * q * i]); }
+    for (int e = tid; e < kT2Y; e += kThreads) { const int i = e / 8 + 1, q = e % 8; T2Y[e] = __ldg(&a.tw[32 * q * i]); }
+
+    // ---- per-thread constants
+    const float2 twp = __ldg(&a.tw[p]);                    // (cos, -sin)(2 pi p / 4096)
+    const float cp = twp.x, sp = -twp.y;
+    const float rp = (float)(p - N / 2) * (1.0f / (N / 2)); // ramp of th' at n = p
+    const int tA = p, tB = p ? 256 - p : 128;              // output residues of this thread
+    const float2 wA = twp;                                  // W_N^{tA}
+    const float2 wB = __ldg(&a.tw[tB]);                     // W_N^{tB}
+    const int zA = 257 * (tA & 15) + 16 * (tA >> 4), zB = 257 * (tB & 15) + 16 * (tB >> 4);
+    const int yA = 129 * (tA & 15) + 8 * (tA >> 4), yB = 129 * (tB & 15) + 8 * (tB >> 4);
+    const int i1 = p & 15, q2 = p >> 4;                    // pass-2 butterfly coordinates
+
+    const long long per_ch = a.f_end - a.f_begin;
+    const long long tiles_per_ch = (per_ch + tile_T - 1) / tile_T;
+    const long long n_tiles = tiles_per_ch * a.channels;
+    const bool hop_even = (a.hop & 1) == 0;
+
+    for (long long tl = blockIdx.x; tl < n_tiles; tl += gridDim.x) {
+        const int ch = (int)(tl / tiles_per_ch);
+        const long long f0 = a.f_begin + (tl - (long long)ch * tiles_per_ch) * tile_T;
+        const int nf = (int)min((long long)tile_T, a.f_end - f0);
+        const int n_samp = (nf - 1) * a.hop + N;
+        const float* src = a.pcm + (long long)ch * a.S + f0 * a.hop;
+        __syncthreads();                                    // previous tile fully consumed
+        for (int s = tid; s < n_samp; s += kThreads) tile[s] = __ldg(src + s);
+        __syncthreads();
+        const long long chan_off = (long long)ch * a.F;
+
+        for (int fi = w; fi < nf; fi += kWorkers) {
+            const float* xs = tile + fi * a.hop;
+            const long long f = f0 + fi;
+
+            // ================= pass 1 of Z: butterflies b = p, p + 128
+            static_for<2>([&](auto uc) {
+                constexpr int u = decltype(uc)::value;
+                const int b = p + 128 * u;
+                float2 v[16];
+                static_for<16>([&](auto jc) {
+                    constexpr int j = decltype(jc)::value;
+                    constexpr int q = u + 2 * j;                           // n = p + 128 q
+                    constexpr float cq = c32(q), sq = s32(q), rq = (float)q * (1.0f / 16.0f);
+                    const float x = xs[b + 256 * j];
+                    const float cs = cp * cq - sp * sq;                    // cos(2 pi n / N)
+                    const float h = 0.5f - 0.5f * cs;
+                    const float re = x * h;
+                    v[j] = make_float2(re, re * (rp + rq));
+                });
+                dft16(v);
+                Zb[b] = v[o16(0)];
+#pragma unroll
+                for (int i = 1; i < 16; ++i) Zb[b + 257 * i] = cmul(v[o16(i)], Ztab[(i - 1) * 256 + b]);
+            });
+            // ================= pass 1 of Y: butterfly b = p on w = x * sin(2 pi n / N)
+            {
+                const float c2 = cp * cp - sp * sp, s2 = 2.0f * sp * cp;   // angle of sample 2p
+                constexpr float cd = 0.99999882345170188f, sd = 0.0015339801862847655f;   // 2 pi / 4096
+                float2 v[16];
+                static_for<16>([&](auto jc) {
+                    constexpr int j = decltype(jc)::value;
+                    constexpr float cq = c32(2 * j), sq = s32(2 * j);
+                    float x0, x1;
+                    if (hop_even) {
+                        const float2 xx = *reinterpret_cast<const float2*>(xs + 2 * p + 256 * j);
+                        x0 = xx.x; x1 = xx.y;
+                    } else {
+                        x0 = xs[2 * p + 256 * j]; x1 = xs[2 * p + 256 * j + 1];
+                    }
+                    const float se = s2 * cq + c2 * sq;
+                    const float ce = c2 * cq - s2 * sq;
+                    v[j] = make_float2(x0 * se, x1 * (se * cd + ce * sd));
+                });
+                dft16(v);
+                Yb[p] = v[o16(0)];
+#pragma unroll
+                for (int i = 1; i < 16; ++i) Yb[p + 129 * i] = cmul(v[o16(i)], Ytab[(i - 1) * 128 + p]);
+            }
+            worker_bar(w);
+
+            // ================= pass 2 of Z: sub-FFTs of length 256, butterflies (i1, q2 + 8u)
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int p2 = q2 + 8 * u;
+                float2* base = Zb + 257 * i1 + p2;
+                float2 v[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = base[16 * j];
+                dft16(v);
+                base[0] = v[o16(0)];
+#pragma unroll
+                for (int i = 1; i < 16; ++i) base[16 * i] = cmul(v[o16(i)], T2[(i - 1) * 16 + p2]);
+            }
+            // ================= pass 2 of Y: sub-FFTs of length 128, butterfly (i1, q2)
+            {
+                float2* base = Yb + 129 * i1 + q2;
+                float2 v[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = base[8 * j];
+                dft16(v);
+                base[0] = v[o16(0)];
+#pragma unroll
+                for (int i = 1; i < 16; ++i) base[8 * i] = cmul(v[o16(i)], T2Y[(i - 1) * 8 + q2]);
+            }
+            worker_bar(w);
+
+            // ================= pass 3: residues tA, tB of Y (radix 8) and Z (radix 16)
+            float2 ya[8], yb[8], za[16], zb[16];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { ya[j] = Yb[yA + j]; yb[j] = Yb[yB + j]; }
+            dft8(ya); dft8(yb);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) { za[j] = Zb[zA + j]; zb[j] = Zb[zB + j]; }
+            dft16(za); dft16(zb);
+
+            if (p != 0) {
+                // bins tA + 256 c and tB + 256 c, c = 0..7
+                static_for<8>([&](auto cc) {
+                    constexpr int c = decltype(cc)::value;
+                    bin_emit(a, chan_off, f, tA + 256 * c, za[o16(c)], zb[o16(15 - c)], ya[o8(c)],
+                             yb[o8(7 - c)], mul_w16<c>(wA));
+                    bin_emit(a, chan_off, f, tB + 256 * c, zb[o16(c)], za[o16(15 - c)], yb[o8(c)],
+                             ya[o8(7 - c)], mul_w16<c>(wB));
+                });
+            } else {
+                // residues 0 and 128 pair with themselves: 17 bins via scratch
+#pragma unroll
+                for (int c = 0; c < 16; ++c) { Sc[c] = za[o16(c)]; Sc[16 + c] = zb[o16(c)]; }
+#pragma unroll
+                for (int c = 0; c < 8; ++c) { Sc[32 + c] = ya[o8(c)]; Sc[40 + c] = yb[o8(c)]; }
+            }
+            if (p < 32) {
+                __syncwarp();
+                if (p <= 16) {
+                    int k;
+                    float2 zk, zn, yk, yn;
+                    if (p <= 8) {
+                        k = 256 * p;
+                        zk = Sc[p]; zn = Sc[(16 - p) & 15]; yk = Sc[32 + (p & 7)]; yn = Sc[32 + ((8 - p) & 7)];
+                    } else {
+                        const int c = p - 9;
+                        k = 128 + 256 * c;
+                        zk = Sc[16 + c]; zn = Sc[16 + 15 - c]; yk = Sc[40 + c]; yn = Sc[40 + 7 - c];
+                    }
+                    bin_emit(a, chan_off, f, k, zk, zn, yk, yn, __ldg(&a.tw[k]));
+                }
+            }
+            worker_bar(w);      // pass-3 reads done before the next frame's pass-1 writes
+        }
+    }
+}
+
+}  // namespace r16
+}  // namespace ems

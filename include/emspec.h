@@ -91,7 +91,8 @@ ems_status ems_destroy(ems_handle* h);
  * channels changes require a new handle (EMS_ERR_INVALID_ARG). */
 ems_status ems_update_display(ems_handle* h, const ems_params* params);
 
-/* Run on a caller-provided cudaStream_t instead of the handle's own stream. */
+/* Run on a caller-provided cudaStream_t instead of the handle's own stream
+ * (NULL = the CUDA default stream). */
 ems_status ems_set_stream(ems_handle* h, void* cuda_stream);
 ems_status ems_get_stream(ems_handle* h, void** cuda_stream);
 ems_status ems_synchronize(ems_handle* h);
