@@ -144,18 +144,70 @@ __host__ __device__ constexpr float c32(int q) {
 }
 __host__ __device__ constexpr float s32(int q) { return c32(q - 8); }   // sin(q pi/16) = cos(q pi/16 - pi/2)
 
-// One bin of the epilogue: untangle the packed spectra and emit.
-//   zk = Z[k], zn = Z[N-k], yk = Y[k mod N/2], yn = Y[(N/2-k) mod N/2], w = W_N^k
-__device__ __forceinline__ void bin_emit(const StftArgs& a, long long chan_off, long long f, int k,
-                                         float2 zk, float2 zn, float2 yk, float2 yn, float2 w) {
-    const float2 A2 = make_float2(zk.x + zn.x, zk.y - zn.y);
-    const float2 B2 = make_float2(zk.y + zn.y, zn.x - zk.x);
-    const float2 E2 = make_float2(yk.x + yn.x, yk.y - yn.y);
-    const float2 O2 = make_float2(yk.y + yn.y, yn.x - yk.x);
-    const float2 D2 = make_float2(E2.x + (w.x * O2.x - w.y * O2.y), E2.y + (w.x * O2.y + w.y * O2.x));
-    reassign_emit<N>(a, chan_off, f, k, A2, B2, D2);
+// Per-frame constants of the epilogue.
+struct FrameCtx {
+    float lo, hi;        // bounds on rint(dt_cols) keeping the column inside [0, F-1]
+    float* pd;           // row (chan, f) of dt_cols / dk_bins / energy (store mode)
+    float* pk;
+    float* pe;
+    long long acc_row;   // (chan*F + f) * B   (deposit modes)
+};
+
+__device__ __forceinline__ float rcp_approx(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
 }
 
+// One bin of the epilogue: untangle the packed spectra, apply the Auger-Flandrin operators
+// and emit — same decisions as reassign_emit (stft_generic.cuh), arranged to be cheap:
+// a whole warp under the gate leaves after 8 instructions, everything else is predicated.
+//   zk = Z[k], zn = Z[N-k], yk = Y[k mod N/2], yn = Y[(N/2-k) mod N/2], w = W_N^k
+// Must be reached by all 32 lanes of the warp (`owner` masks lanes that only tag along).
+template <int MODE>
+__device__ __forceinline__ void bin_emit(const StftArgs& a, const FrameCtx& fc, bool owner, int k,
+                                         float kf, float2 zk, float2 zn, float2 yk, float2 yn,
+                                         float2 w) {
+    constexpr int B = N / 2 + 1;
+    const float2 A2 = make_float2(zk.x + zn.x, zk.y - zn.y);           // 2 X_h
+    const float p2 = A2.x * A2.x + A2.y * A2.y;
+    const float e = p2 * (float)(4.0 / ((double)N * (double)N));
+    const bool live = e > a.gate_lin;
+    if (!__any_sync(0xffffffffu, live)) {
+        if (MODE == kStorePoints && owner) { fc.pd[k] = 0.f; fc.pk[k] = 0.f; fc.pe[k] = 0.f; }
+        return;
+    }
+    bool ok = live;
+    float dtc = 0.f, dk = 0.f, rc = 0.f;
+    if (a.reassign) {
+        const float2 B2 = make_float2(zk.y + zn.y, zn.x - zk.x);       // 2 X_th'
+        const float2 E2 = make_float2(yk.x + yn.x, yk.y - yn.y);
+        const float2 O2 = make_float2(yk.y + yn.y, yn.x - yk.x);
+        const float2 D2 = make_float2(E2.x + (w.x * O2.x - w.y * O2.y),
+                                      E2.y + (w.x * O2.y + w.y * O2.x));   // 2 X_dh'
+        const float inv = rcp_approx(p2);
+        const float dts = (B2.x * A2.x + B2.y * A2.y) * inv * (float)(N / 2);   // samples
+        dk = (D2.y * A2.x - D2.x * A2.y) * inv * -0.5f;                          // bins
+        dtc = dts * a.inv_hop;
+        rc = rintf(dtc);
+        const float wh = kf + dk;
+        ok = live && (fabsf(dts) <= (float)(N / 2)) && (wh >= 0.f) && (wh <= (float)(N / 2)) &&
+             (rc >= fc.lo) && (rc <= fc.hi);
+        dtc = ok ? dtc : 0.f;
+        dk = ok ? dk : 0.f;
+    }
+    if (MODE == kStorePoints) {
+        if (owner) { fc.pd[k] = dtc; fc.pk[k] = dk; fc.pe[k] = ok ? e : 0.f; }
+    } else if (ok && owner) {
+        const long long o = fc.acc_row + (long long)((int)rc * B + k + (int)rintf(dk));
+        if (MODE == kDepositU64)
+            atomicAdd(reinterpret_cast<unsigned long long*>(a.acc) + o, __float2ull_rn(e * kFixScale));
+        else
+            atomicAdd(reinterpret_cast<float*>(a.acc) + o, e);
+    }
+}
+
+template <int MODE>
 __global__ void __launch_bounds__(kThreads, 1)
 stft_reassign_r16(const StftArgs a, const int tile_T) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -169,7 +221,9 @@ stft_reassign_r16(const StftArgs a, const int tile_T) {
 
     const int tid = threadIdx.x;
     const int w = tid >> 7;                    // worker
-    const int p = tid & 127;                   // thread in worker
+    // role of this thread inside its worker; rotated by one warp per worker so that the warp
+    // carrying the extra self-paired bins lands on a different scheduler in each worker
+    const int p = (tid + 32 * w) & 127;
     float2* Zb = wbuf + w * (kZBuf + kYBuf + kScratch);
     float2* Yb = Zb + kZBuf;
     float2* Sc = Yb + kYBuf;
@@ -190,11 +244,14 @@ stft_reassign_r16(const StftArgs a, const int tile_T) {
     const int zA = 257 * (tA & 15) + 16 * (tA >> 4), zB = 257 * (tB & 15) + 16 * (tB >> 4);
     const int yA = 129 * (tA & 15) + 8 * (tA >> 4), yB = 129 * (tB & 15) + 8 * (tB >> 4);
     const int i1 = p & 15, q2 = p >> 4;                    // pass-2 butterfly coordinates
+    const bool owner = p != 0;                              // thread 0's residues pair with themselves
+    const float tAf = (float)tA, tBf = (float)tB;
 
     const long long per_ch = a.f_end - a.f_begin;
     const long long tiles_per_ch = (per_ch + tile_T - 1) / tile_T;
     const long long n_tiles = tiles_per_ch * a.channels;
     const bool hop_even = (a.hop & 1) == 0;
+    constexpr int B = N / 2 + 1;
 
     for (long long tl = blockIdx.x; tl < n_tiles; tl += gridDim.x) {
         const int ch = (int)(tl / tiles_per_ch);
@@ -212,43 +269,46 @@ stft_reassign_r16(const StftArgs a, const int tile_T) {
             const long long f = f0 + fi;
 
             // ================= pass 1 of Z: butterflies b = p, p + 128
-            static_for<2>([&](auto uc) {
-                constexpr int u = decltype(uc)::value;
+#pragma unroll 1
+            for (int u = 0; u < 2; ++u) {
                 const int b = p + 128 * u;
+                // base angle of sample b: theta_p (+ pi/16 for the second butterfly)
+                const float cb = u ? cp * c32(1) - sp * s32(1) : cp;
+                const float sb = u ? sp * c32(1) + cp * s32(1) : sp;
+                const float rb = rp + (float)u * (1.0f / 16.0f);
                 float2 v[16];
                 static_for<16>([&](auto jc) {
-                    constexpr int j = decltype(jc)::value;
-                    constexpr int q = u + 2 * j;                           // n = p + 128 q
-                    constexpr float cq = c32(q), sq = s32(q), rq = (float)q * (1.0f / 16.0f);
+                    constexpr int j = decltype(jc)::value;             // n = b + 256 j
+                    constexpr float cq = c32(2 * j), sq = s32(2 * j), rq = (float)j * (1.0f / 8.0f);
                     const float x = xs[b + 256 * j];
-                    const float cs = cp * cq - sp * sq;                    // cos(2 pi n / N)
+                    const float cs = cb * cq - sb * sq;                // cos(2 pi n / N)
                     const float h = 0.5f - 0.5f * cs;
                     const float re = x * h;
-                    v[j] = make_float2(re, re * (rp + rq));
+                    v[j] = make_float2(re, re * (rb + rq));
                 });
                 dft16(v);
                 Zb[b] = v[o16(0)];
 #pragma unroll
                 for (int i = 1; i < 16; ++i) Zb[b + 257 * i] = cmul(v[o16(i)], Ztab[(i - 1) * 256 + b]);
-            });
+            }
             // ================= pass 1 of Y: butterfly b = p on w = x * sin(2 pi n / N)
             {
                 const float c2 = cp * cp - sp * sp, s2 = 2.0f * sp * cp;   // angle of sample 2p
                 constexpr float cd = 0.99999882345170188f, sd = 0.0015339801862847655f;   // 2 pi / 4096
                 float2 v[16];
+                if (hop_even) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] = *reinterpret_cast<const float2*>(xs + 2 * p + 256 * j);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] = make_float2(xs[2 * p + 256 * j], xs[2 * p + 256 * j + 1]);
+                }
                 static_for<16>([&](auto jc) {
                     constexpr int j = decltype(jc)::value;
                     constexpr float cq = c32(2 * j), sq = s32(2 * j);
-                    float x0, x1;
-                    if (hop_even) {
-                        const float2 xx = *reinterpret_cast<const float2*>(xs + 2 * p + 256 * j);
-                        x0 = xx.x; x1 = xx.y;
-                    } else {
-                        x0 = xs[2 * p + 256 * j]; x1 = xs[2 * p + 256 * j + 1];
-                    }
                     const float se = s2 * cq + c2 * sq;
                     const float ce = c2 * cq - s2 * sq;
-                    v[j] = make_float2(x0 * se, x1 * (se * cd + ce * sd));
+                    v[j] = make_float2(v[j].x * se, v[j].y * (se * cd + ce * sd));
                 });
                 dft16(v);
                 Yb[p] = v[o16(0)];
@@ -258,17 +318,18 @@ stft_reassign_r16(const StftArgs a, const int tile_T) {
             worker_bar(w);
 
             // ================= pass 2 of Z: sub-FFTs of length 256, butterflies (i1, q2 + 8u)
-#pragma unroll
+#pragma unroll 1
             for (int u = 0; u < 2; ++u) {
                 const int p2 = q2 + 8 * u;
                 float2* base = Zb + 257 * i1 + p2;
+                const float2* t2 = T2 + p2;
                 float2 v[16];
 #pragma unroll
                 for (int j = 0; j < 16; ++j) v[j] = base[16 * j];
                 dft16(v);
                 base[0] = v[o16(0)];
 #pragma unroll
-                for (int i = 1; i < 16; ++i) base[16 * i] = cmul(v[o16(i)], T2[(i - 1) * 16 + p2]);
+                for (int i = 1; i < 16; ++i) base[16 * i] = cmul(v[o16(i)], t2[(i - 1) * 16]);
             }
             // ================= pass 2 of Y: sub-FFTs of length 128, butterfly (i1, q2)
             {
@@ -292,37 +353,41 @@ stft_reassign_r16(const StftArgs a, const int tile_T) {
             for (int j = 0; j < 16; ++j) { za[j] = Zb[zA + j]; zb[j] = Zb[zB + j]; }
             dft16(za); dft16(zb);
 
-            if (p != 0) {
-                // bins tA + 256 c and tB + 256 c, c = 0..7
-                static_for<8>([&](auto cc) {
-                    constexpr int c = decltype(cc)::value;
-                    bin_emit(a, chan_off, f, tA + 256 * c, za[o16(c)], zb[o16(15 - c)], ya[o8(c)],
-                             yb[o8(7 - c)], mul_w16<c>(wA));
-                    bin_emit(a, chan_off, f, tB + 256 * c, zb[o16(c)], za[o16(15 - c)], yb[o8(c)],
-                             ya[o8(7 - c)], mul_w16<c>(wB));
-                });
-            } else {
-                // residues 0 and 128 pair with themselves: 17 bins via scratch
-#pragma unroll
-                for (int c = 0; c < 16; ++c) { Sc[c] = za[o16(c)]; Sc[16 + c] = zb[o16(c)]; }
-#pragma unroll
-                for (int c = 0; c < 8; ++c) { Sc[32 + c] = ya[o8(c)]; Sc[40 + c] = yb[o8(c)]; }
-            }
+            // ================= epilogue
+            FrameCtx fc;
+            fc.lo = (float)max(-f, -1048576LL);
+            fc.hi = (float)min(a.F - 1 - f, 1048576LL);
+            fc.acc_row = (chan_off + f) * B;
+            fc.pd = a.dt_cols + fc.acc_row; fc.pk = a.dk_bins + fc.acc_row; fc.pe = a.energy + fc.acc_row;
+            // bins tA + 256 c and tB + 256 c, c = 0..7 (thread 0 tags along, its bins come below)
+            static_for<8>([&](auto cc) {
+                constexpr int c = decltype(cc)::value;
+                bin_emit<MODE>(a, fc, owner, tA + 256 * c, tAf + (float)(256 * c), za[o16(c)],
+                               zb[o16(15 - c)], ya[o8(c)], yb[o8(7 - c)], mul_w16<c>(wA));
+                bin_emit<MODE>(a, fc, owner, tB + 256 * c, tBf + (float)(256 * c), zb[o16(c)],
+                               za[o16(15 - c)], yb[o8(c)], ya[o8(7 - c)], mul_w16<c>(wB));
+            });
             if (p < 32) {
-                __syncwarp();
-                if (p <= 16) {
-                    int k;
-                    float2 zk, zn, yk, yn;
-                    if (p <= 8) {
-                        k = 256 * p;
-                        zk = Sc[p]; zn = Sc[(16 - p) & 15]; yk = Sc[32 + (p & 7)]; yn = Sc[32 + ((8 - p) & 7)];
-                    } else {
-                        const int c = p - 9;
-                        k = 128 + 256 * c;
-                        zk = Sc[16 + c]; zn = Sc[16 + 15 - c]; yk = Sc[40 + c]; yn = Sc[40 + 7 - c];
-                    }
-                    bin_emit(a, chan_off, f, k, zk, zn, yk, yn, __ldg(&a.tw[k]));
+                // residues 0 and 128 pair with themselves: 17 bins through the scratch
+                if (p == 0) {
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) { Sc[c] = za[o16(c)]; Sc[16 + c] = zb[o16(c)]; }
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) { Sc[32 + c] = ya[o8(c)]; Sc[40 + c] = yb[o8(c)]; }
                 }
+                __syncwarp();
+                const int l = min(p, 16);
+                int k;
+                float2 zk, zn, yk, yn;
+                if (l <= 8) {
+                    k = 256 * l;
+                    zk = Sc[l]; zn = Sc[(16 - l) & 15]; yk = Sc[32 + (l & 7)]; yn = Sc[32 + ((8 - l) & 7)];
+                } else {
+                    const int c = l - 9;
+                    k = 128 + 256 * c;
+                    zk = Sc[16 + c]; zn = Sc[16 + 15 - c]; yk = Sc[40 + c]; yn = Sc[40 + 7 - c];
+                }
+                bin_emit<MODE>(a, fc, p <= 16, k, (float)k, zk, zn, yk, yn, __ldg(&a.tw[k]));
             }
             worker_bar(w);      // pass-3 reads done before the next frame's pass-1 writes
         }
