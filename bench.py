@@ -223,7 +223,7 @@ def run_ours(args):
     F = frame_count(S, N_FFT, HOP)
     B = N_FFT // 2 + 1
     pcm = synth_device(S, seed=rank, device=dev)
-    eng = emspec.Engine(n_fft=N_FFT, hop=HOP)
+    eng = emspec.Engine(n_fft=N_FFT, hop=HOP, noise_gate_db=args.gate_db)
     eng.use_torch_stream()
     out = tuple(torch.empty((1, F, B), dtype=torch.float32, device=dev) for _ in range(3))
 
@@ -348,6 +348,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--seconds", type=float, default=3600.0, help="stream length per GPU")
     ap.add_argument("--cpu-seconds", type=float, default=60.0, help="audio seconds of the CPU sample")
+    ap.add_argument("--gate-db", type=float, default=-65.0,
+                    help="noise gate; -200 keeps every bin (worst case for the epilogue)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-pipeline", action="store_true")

@@ -2,7 +2,8 @@
 //
 // Layout of the work (DESIGN.md "K1-K3"):
 //   * persistent CTAs, one per SM, 3 workers x 128 threads; a CTA walks tiles of T
-//     consecutive frames whose samples ((T-1)*hop + 4096 floats) sit once in shared memory;
+//     consecutive frames whose samples ((T-1)*hop + 4096 floats) sit once in shared memory,
+//     double-buffered with cp.async so the next tile lands while this one is analysed;
 //   * a worker analyses one frame at a time, entirely on-chip:
 //       Z = FFT_4096(x*h + j*x*th')   as 16 x 16 x 16   (two radix-16 butterflies / thread / pass)
 //       Y = FFT_2048(w[2n] + j*w[2n+1]), w = x*dh'  as 16 x 16 x 8
@@ -34,15 +35,15 @@ constexpr int kThreads = kWorkers * kWorkerThreads;
 constexpr int kZBuf = 4112;            // float2, padZ(4095) = 4110
 constexpr int kYBuf = 2064;            // float2, padY(2047) = 2062
 constexpr int kZtab = 15 * 256;        // W_4096^{b i}, i = 1..15, b < 256
-constexpr int kYtab = 15 * 128;        // W_2048^{b i}, b < 128
 constexpr int kT2 = 15 * 16;           // W_256^{p2 i}
 constexpr int kT2Y = 15 * 8;           // W_128^{p2 i}
 constexpr int kScratch = 48;           // thread-0 self-paired residues
-constexpr int kTabFloat2 = kZtab + kYtab + kT2 + kT2Y;
+constexpr int kTabFloat2 = kZtab + kT2 + kT2Y;
 constexpr int kFixedBytes = (kWorkers * (kZBuf + kYBuf + kScratch) + kTabFloat2) * 8;
 constexpr int kMaxSmem = 232448;       // 227 KB
-constexpr int kTileFloats = (kMaxSmem - kFixedBytes) / 4;
+constexpr int kTileFloats = ((kMaxSmem - kFixedBytes) / 8) & ~3;   // per buffer, two buffers
 
+// frames per tile: both tile buffers must hold (T-1)*hop + N samples
 __host__ __device__ constexpr int tile_frames(int hop) {
     int t = (kTileFloats - N) / hop + 1;
     t -= t % kWorkers;
@@ -213,11 +214,10 @@ stft_reassign_r16(const StftArgs a, const int tile_T) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* sm = reinterpret_cast<float2*>(smem_raw);
     float2* Ztab = sm;                         // [15][256]
-    float2* Ytab = Ztab + kZtab;               // [15][128]
-    float2* T2 = Ytab + kYtab;                 // [15][16]
+    float2* T2 = Ztab + kZtab;                 // [15][16]
     float2* T2Y = T2 + kT2;                    // [15][8]
     float2* wbuf = T2Y + kT2Y;                 // per worker: Z, Y, scratch
-    float* tile = reinterpret_cast<float*>(wbuf + kWorkers * (kZBuf + kYBuf + kScratch));
+    float* tile0 = reinterpret_cast<float*>(wbuf + kWorkers * (kZBuf + kYBuf + kScratch));   // 2 x kTileFloats
 
     const int tid = threadIdx.x;
     const int w = tid >> 7;                    // worker
@@ -230,7 +230,6 @@ stft_reassign_r16(const StftArgs a, const int tile_T) {
 
     // ---- twiddle tables (once per CTA)
     for (int e = tid; e < kZtab; e += kThreads) { const int i = e / 256 + 1, b = e % 256; Ztab[e] = __ldg(&a.tw[b * i]); }
-    for (int e = tid; e < kYtab; e += kThreads) { const int i = e / 128 + 1, b = e % 128; Ytab[e] = __ldg(&a.tw[2 * b * i]); }
     for (int e = tid; e < kT2; e += kThreads) { const int i = e / 16 + 1, q = e % 16; T2[e] = __ldg(&a.tw[16 * q * i]); }
     for (int e = tid; e < kT2Y; e += kThreads) { const int i = e / 8 + 1, q = e % 8; T2Y[e] = __ldg(&a.tw[32 * q * i]); }
 
@@ -245,6 +244,10 @@ stft_reassign_r16(const StftArgs a, const int tile_T) {
     const int yA = 129 * (tA & 15) + 8 * (tA >> 4), yB = 129 * (tB & 15) + 8 * (tB >> 4);
     const int i1 = p & 15, q2 = p >> 4;                    // pass-2 butterfly coordinates
     const bool owner = p != 0;                              // thread 0's residues pair with themselves
+    // self-paired bins (residues 0 and 128): lane l <= 8 takes bin 256 l, lanes 9..16 bins 128 + 256 (l - 9)
+    const int ls = min(p, 16);
+    const int ks = ls <= 8 ? 256 * ls : 128 + 256 * (ls - 9);
+    const float2 ws = __ldg(&a.tw[ks]);                     // W_N^{ks}
     const float tAf = (float)tA, tBf = (float)tB;
 
     const long long per_ch = a.f_end - a.f_begin;
@@ -253,15 +256,31 @@ stft_reassign_r16(const StftArgs a, const int tile_T) {
     const bool hop_even = (a.hop & 1) == 0;
     constexpr int B = N / 2 + 1;
 
-    for (long long tl = blockIdx.x; tl < n_tiles; tl += gridDim.x) {
+    // Tiles are double-buffered: while the workers analyse tile i, cp.async brings the
+    // samples of this CTA's next tile into the other buffer (4-byte copies: no alignment
+    // demands on pcm, hop or the channel stride).
+    auto prefetch = [&](long long tl, float* dst) {
         const int ch = (int)(tl / tiles_per_ch);
         const long long f0 = a.f_begin + (tl - (long long)ch * tiles_per_ch) * tile_T;
         const int nf = (int)min((long long)tile_T, a.f_end - f0);
         const int n_samp = (nf - 1) * a.hop + N;
         const float* src = a.pcm + (long long)ch * a.S + f0 * a.hop;
-        __syncthreads();                                    // previous tile fully consumed
-        for (int s = tid; s < n_samp; s += kThreads) tile[s] = __ldg(src + s);
-        __syncthreads();
+        const unsigned d0 = (unsigned)__cvta_generic_to_shared(dst);
+        for (int s = tid; s < n_samp; s += kThreads)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d0 + 4u * s), "l"(src + s) : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    int buf = 0;
+    if ((long long)blockIdx.x < n_tiles) prefetch(blockIdx.x, tile0);
+
+    for (long long tl = blockIdx.x; tl < n_tiles; tl += gridDim.x, buf ^= 1) {
+        const int ch = (int)(tl / tiles_per_ch);
+        const long long f0 = a.f_begin + (tl - (long long)ch * tiles_per_ch) * tile_T;
+        const int nf = (int)min((long long)tile_T, a.f_end - f0);
+        const float* tile = tile0 + buf * kTileFloats;
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();            // this tile has landed; the other buffer is fully consumed
+        if (tl + gridDim.x < n_tiles) prefetch(tl + gridDim.x, tile0 + (buf ^ 1) * kTileFloats);
         const long long chan_off = (long long)ch * a.F;
 
         for (int fi = w; fi < nf; fi += kWorkers) {
@@ -313,7 +332,7 @@ stft_reassign_r16(const StftArgs a, const int tile_T) {
                 dft16(v);
                 Yb[p] = v[o16(0)];
 #pragma unroll
-                for (int i = 1; i < 16; ++i) Yb[p + 129 * i] = cmul(v[o16(i)], Ytab[(i - 1) * 128 + p]);
+                for (int i = 1; i < 16; ++i) Yb[p + 129 * i] = cmul(v[o16(i)], Ztab[(i - 1) * 256 + 2 * p]);   // W_2048^{p i}
             }
             worker_bar(w);
 
@@ -348,9 +367,12 @@ stft_reassign_r16(const StftArgs a, const int tile_T) {
             float2 ya[8], yb[8], za[16], zb[16];
 #pragma unroll
             for (int j = 0; j < 8; ++j) { ya[j] = Yb[yA + j]; yb[j] = Yb[yB + j]; }
-            dft8(ya); dft8(yb);
 #pragma unroll
             for (int j = 0; j < 16; ++j) { za[j] = Zb[zA + j]; zb[j] = Zb[zB + j]; }
+            // the buffers are dead from here: warps that finish early start the next frame's
+            // pass 1 while the others are still in the epilogue
+            worker_bar(w);
+            dft8(ya); dft8(yb);
             dft16(za); dft16(zb);
 
             // ================= epilogue
@@ -376,20 +398,16 @@ stft_reassign_r16(const StftArgs a, const int tile_T) {
                     for (int c = 0; c < 8; ++c) { Sc[32 + c] = ya[o8(c)]; Sc[40 + c] = yb[o8(c)]; }
                 }
                 __syncwarp();
-                const int l = min(p, 16);
-                int k;
+                const int l = ls;
                 float2 zk, zn, yk, yn;
                 if (l <= 8) {
-                    k = 256 * l;
                     zk = Sc[l]; zn = Sc[(16 - l) & 15]; yk = Sc[32 + (l & 7)]; yn = Sc[32 + ((8 - l) & 7)];
                 } else {
                     const int c = l - 9;
-                    k = 128 + 256 * c;
                     zk = Sc[16 + c]; zn = Sc[16 + 15 - c]; yk = Sc[40 + c]; yn = Sc[40 + 7 - c];
                 }
-                bin_emit<MODE>(a, fc, p <= 16, k, (float)k, zk, zn, yk, yn, __ldg(&a.tw[k]));
+                bin_emit<MODE>(a, fc, p <= 16, ks, (float)ks, zk, zn, yk, yn, ws);
             }
-            worker_bar(w);      // pass-3 reads done before the next frame's pass-1 writes
         }
     }
 }
