@@ -38,7 +38,31 @@ struct StftArgs {
     float         inv_hop;
     int           mode;       // DepositMode
     int           reassign;   // 0: plain spectrogram columns
+    long long     samp_off;   // frame f starts at sample f*hop + samp_off of its channel
+    int           ring;       // > 0: the accumulator is a ring of `ring` columns per channel (streaming)
+    int           stream_M;   // streaming: pushes per ring lap = ceil(n_fft / hop)
+    const long long* sstate;  // streaming: device counter of completed pushes (frame range decoded on device)
 };
+
+// Streaming launches sit in a CUDA graph, so the frame they analyse is derived on the device
+// from the push counter: push i (0-based) completes frame f = i + 1 - M, whose first sample
+// sits at ((i mod M) + 1) * hop of the doubled sample ring.  Returns false while the ring fills.
+__device__ __forceinline__ bool stream_decode(StftArgs& a) {
+    if (!a.sstate) return true;
+    const long long i = a.sstate[0];
+    const long long f = i + 1 - a.stream_M;
+    if (f < 0) return false;
+    a.f_begin = f;
+    a.f_end = f + 1;
+    a.samp_off = ((i % a.stream_M) + 1) * a.hop - f * a.hop;
+    return true;
+}
+
+// Accumulator cell of (channel, column, bin): linear [channels][F][B] or a column ring.
+__device__ __forceinline__ long long acc_cell(const StftArgs& a, int ch, long long col, int row, int B) {
+    return a.ring ? ((long long)ch * a.ring + (col % a.ring)) * B + row
+                  : ((long long)ch * a.F + col) * B + row;
+}
 
 struct PostArgs {
     const void*   acc;        // u64 or f32 [channels][F][B]

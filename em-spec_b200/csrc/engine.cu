@@ -15,6 +15,7 @@
 #include "scatter_post.cuh"
 #include "stft_generic.cuh"
 #include "stft_r16.cuh"
+#include "stream.cuh"
 
 namespace ems {
 
@@ -43,6 +44,22 @@ struct ems_handle {
     cudaEvent_t ev[EMS_STAGE_COUNT][2]{};
     bool ev_valid[EMS_STAGE_COUNT]{};
     uint64_t launches = 0;
+    // streaming state (allocated on the first push)
+    struct Stream {
+        bool ready = false;
+        cudaGraphExec_t graph = nullptr;
+        long long* sstate = nullptr;     // device push counter
+        float* in_dev = nullptr;         // [hop][channels]
+        float* ring = nullptr;           // [channels][2*Lr]
+        void* acc = nullptr;             // [channels][ring_cols][B]
+        float* carry = nullptr;          // [channels][B]
+        uint8_t* out_dev = nullptr;      // [channels][B]
+        float* in_pin = nullptr;         // pinned staging
+        uint8_t* out_pin = nullptr;
+        int M = 0, Lr = 0, R = 0, ring_cols = 0;
+        long long pushes = 0;            // host mirror of the device counter
+        size_t acc_bytes = 0;
+    } st;
     bool force_generic = false;         // EMS_FORCE_GENERIC=1: bypass the tuned kernels (A/B tests)
     char err[256] = "";
 };
@@ -240,6 +257,93 @@ static ems_status finish(ems_handle* h) {
     return EMS_OK;
 }
 
+
+// ---------------------------------------------------------------- streaming
+static void stream_free(ems_handle* h) {
+    auto& st = h->st;
+    if (st.graph) cudaGraphExecDestroy(st.graph);
+    for (void* p : {(void*)st.sstate, (void*)st.in_dev, (void*)st.ring, st.acc, (void*)st.carry,
+                    (void*)st.out_dev})
+        if (p) cudaFree(p);
+    if (st.in_pin) cudaFreeHost(st.in_pin);
+    if (st.out_pin) cudaFreeHost(st.out_pin);
+    st = ems_handle::Stream{};
+}
+
+static ems_status stream_zero(ems_handle* h) {
+    auto& st = h->st;
+    const int N = h->prm.n_fft, C = h->prm.channels, B = N / 2 + 1;
+    EMS_CUDA(h, cudaMemsetAsync(st.sstate, 0, sizeof(long long), h->stream));
+    EMS_CUDA(h, cudaMemsetAsync(st.ring, 0, sizeof(float) * C * 2 * st.Lr, h->stream));
+    EMS_CUDA(h, cudaMemsetAsync(st.acc, 0, st.acc_bytes, h->stream));
+    EMS_CUDA(h, cudaMemsetAsync(st.carry, 0, sizeof(float) * C * B, h->stream));
+    EMS_CUDA(h, cudaStreamSynchronize(h->stream));
+    st.pushes = 0;
+    return EMS_OK;
+}
+
+static ems_status stream_init(ems_handle* h) {
+    auto& st = h->st;
+    const int N = h->prm.n_fft, H = h->prm.hop, C = h->prm.channels, B = N / 2 + 1;
+    const bool det = h->prm.flags & EMS_FLAG_DETERMINISTIC;
+    st.M = (N + H - 1) / H;
+    st.Lr = st.M * H;
+    st.R = (N / 2 + H - 1) / H;
+    st.ring_cols = 2 * st.R + 1;
+    st.acc_bytes = (size_t)C * st.ring_cols * B * (det ? 8 : 4);
+    EMS_CUDA(h, cudaMalloc(&st.sstate, sizeof(long long)));
+    EMS_CUDA(h, cudaMalloc(&st.in_dev, sizeof(float) * H * C));
+    EMS_CUDA(h, cudaMalloc(&st.ring, sizeof(float) * C * 2 * st.Lr));
+    EMS_CUDA(h, cudaMalloc(&st.acc, st.acc_bytes));
+    EMS_CUDA(h, cudaMalloc(&st.carry, sizeof(float) * C * B));
+    EMS_CUDA(h, cudaMalloc(&st.out_dev, (size_t)C * B));
+    EMS_CUDA(h, cudaMallocHost(&st.in_pin, sizeof(float) * H * C));
+    EMS_CUDA(h, cudaMallocHost(&st.out_pin, (size_t)C * B));
+    ems_status s = stream_zero(h);
+    if (s != EMS_OK) return s;
+    st.ready = true;
+    return EMS_OK;
+}
+
+// Records one push as a graph: H2D of the hop, ring ingest, fused STFT + reassignment +
+// deposit of the frame the hop completes, post-pass of the column that became final,
+// counter advance, D2H of that column.
+static ems_status stream_capture(ems_handle* h) {
+    auto& st = h->st;
+    const int N = h->prm.n_fft, H = h->prm.hop, C = h->prm.channels, B = N / 2 + 1;
+    const bool det = h->prm.flags & EMS_FLAG_DETERMINISTIC;
+    StreamArgs sa{};
+    sa.sstate = st.sstate; sa.in = st.in_dev; sa.ring = st.ring; sa.acc = st.acc;
+    sa.carry = st.carry; sa.weight = h->weight; sa.out = st.out_dev;
+    sa.hop = H; sa.channels = C; sa.M = st.M; sa.Lr = st.Lr; sa.R = st.R;
+    sa.ring_cols = st.ring_cols; sa.B = B; sa.acc_is_u64 = det;
+    sa.smoothing = h->prm.smoothing;
+    sa.db_floor = (float)(kTopDb - (double)h->prm.db_range);
+    sa.inv_range = 255.0f / h->prm.db_range;
+    sa.gate_db = h->prm.noise_gate_db;
+    StftArgs a = make_args(h, st.ring, (size_t)2 * st.Lr, /*F=*/(long long)1 << 60);
+    a.f_begin = 0; a.f_end = 1;                       // grid sizing; the kernel decodes the real frame
+    a.acc = st.acc; a.mode = det ? kDepositU64 : kDepositF32;
+    a.ring = st.ring_cols; a.stream_M = st.M; a.sstate = st.sstate;
+
+    cudaGraph_t g = nullptr;
+    EMS_CUDA(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+    cudaMemcpyAsync(st.in_dev, st.in_pin, sizeof(float) * H * C, cudaMemcpyHostToDevice, h->stream);
+    stream_ingest_kernel<<<(H * C + 255) / 256, 256, 0, h->stream>>>(sa);
+    ems_status ls = launch_stft(h, a);
+    stream_post_kernel<<<(B * C + 255) / 256, 256, 0, h->stream>>>(sa);
+    stream_advance_kernel<<<1, 1, 0, h->stream>>>(st.sstate);
+    cudaMemcpyAsync(st.out_pin, st.out_dev, (size_t)C * B, cudaMemcpyDeviceToHost, h->stream);
+    cudaError_t ce = cudaStreamEndCapture(h->stream, &g);
+    h->launches -= 1;                                  // counted per push below, not at capture
+    if (ls != EMS_OK) { if (g) cudaGraphDestroy(g); return ls; }
+    if (ce != cudaSuccess) return fail(h, EMS_ERR_CUDA, "stream capture: %s", cudaGetErrorString(ce));
+    ce = cudaGraphInstantiate(&st.graph, g, 0);
+    cudaGraphDestroy(g);
+    if (ce != cudaSuccess) return fail(h, EMS_ERR_CUDA, "graph instantiate: %s", cudaGetErrorString(ce));
+    return EMS_OK;
+}
+
 }  // namespace ems
 
 using namespace ems;
@@ -325,6 +429,7 @@ ems_status ems_destroy(ems_handle* h) {
     for (DevBuf* b : {&h->acc, &h->carry, &h->ema_local, &h->ema_carry, &h->host_pcm,
                       &h->host_idx, &h->host_grid})
         if (b->p) cudaFree(b->p);
+    stream_free(h);
     if (h->win) cudaFree(h->win);
     if (h->tw) cudaFree(h->tw);
     if (h->weight) cudaFree(h->weight);
@@ -344,6 +449,7 @@ ems_status ems_update_display(ems_handle* h, const ems_params* p) {
         p->channels != h->prm.channels || p->sample_rate != h->prm.sample_rate)
         return fail(h, EMS_ERR_INVALID_ARG, "n_fft/hop/channels/sample_rate need a new handle");
     h->prm = *p;
+    if (h->st.graph) { cudaGraphExecDestroy(h->st.graph); h->st.graph = nullptr; }   // scalars are baked into the graph
     return upload_display(h);
 }
 
@@ -546,12 +652,30 @@ ems_status ems_launch_count(const ems_handle* h, uint64_t* n) {
     return EMS_OK;
 }
 
-ems_status ems_stream_push(ems_handle* h, const float*, uint8_t*, int*, int64_t*) {
-    return fail(h, EMS_ERR_UNSUPPORTED, "streaming mode not built yet");
+ems_status ems_stream_push(ems_handle* h, const float* pcm_host, uint8_t* column_host,
+                           int* column_ready, int64_t* column_index) {
+    if (!h || !pcm_host || !column_host || !column_ready) return EMS_ERR_INVALID_ARG;
+    auto& st = h->st;
+    ems_status s;
+    if (!st.ready && (s = stream_init(h)) != EMS_OK) return s;
+    if (!st.graph && (s = stream_capture(h)) != EMS_OK) return s;
+    const int N = h->prm.n_fft, H = h->prm.hop, C = h->prm.channels, B = N / 2 + 1;
+    memcpy(st.in_pin, pcm_host, sizeof(float) * H * C);
+    EMS_CUDA(h, cudaGraphLaunch(st.graph, h->stream));
+    h->launches += 4;
+    EMS_CUDA(h, cudaStreamSynchronize(h->stream));
+    const long long cf = st.pushes + 1 - st.M - st.R;   // column finalised by this push
+    ++st.pushes;
+    *column_ready = cf >= 0;
+    if (column_index) *column_index = cf;
+    if (cf >= 0) memcpy(column_host, st.out_pin, (size_t)C * B);
+    return EMS_OK;
 }
 
 ems_status ems_stream_reset(ems_handle* h) {
-    return fail(h, EMS_ERR_UNSUPPORTED, "streaming mode not built yet");
+    if (!h) return EMS_ERR_INVALID_ARG;
+    if (!h->st.ready) return EMS_OK;
+    return stream_zero(h);
 }
 
 }  // extern "C"

@@ -78,7 +78,7 @@ __device__ __forceinline__ int dif_pos(int k) {
 //   A2 = 2 X_h, B2 = 2 X_th', D2 = 2 X_dh'  (the common factor 2 cancels in the ratios)
 // Emits (dt_cols, dk_bins, energy) or deposits the energy; `f` = frame in its channel.
 template <int N>
-__device__ __forceinline__ void reassign_emit(const StftArgs& a, long long chan_off,
+__device__ __forceinline__ void reassign_emit(const StftArgs& a, int ch,
                                               long long f, int k, float2 A2, float2 B2,
                                               float2 D2) {
     constexpr int B = N / 2 + 1;
@@ -102,12 +102,12 @@ __device__ __forceinline__ void reassign_emit(const StftArgs& a, long long chan_
         if (!ok) { dtc = 0.f; dk = 0.f; }
     }
     if (a.mode == kStorePoints) {
-        const long long o = (chan_off + f) * B + k;
+        const long long o = ((long long)ch * a.F + f) * B + k;
         a.dt_cols[o] = dtc;
         a.dk_bins[o] = dk;
         a.energy[o] = ok ? e : 0.f;
     } else if (ok) {
-        const long long o = (chan_off + col) * B + row;
+        const long long o = acc_cell(a, ch, col, row, B);
         if (a.mode == kDepositU64)
             atomicAdd(reinterpret_cast<unsigned long long*>(a.acc) + o,
                       __float2ull_rn(e * kFixScale));
@@ -118,8 +118,10 @@ __device__ __forceinline__ void reassign_emit(const StftArgs& a, long long chan_
 
 template <int LOG2N, int THREADS>
 __global__ void __launch_bounds__(THREADS)
-stft_reassign_generic(const StftArgs a) {
+stft_reassign_generic(const StftArgs a_in) {
     constexpr int N = 1 << LOG2N;
+    StftArgs a = a_in;
+    if (!stream_decode(a)) return;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* Z = reinterpret_cast<float2*>(smem_raw);          // [N]
     float2* Y = Z + N;                                         // [N/2]
@@ -131,7 +133,7 @@ stft_reassign_generic(const StftArgs a) {
     for (long long it = blockIdx.x; it < total; it += gridDim.x) {
         const int ch = (int)(it / per_ch);
         const long long f = a.f_begin + (it - (long long)ch * per_ch);
-        const float* x = a.pcm + (long long)ch * a.S + f * a.hop;
+        const float* x = a.pcm + (long long)ch * a.S + f * a.hop + a.samp_off;
         for (int n = tid; n < N; n += THREADS) {
             const float v = __ldg(x + n);
             const float4 w = __ldg(&a.win[n]);
@@ -142,7 +144,6 @@ stft_reassign_generic(const StftArgs a) {
         fft_inplace_dif<LOG2N>(Z, a.tw, 0, tid, THREADS);
         fft_inplace_dif<LOG2N - 1>(Y, a.tw, 1, tid, THREADS);
 
-        const long long chan_off = (long long)ch * a.F;
         for (int k = tid; k <= N / 2; k += THREADS) {
             const float2 zk = Z[dif_pos<LOG2N>(k)];
             const float2 zn = Z[dif_pos<LOG2N>((N - k) & (N - 1))];
@@ -155,7 +156,7 @@ stft_reassign_generic(const StftArgs a) {
             const float2 w = __ldg(&a.tw[k]);                  // W_N^k = (cos, -sin)
             const float2 D2 = make_float2(E2.x + (w.x * O2.x - w.y * O2.y),
                                           E2.y + (w.x * O2.y + w.y * O2.x));
-            reassign_emit<N>(a, chan_off, f, k, A2, B2, D2);
+            reassign_emit<N>(a, ch, f, k, A2, B2, D2);
         }
         __syncthreads();
     }

@@ -151,7 +151,9 @@ struct FrameCtx {
     float* pd;           // row (chan, f) of dt_cols / dk_bins / energy (store mode)
     float* pk;
     float* pe;
-    long long acc_row;   // (chan*F + f) * B   (deposit modes)
+    long long acc_row;   // (chan*F + f) * B   (linear accumulator / stored points)
+    long long f;         // frame index in its channel
+    int ch;
 };
 
 __device__ __forceinline__ float rcp_approx(float x) {
@@ -200,7 +202,8 @@ __device__ __forceinline__ void bin_emit(const StftArgs& a, const FrameCtx& fc, 
     if (MODE == kStorePoints) {
         if (owner) { fc.pd[k] = dtc; fc.pk[k] = dk; fc.pe[k] = ok ? e : 0.f; }
     } else if (ok && owner) {
-        const long long o = fc.acc_row + (long long)((int)rc * B + k + (int)rintf(dk));
+        const long long o = a.ring ? acc_cell(a, fc.ch, fc.f + (long long)rc, k + (int)rintf(dk), B)
+                                   : fc.acc_row + (long long)((int)rc * B + k + (int)rintf(dk));
         if (MODE == kDepositU64)
             atomicAdd(reinterpret_cast<unsigned long long*>(a.acc) + o, __float2ull_rn(e * kFixScale));
         else
@@ -210,7 +213,9 @@ __device__ __forceinline__ void bin_emit(const StftArgs& a, const FrameCtx& fc, 
 
 template <int MODE>
 __global__ void __launch_bounds__(kThreads, 1)
-stft_reassign_r16(const StftArgs a, const int tile_T) {
+stft_reassign_r16(const StftArgs a_in, const int tile_T) {
+    StftArgs a = a_in;
+    if (!stream_decode(a)) return;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* sm = reinterpret_cast<float2*>(smem_raw);
     float2* Ztab = sm;                         // [15][256]
@@ -264,7 +269,7 @@ stft_reassign_r16(const StftArgs a, const int tile_T) {
         const long long f0 = a.f_begin + (tl - (long long)ch * tiles_per_ch) * tile_T;
         const int nf = (int)min((long long)tile_T, a.f_end - f0);
         const int n_samp = (nf - 1) * a.hop + N;
-        const float* src = a.pcm + (long long)ch * a.S + f0 * a.hop;
+        const float* src = a.pcm + (long long)ch * a.S + f0 * a.hop + a.samp_off;
         const unsigned d0 = (unsigned)__cvta_generic_to_shared(dst);
         for (int s = tid; s < n_samp; s += kThreads)
             asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d0 + 4u * s), "l"(src + s) : "memory");
@@ -281,7 +286,7 @@ stft_reassign_r16(const StftArgs a, const int tile_T) {
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();            // this tile has landed; the other buffer is fully consumed
         if (tl + gridDim.x < n_tiles) prefetch(tl + gridDim.x, tile0 + (buf ^ 1) * kTileFloats);
-        const long long chan_off = (long long)ch * a.F;
+        const long long chan_off = a.ring ? 0 : (long long)ch * a.F;
 
         for (int fi = w; fi < nf; fi += kWorkers) {
             const float* xs = tile + fi * a.hop;
@@ -380,6 +385,7 @@ stft_reassign_r16(const StftArgs a, const int tile_T) {
             fc.lo = (float)max(-f, -1048576LL);
             fc.hi = (float)min(a.F - 1 - f, 1048576LL);
             fc.acc_row = (chan_off + f) * B;
+            fc.f = f; fc.ch = ch;
             fc.pd = a.dt_cols + fc.acc_row; fc.pk = a.dk_bins + fc.acc_row; fc.pe = a.energy + fc.acc_row;
             // bins tA + 256 c and tB + 256 c, c = 0..7 (thread 0 tags along, its bins come below)
             static_for<8>([&](auto cc) {

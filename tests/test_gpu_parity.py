@@ -238,3 +238,42 @@ def test_long_stream_properties(emspec):
     assert np.percentile(np.abs(a[0] - o[0])[both], 99) <= 1e-3
     assert np.percentile(np.abs(a[1] - o[1])[both], 99) <= 1e-3
     eng.close()
+
+
+@pytest.mark.parametrize("n_fft,hop,channels,smoothing", [
+    (2048, 256, 2, 0.0), (4096, 128, 1, 0.0), (1024, 300, 1, 0.0), (8192, 256, 2, 0.4),
+])
+def test_streaming_matches_offline(emspec, n_fft, hop, channels, smoothing):
+    """ems_stream_push (one frame per push, CUDA graph) emits, R pushes late, exactly the columns
+    the offline call computes for the same samples (configs[1] geometry is the last case)."""
+    S = int(0.6 * SR) // hop * hop
+    x = np.stack([orc.synth_signal(S, SR, seed=20 + c) for c in range(channels)])
+    eng = emspec.Engine(n_fft=n_fft, hop=hop, channels=channels, smoothing=smoothing,
+                        flags=emspec.FLAG_REASSIGN | emspec.FLAG_DETERMINISTIC | emspec.FLAG_SYNC)
+    _, idx_off = eng.process_grid(torch.from_numpy(x).cuda(), want_grid=False)
+    idx_off = idx_off.cpu().numpy()
+    B = n_fft // 2 + 1
+    col = torch.empty((channels, B), dtype=torch.uint8).pin_memory()
+    inter = torch.from_numpy(np.ascontiguousarray(x.T))          # [S][channels] interleaved
+    got = {}
+    for i in range(S // hop):
+        ready, ci = eng.stream_push(inter[i * hop:(i + 1) * hop].contiguous(), col)
+        if ready:
+            got[ci] = col.numpy().copy()
+    F = idx_off.shape[1]
+    R = -(-(n_fft // 2) // hop)
+    assert sorted(got) == list(range(0, F - R)), (len(got), F, R)
+    worst = 0
+    for ci, c in got.items():
+        d = np.abs(c.astype(int) - idx_off[:, ci].astype(int))
+        worst = max(worst, d.max())
+    assert worst <= (1 if smoothing > 0 else 0), worst
+    # reset: the same pushes give the same columns again
+    eng.stream_reset()
+    again = {}
+    for i in range(S // hop):
+        ready, ci = eng.stream_push(inter[i * hop:(i + 1) * hop].contiguous(), col)
+        if ready:
+            again[ci] = col.numpy().copy()
+    assert all((again[k] == got[k]).all() for k in got)
+    eng.close()
