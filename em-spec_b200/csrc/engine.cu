@@ -40,7 +40,7 @@ struct ems_handle {
     float4* win = nullptr;              // [N]
     float2* tw = nullptr;               // [N]
     float*  weight = nullptr;           // [B]
-    ems::DevBuf acc, carry, ema_local, ema_carry, host_pcm, host_idx, host_grid;
+    ems::DevBuf acc, carry, ema_local, ema_carry, host_pcm, host_idx, host_grid, big_scratch;
     cudaEvent_t ev[EMS_STAGE_COUNT][2]{};
     bool ev_valid[EMS_STAGE_COUNT]{};
     uint64_t launches = 0;
@@ -145,6 +145,28 @@ static ems_status launch_generic(ems_handle* h, const StftArgs& a) {
     return EMS_OK;
 }
 
+template <int LOG2N>
+static ems_status launch_big(ems_handle* h, const StftArgs& a) {
+    constexpr int N = 1 << LOG2N;
+    constexpr int THREADS = 1024;
+    const size_t smem = (size_t)N * 4;
+    auto kern = stft_reassign_big<LOG2N, THREADS>;
+    EMS_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const long long total = (a.f_end - a.f_begin) * a.channels;
+    long long grid = h->sm_count;
+    if (grid > total) grid = total;
+    if (grid < 1) return EMS_OK;
+    const size_t need = (size_t)h->sm_count * 2 * (N / 2 + 1) * sizeof(float2);
+    if (h->big_scratch.bytes < need) {     // never reallocated inside a stream capture: sized for all SMs
+        ems_status s = ensure(h, h->big_scratch, need);
+        if (s != EMS_OK) return s;
+    }
+    kern<<<(unsigned)grid, THREADS, smem, h->stream>>>(a, (float2*)h->big_scratch.p);
+    ++h->launches;
+    EMS_CUDA(h, cudaGetLastError());
+    return EMS_OK;
+}
+
 // Tuned n_fft = 4096 kernel: persistent, one CTA per SM, 3 workers x 128 threads.
 static ems_status launch_r16(ems_handle* h, const StftArgs& a, int tile_T) {
     const size_t smem = (size_t)r16::kFixedBytes + 2 * (size_t)r16::kTileFloats * sizeof(float);
@@ -177,6 +199,7 @@ static ems_status launch_stft(ems_handle* h, const StftArgs& a) {
         case 12: return launch_generic<12>(h, a);
         case 13: return launch_generic<13>(h, a);
         case 14: return launch_generic<14>(h, a);
+        case 15: return launch_big<15>(h, a);
         default: return fail(h, EMS_ERR_UNSUPPORTED, "n_fft=%d has no kernel in this build",
                              h->prm.n_fft);
     }
@@ -301,6 +324,7 @@ static ems_status stream_init(ems_handle* h) {
     EMS_CUDA(h, cudaMallocHost(&st.out_pin, (size_t)C * B));
     ems_status s = stream_zero(h);
     if (s != EMS_OK) return s;
+    if (N == 32768 && (s = ensure(h, h->big_scratch, (size_t)h->sm_count * 2 * B * sizeof(float2))) != EMS_OK) return s;
     st.ready = true;
     return EMS_OK;
 }
@@ -427,7 +451,7 @@ ems_status ems_destroy(ems_handle* h) {
     if (!h) return EMS_ERR_INVALID_ARG;
     if (h->stream) cudaStreamSynchronize(h->stream);
     for (DevBuf* b : {&h->acc, &h->carry, &h->ema_local, &h->ema_carry, &h->host_pcm,
-                      &h->host_idx, &h->host_grid})
+                      &h->host_idx, &h->host_grid, &h->big_scratch})
         if (b->p) cudaFree(b->p);
     stream_free(h);
     if (h->win) cudaFree(h->win);

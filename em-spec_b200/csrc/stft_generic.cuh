@@ -162,4 +162,50 @@ stft_reassign_generic(const StftArgs a_in) {
     }
 }
 
+// n_fft too large for Z and Y to share the SM (32768: 384 KB): the three real FFTs run one
+// after another as half-size complex FFTs (N/2 points, 4N bytes of shared memory), X_h and
+// X_th wait in an L2-resident per-CTA scratch until X_dh is ready.  Same arithmetic and
+// decisions as the kernel above; only used where that one cannot be launched.
+template <int LOG2N, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+stft_reassign_big(const StftArgs a_in, float2* __restrict__ scratch_all) {
+    constexpr int N = 1 << LOG2N, H2 = N / 2, B = N / 2 + 1;
+    StftArgs a = a_in;
+    if (!stream_decode(a)) return;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* Y = reinterpret_cast<float2*>(smem_raw);          // [N/2]
+    float* Yf = reinterpret_cast<float*>(Y);
+    float2* scratch = scratch_all + (size_t)blockIdx.x * 2 * B;   // [2][B]: 2 X_h, 2 X_th'
+    const int tid = threadIdx.x;
+    const long long per_ch = a.f_end - a.f_begin;
+    const long long total = per_ch * a.channels;
+
+    for (long long it = blockIdx.x; it < total; it += gridDim.x) {
+        const int ch = (int)(it / per_ch);
+        const long long f = a.f_begin + (it - (long long)ch * per_ch);
+        const float* x = a.pcm + (long long)ch * a.S + f * a.hop + a.samp_off;
+#pragma unroll 1
+        for (int wi = 0; wi < 3; ++wi) {
+            for (int n = tid; n < N; n += THREADS) {
+                const float4 w = __ldg(&a.win[n]);
+                Yf[n] = __ldg(x + n) * (wi == 0 ? w.x : wi == 1 ? w.y : w.z);
+            }
+            __syncthreads();
+            fft_inplace_dif<LOG2N - 1>(Y, a.tw, 1, tid, THREADS);
+            for (int k = tid; k <= H2; k += THREADS) {
+                const float2 yk = Y[dif_pos<LOG2N - 1>(k & (H2 - 1))];
+                const float2 yn = Y[dif_pos<LOG2N - 1>((H2 - k) & (H2 - 1))];
+                const float2 E2 = make_float2(yk.x + yn.x, yk.y - yn.y);
+                const float2 O2 = make_float2(yk.y + yn.y, yn.x - yk.x);
+                const float2 w = __ldg(&a.tw[k]);
+                const float2 X2 = make_float2(E2.x + (w.x * O2.x - w.y * O2.y),
+                                              E2.y + (w.x * O2.y + w.y * O2.x));
+                if (wi < 2) scratch[wi * B + k] = X2;
+                else reassign_emit<N>(a, ch, f, k, scratch[k], scratch[B + k], X2);
+            }
+            __syncthreads();
+        }
+    }
+}
+
 }  // namespace ems

@@ -46,7 +46,7 @@ def run_grid(m, x, prm, want_grid=True):
 
 @pytest.mark.parametrize("n_fft,hop,secs", [
     (256, 64, 0.25), (512, 128, 0.5), (1024, 256, 0.5), (2048, 512, 2.0),   # configs[0] geometry
-    (4096, 128, 1.0), (4096, 256, 1.0), (8192, 256, 1.0), (16384, 4096, 2.0),
+    (4096, 128, 1.0), (4096, 256, 1.0), (8192, 256, 1.0), (16384, 4096, 2.0), (32768, 8192, 3.0),
     (4096, 1000, 0.5), (2048, 2048, 0.5),                                   # odd hop, hop = n_fft
 ])
 def test_points_vs_oracle(emspec, n_fft, hop, secs):
@@ -129,6 +129,17 @@ def test_grid_and_index_vs_oracle(emspec, n_fft, hop):
     # energy conservation: the grid holds exactly the kept point energy
     dt, dk, e = run_points(emspec, x, prm)
     assert abs(g.sum(dtype=np.float64) - e.sum(dtype=np.float64)) <= 1e-5 * e.sum(dtype=np.float64)
+
+
+@pytest.mark.parametrize("n_fft", [256, 512, 1024, 2048, 4096, 8192, 16384, 32768])
+def test_nfft_sweep_display_controls(emspec, n_fft):
+    """configs[4]: n_fft sweep 256-32768 at hop = n_fft/4 with low-end boost + smoothing + gate."""
+    x = orc.synth_signal(max(SR // 2, 6 * n_fft), SR, seed=12)
+    prm = orc.Params(n_fft=n_fft, hop=n_fft // 4, low_end_boost=3.9, smoothing=0.5, noise_gate_db=-65.0)
+    check_points(run_points(emspec, x, prm), x, prm)
+    g, idx = run_grid(emspec, x, prm)
+    err, grid_o, _ = check_grid(g, x, prm)
+    check_index(idx, grid_o, prm)
 
 
 def test_display_controls(emspec):
