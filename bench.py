@@ -97,7 +97,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                 "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -106,9 +106,10 @@ class ClockSampler:
 
     def _read(self):
         for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
+            self.lines.append((time.perf_counter(), ln.strip()))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """Summary of the samples that arrived inside [t0, t1] (all samples if too few did)."""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -118,7 +119,11 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        inside = [ln for (t, ln) in self.lines if t0 is None or (t0 <= t <= t1 + 0.05)]
+        scope = "timed region"
+        if len(inside) < 3:
+            inside, scope = [ln for (_, ln) in self.lines], "warm-up + timed region (region too short for 3 samples)"
+        for ln in inside:
             p = [v.strip() for v in ln.split(",")]
             if len(p) < 7:
                 continue
@@ -131,7 +136,7 @@ class ClockSampler:
                     reasons.add(nm)
         return {"sm_mhz": statistics.median(sm) if sm else None,
                 "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "scope": scope, "reasons": sorted(reasons)}
 
 
 # ------------------------------------------------------------------ synthetic stream on device
@@ -155,6 +160,11 @@ def synth_device(S: int, seed: int, device):
         v = 0.5 * torch.sin(ph) + 0.25 * torch.sin(2 * math.pi * fa * t) + 0.125 * torch.sin(2 * math.pi * fb * t)
         x[s0:s1] = v.float() + 1e-3 * torch.randn(s1 - s0, device=device, generator=g)
     return x
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum of stft_reassign_r16<store>, one `ncu --set full`
+# capture of a 224,969-frame launch (profiles/r01_ncu_stft_reassign_r16.txt): 5.5928 GB
+NCU_DRAM_BYTES_PER_FRAME = (118.815232e6 + 5.474033e9) / 224969
 
 
 def peaks():
@@ -228,12 +238,13 @@ def run_ours(args):
     out = tuple(torch.empty((1, F, B), dtype=torch.float32, device=dev) for _ in range(3))
 
     # ---- device-resident: ems_process_points
-    for _ in range(args.warmup):
-        eng.process_points(pcm, out=out)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for _ in range(args.warmup):
+        eng.process_points(pcm, out=out)
     barrier()
+    t_region0 = time.perf_counter()
     l0 = eng.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -251,7 +262,7 @@ def run_ours(args):
     ms = torch.tensor([my_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_region0, time.perf_counter()) if rank == 0 else None
     total_ms = ms.item()
     frames_all = F * world
     value = frames_all * args.steps / (total_ms * 1e-3)
@@ -308,7 +319,7 @@ def run_ours(args):
         if world > 1:
             dist.all_reduce(wall, op=dist.ReduceOp.MAX)
         e2e = {"value": frames_all * args.steps / wall.item(), "unit": UNIT,
-               "h2d_bytes_per_step": S * 4, "d2h_bytes_per_step": F * B,
+               "h2d_bytes_per_step": S * 4 * world, "d2h_bytes_per_step": F * B * world,
                "what": "ems_process_host: pinned host fp32 PCM -> pinned host u8 colour-index "
                        "image [F][B] (a1-a5), chunked copies overlapped with compute"}
 
@@ -356,7 +367,12 @@ def run_ours(args):
                        "l2_policy": "inputs (0.69 GB) and outputs (33 GB) larger than L2, no flush needed",
                        "parallelism": f"clip-sharded x{world}, NCCL all_gather of per-rank summaries only"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak,
+                         "traffic": NCU_DRAM_BYTES_PER_FRAME * F if args.gate_db == -65.0 else None,
+                         "traffic_unit": "bytes per launch (ncu dram bytes per frame of a 224,969-frame "
+                                         "launch x frames of this launch; algorithmic = bytes_per_frame x frames)",
+                         "algorithmic_bytes_per_launch": b_points(N_FFT, HOP) * F,
+                         "peak_source": peak_src,
                          "kernel": "stft_reassign (fused frame gather + 3-window STFT + reassignment)",
                          "kernel_ms": kern_ms, "kernel_ms_last_step_lib_events": kern_last_ms,
                          "bytes_per_frame": b_points(N_FFT, HOP),
@@ -375,7 +391,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--seconds", type=float, default=3600.0, help="stream length per GPU")
