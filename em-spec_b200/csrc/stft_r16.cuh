@@ -61,16 +61,38 @@ __device__ __forceinline__ void static_for(Fn&& fn) {
     static_for_impl(std::make_integer_sequence<int, Count>{}, fn);
 }
 
-__device__ __forceinline__ float2 operator+(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ float2 operator-(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+// ---- packed fp32x2 arithmetic (sm_100 FADD2 / FMUL2 / FFMA2).  A complex value lives in an
+// aligned register pair; one packed instruction does the work of two scalar ones at the same
+// lane throughput, i.e. half the issue slots (tools/microbench/fp32x2.cu).  ptxas folds the
+// half swaps and per-half negations written below into operand modifiers (.LO_HI, .NP) and
+// single-register broadcasts (.F32), so rotations by +-j and complex multiplies cost no moves.
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pk(float x, float y) { u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(x), "f"(y)); return r; }
+__device__ __forceinline__ u64 pk(float2 a) { return pk(a.x, a.y); }
+__device__ __forceinline__ float2 up(u64 a) { float2 r; asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(a)); return r; }
+__device__ __forceinline__ float2 add2(float2 a, float2 b) { u64 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(pk(a)), "l"(pk(b))); return up(r); }
+__device__ __forceinline__ float2 sub2(float2 a, float2 b) { u64 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(pk(a)), "l"(pk(b))); return up(r); }
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) { u64 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(pk(a)), "l"(pk(b))); return up(r); }
+// a * b + c, element-wise
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) { u64 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(pk(a)), "l"(pk(b)), "l"(pk(c))); return up(r); }
+__device__ __forceinline__ float2 operator+(float2 a, float2 b) { return add2(a, b); }
+__device__ __forceinline__ float2 operator-(float2 a, float2 b) { return sub2(a, b); }
+// -j * a and +j * a
+__device__ __forceinline__ float2 mulmj(float2 a) { return make_float2(a.y, -a.x); }
+__device__ __forceinline__ float2 mulpj(float2 a) { return make_float2(-a.y, a.x); }
+// complex product v * w in two packed instructions
+__device__ __forceinline__ float2 cmul2(float2 v, float2 w) {
+    const float2 t = mul2(v, make_float2(w.x, w.x));
+    return fma2(make_float2(-v.y, v.x), make_float2(w.y, w.y), t);
+}
 
 // forward DFT-4 in place: (x0, x1, x2, x3) <- outputs 0..3
 __device__ __forceinline__ void dft4(float2& x0, float2& x1, float2& x2, float2& x3) {
     const float2 s02 = x0 + x2, d02 = x0 - x2, s13 = x1 + x3, d13 = x1 - x3;
     x0 = s02 + s13;
     x2 = s02 - s13;
-    x1 = make_float2(d02.x + d13.y, d02.y - d13.x);
-    x3 = make_float2(d02.x - d13.y, d02.y + d13.x);
+    x1 = d02 + mulmj(d13);
+    x3 = d02 - mulmj(d13);
 }
 
 // multiply by W16^E = exp(-2 pi j E / 16), E compile-time
@@ -79,20 +101,18 @@ __device__ __forceinline__ float2 mul_w16(float2 v) {
     constexpr float C1 = 0.92387953251128674f, S1 = 0.38268343236508977f, R = 0.70710678118654752f;
     constexpr int e = E & 15;
     if constexpr (e == 0) return v;
-    else if constexpr (e == 4) return make_float2(v.y, -v.x);
+    else if constexpr (e == 4) return mulmj(v);
     else if constexpr (e == 8) return make_float2(-v.x, -v.y);
-    else if constexpr (e == 12) return make_float2(-v.y, v.x);
-    else if constexpr (e == 2) return make_float2((v.x + v.y) * R, (v.y - v.x) * R);
-    else if constexpr (e == 6) return make_float2((v.y - v.x) * R, -(v.x + v.y) * R);
-    else if constexpr (e == 10) return make_float2(-(v.x + v.y) * R, (v.x - v.y) * R);
-    else if constexpr (e == 14) return make_float2((v.x - v.y) * R, (v.x + v.y) * R);
+    else if constexpr (e == 12) return mulpj(v);
     else {
-        // (c, -s) with c = cos(2 pi e/16), s = sin(2 pi e/16)
+        // (c, -s): v * W = v * c + (-j v) * s
         constexpr float c = (e == 1 || e == 15) ? C1 : (e == 3 || e == 13) ? S1
-                          : (e == 5 || e == 11) ? -S1 : -C1;               // e == 7, 9
+                          : (e == 5 || e == 11) ? -S1 : (e == 7 || e == 9) ? -C1
+                          : (e == 2 || e == 14) ? R : -R;                  // e == 6, 10
         constexpr float s = (e == 1 || e == 7) ? S1 : (e == 3 || e == 5) ? C1
-                          : (e == 9 || e == 15) ? -S1 : -C1;               // e == 11, 13
-        return make_float2(v.x * c + v.y * s, v.y * c - v.x * s);
+                          : (e == 9 || e == 15) ? -S1 : (e == 11 || e == 13) ? -C1
+                          : (e == 2 || e == 6) ? R : -R;                   // e == 10, 14
+        return fma2(mulmj(v), make_float2(s, s), mul2(v, make_float2(c, c)));
     }
 }
 
@@ -313,7 +333,7 @@ stft_reassign_r16(const StftArgs a_in, const int tile_T) {
                 dft16(v);
                 Zb[b] = v[o16(0)];
 #pragma unroll
-                for (int i = 1; i < 16; ++i) Zb[b + 257 * i] = cmul(v[o16(i)], Ztab[(i - 1) * 256 + b]);
+                for (int i = 1; i < 16; ++i) Zb[b + 257 * i] = cmul2(v[o16(i)], Ztab[(i - 1) * 256 + b]);
             }
             // ================= pass 1 of Y: butterfly b = p on w = x * sin(2 pi n / N)
             {
@@ -337,7 +357,7 @@ stft_reassign_r16(const StftArgs a_in, const int tile_T) {
                 dft16(v);
                 Yb[p] = v[o16(0)];
 #pragma unroll
-                for (int i = 1; i < 16; ++i) Yb[p + 129 * i] = cmul(v[o16(i)], Ztab[(i - 1) * 256 + 2 * p]);   // W_2048^{p i}
+                for (int i = 1; i < 16; ++i) Yb[p + 129 * i] = cmul2(v[o16(i)], Ztab[(i - 1) * 256 + 2 * p]);   // W_2048^{p i}
             }
             worker_bar(w);
 
@@ -353,7 +373,7 @@ stft_reassign_r16(const StftArgs a_in, const int tile_T) {
                 dft16(v);
                 base[0] = v[o16(0)];
 #pragma unroll
-                for (int i = 1; i < 16; ++i) base[16 * i] = cmul(v[o16(i)], t2[(i - 1) * 16]);
+                for (int i = 1; i < 16; ++i) base[16 * i] = cmul2(v[o16(i)], t2[(i - 1) * 16]);
             }
             // ================= pass 2 of Y: sub-FFTs of length 128, butterfly (i1, q2)
             {
@@ -364,7 +384,7 @@ stft_reassign_r16(const StftArgs a_in, const int tile_T) {
                 dft16(v);
                 base[0] = v[o16(0)];
 #pragma unroll
-                for (int i = 1; i < 16; ++i) base[8 * i] = cmul(v[o16(i)], T2Y[(i - 1) * 8 + q2]);
+                for (int i = 1; i < 16; ++i) base[8 * i] = cmul2(v[o16(i)], T2Y[(i - 1) * 8 + q2]);
             }
             worker_bar(w);
 
