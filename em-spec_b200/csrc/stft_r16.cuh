@@ -361,30 +361,32 @@ stft_reassign_r16(const StftArgs a_in, const int tile_T) {
             }
             worker_bar(w);
 
-            // ================= pass 2 of Z: sub-FFTs of length 256, butterflies (i1, q2 + 8u)
-#pragma unroll 1
-            for (int u = 0; u < 2; ++u) {
-                const int p2 = q2 + 8 * u;
-                float2* base = Zb + 257 * i1 + p2;
-                const float2* t2 = T2 + p2;
-                float2 v[16];
-#pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] = base[16 * j];
-                dft16(v);
-                base[0] = v[o16(0)];
-#pragma unroll
-                for (int i = 1; i < 16; ++i) base[16 * i] = cmul2(v[o16(i)], t2[(i - 1) * 16]);
-            }
-            // ================= pass 2 of Y: sub-FFTs of length 128, butterfly (i1, q2)
+            // ================= pass 2: Z sub-FFTs of length 256, butterflies (i1, q2), (i1, q2 + 8);
+            // Y sub-FFTs of length 128, butterfly (i1, q2).  Software-pipelined by hand: the
+            // loads of the next butterfly are in flight while the current one is computed.
             {
-                float2* base = Yb + 129 * i1 + q2;
-                float2 v[16];
+                float2* bz0 = Zb + 257 * i1 + q2;
+                float2* bz1 = bz0 + 8;
+                float2* by = Yb + 129 * i1 + q2;
+                float2 v0[16], v1[16];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] = base[8 * j];
-                dft16(v);
-                base[0] = v[o16(0)];
+                for (int j = 0; j < 16; ++j) v0[j] = bz0[16 * j];
 #pragma unroll
-                for (int i = 1; i < 16; ++i) base[8 * i] = cmul2(v[o16(i)], T2Y[(i - 1) * 8 + q2]);
+                for (int j = 0; j < 16; ++j) v1[j] = bz1[16 * j];
+                dft16(v0);
+                bz0[0] = v0[o16(0)];
+#pragma unroll
+                for (int i = 1; i < 16; ++i) bz0[16 * i] = cmul2(v0[o16(i)], T2[(i - 1) * 16 + q2]);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v0[j] = by[8 * j];
+                dft16(v1);
+                bz1[0] = v1[o16(0)];
+#pragma unroll
+                for (int i = 1; i < 16; ++i) bz1[16 * i] = cmul2(v1[o16(i)], T2[(i - 1) * 16 + q2 + 8]);
+                dft16(v0);
+                by[0] = v0[o16(0)];
+#pragma unroll
+                for (int i = 1; i < 16; ++i) by[8 * i] = cmul2(v0[o16(i)], T2Y[(i - 1) * 8 + q2]);
             }
             worker_bar(w);
 
