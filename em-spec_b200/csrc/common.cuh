@@ -34,6 +34,7 @@ struct StftArgs {
     float*        dk_bins;
     float*        energy;
     void*         acc;        // [channels][F][B] u64 or f32 accumulator, or null
+    unsigned char* flags;     // [channels][NB][F] "this 64-bin block of this column holds energy", or null
     float         gate_lin;   // drop points with energy <= gate
     float         inv_hop;
     int           mode;       // DepositMode
@@ -58,6 +59,14 @@ __device__ __forceinline__ bool stream_decode(StftArgs& a) {
     return true;
 }
 
+constexpr int kFlagShift = 6;                              // one dirty flag per 64 bins of a column
+__host__ __device__ constexpr int flag_blocks(int B) { return (B + 63) >> kFlagShift; }
+// Flags are column-contiguous per bin block ([channels][NB][F]) so the post-pass reads the
+// flags of 16 consecutive columns from one cache line.
+__device__ __forceinline__ long long flag_index(int ch, long long F, int B, long long col, int row) {
+    return ((long long)ch * flag_blocks(B) + (row >> kFlagShift)) * F + col;
+}
+
 // Accumulator cell of (channel, column, bin): linear [channels][F][B] or a column ring.
 __device__ __forceinline__ long long acc_cell(const StftArgs& a, int ch, long long col, int row, int B) {
     return a.ring ? ((long long)ch * a.ring + (col % a.ring)) * B + row
@@ -65,7 +74,9 @@ __device__ __forceinline__ long long acc_cell(const StftArgs& a, int ch, long lo
 }
 
 struct PostArgs {
-    const void*   acc;        // u64 or f32 [channels][F][B]
+    void*         acc;        // u64 or f32 [channels][F][B]; cells read by the emit pass are cleared
+    unsigned char* flags;     // [channels][NB][F] dirty flags written by the deposits
+    int           NB;
     int           acc_is_u64;
     float*        grid;       // fp32 [channels][F][B] or null
     uint8_t*      index;      // u8   [channels][F][B] or null

@@ -40,7 +40,8 @@ struct ems_handle {
     float4* win = nullptr;              // [N]
     float2* tw = nullptr;               // [N]
     float*  weight = nullptr;           // [B]
-    ems::DevBuf acc, carry, ema_local, ema_carry, host_pcm, host_idx, host_grid, big_scratch;
+    ems::DevBuf acc, flags, carry, ema_local, ema_carry, host_pcm, host_idx, host_grid, big_scratch;
+    bool acc_clean = false;             // accumulator and dirty flags are all zero (kept so by the post-pass)
     cudaEvent_t ev[EMS_STAGE_COUNT][2]{};
     bool ev_valid[EMS_STAGE_COUNT]{};
     uint64_t launches = 0;
@@ -219,6 +220,8 @@ static StftArgs make_args(ems_handle* h, const float* pcm, size_t S, long long F
 static PostArgs make_post(ems_handle* h, long long F, float* grid, uint8_t* index) {
     PostArgs p{};
     p.acc = h->acc.p;
+    p.flags = (unsigned char*)h->flags.p;
+    p.NB = flag_blocks(h->prm.n_fft / 2 + 1);
     p.acc_is_u64 = (h->prm.flags & EMS_FLAG_DETERMINISTIC) ? 1 : 0;
     p.grid = grid; p.index = index; p.weight = h->weight;
     p.carry = (float*)h->carry.p;
@@ -231,31 +234,88 @@ static PostArgs make_post(ems_handle* h, long long F, float* grid, uint8_t* inde
     return p;
 }
 
+static ems_status clear_flags(ems_handle* h, long long F, long long c0, long long c1, int B);
+
 // Post-pass over columns [col_begin, col_end) of every channel; h->carry holds the EMA
 // state entering col_begin and leaves with the state after col_end - 1.
 static ems_status run_post(ems_handle* h, PostArgs p) {
     const long long ncols = p.col_end - p.col_begin;
     if (ncols <= 0) return EMS_OK;
-    const int n_chunks = (int)((ncols + kPostChunk - 1) / kPostChunk);
+    const bool ema = p.smoothing > 0.f && p.index;
+    if (!ema) {
+        // no recurrence along time: zero-fill the outputs, then visit only the dirty blocks
+        for (int ch = 0; ch < p.channels; ++ch) {
+            const size_t off = ((size_t)ch * p.F + p.col_begin) * p.B, cnt = (size_t)ncols * p.B;
+            if (p.index) EMS_CUDA(h, cudaMemsetAsync(p.index + off, 0, cnt, h->stream));
+            if (p.grid) EMS_CUDA(h, cudaMemsetAsync(p.grid + off, 0, cnt * sizeof(float), h->stream));
+        }
+        const dim3 g((unsigned)((ncols + 255) / 256), p.channels * p.NB);
+        post_sparse_kernel<<<g, 256, 0, h->stream>>>(p);
+        ++h->launches;
+        EMS_CUDA(h, cudaGetLastError());
+        return EMS_OK;
+    }
+    // With smoothing the EMA runs along time: 256-column chunks, local pass + carries + emit,
+    // then the flags of the covered columns are cleared.
+    const int chunk_cols = ema ? kPostChunk : kPostTile;
+    const long long n_chunks = (ncols + chunk_cols - 1) / chunk_cols;
     const dim3 blk(128);
-    const dim3 grd((p.B + 127) / 128, n_chunks, p.channels);
+    const dim3 grd((unsigned)n_chunks, (p.B + 127) / 128, p.channels);
     const float* carry_in = nullptr;
-    if (p.smoothing > 0.f && p.index) {
+    if (ema) {
         const size_t bytes = (size_t)p.channels * n_chunks * p.B * sizeof(float);
         ems_status s;
         if ((s = ensure(h, h->ema_local, bytes)) != EMS_OK) return s;
         if ((s = ensure(h, h->ema_carry, bytes)) != EMS_OK) return s;
         p.carry = (float*)h->carry.p;
-        post_ema_local_kernel<<<grd, blk, 0, h->stream>>>(p, (float*)h->ema_local.p, n_chunks);
-        const long long last = ncols - (long long)(n_chunks - 1) * kPostChunk;
+        post_ema_local_kernel<<<grd, blk, 0, h->stream>>>(p, (float*)h->ema_local.p, (int)n_chunks);
+        const long long last = ncols - (n_chunks - 1) * kPostChunk;
         post_ema_carry_kernel<<<dim3((p.B + 127) / 128, p.channels), blk, 0, h->stream>>>(
-            p, (const float*)h->ema_local.p, (float*)h->ema_carry.p, n_chunks,
+            p, (const float*)h->ema_local.p, (float*)h->ema_carry.p, (int)n_chunks,
             (float)std::pow((double)p.smoothing, (double)kPostChunk),
             (float)std::pow((double)p.smoothing, (double)last));
         h->launches += 2;
         carry_in = (const float*)h->ema_carry.p;
     }
-    post_emit_kernel<<<grd, blk, 0, h->stream>>>(p, carry_in, n_chunks);
+    post_emit_kernel<<<grd, blk, 0, h->stream>>>(p, carry_in, (int)n_chunks, chunk_cols);
+    ++h->launches;
+    {
+        ems_status s = clear_flags(h, p.F, p.col_begin, p.col_end, p.B);
+        if (s != EMS_OK) return s;
+    }
+    EMS_CUDA(h, cudaGetLastError());
+    return EMS_OK;
+}
+
+// The accumulator [channels][F][B] and its dirty flags [channels][F][NB].  Both are all zero
+// between calls: deposits flag the 64-bin blocks they touch and the emit pass clears exactly
+// those, so no call pays a 22 GB memset.  A call that fails midway leaves acc_clean false
+// and the next one starts with a full clear.
+static ems_status prepare_acc(ems_handle* h, size_t cells, size_t rows, int B) {
+    const bool det = h->prm.flags & EMS_FLAG_DETERMINISTIC;
+    const size_t need = cells * (det ? 8 : 4), need_f = rows * flag_blocks(B);
+    if (h->acc.bytes < need || h->flags.bytes < need_f) h->acc_clean = false;
+    ems_status s;
+    if ((s = ensure(h, h->acc, need)) != EMS_OK) return s;
+    if ((s = ensure(h, h->flags, need_f)) != EMS_OK) return s;
+    if (!h->acc_clean) {
+        EMS_CUDA(h, cudaMemsetAsync(h->acc.p, 0, h->acc.bytes, h->stream));
+        EMS_CUDA(h, cudaMemsetAsync(h->flags.p, 0, h->flags.bytes, h->stream));
+    }
+    h->acc_clean = false;   // until the post-pass has covered every column of this call
+    return EMS_OK;
+}
+
+// Clears the dirty flags of columns [c0, c1) of every channel after their emit pass.
+static ems_status clear_flags(ems_handle* h, long long F, long long c0, long long c1, int B) {
+    const int rows = flag_blocks(B) * h->prm.channels;
+    if (c0 == 0 && c1 == F) {
+        EMS_CUDA(h, cudaMemsetAsync(h->flags.p, 0, (size_t)rows * F, h->stream));
+        return EMS_OK;
+    }
+    long long blocks = ((c1 - c0) * rows + 255) / 256;
+    if (blocks > 4096) blocks = 4096;
+    clear_flags_kernel<<<(unsigned)blocks, 256, 0, h->stream>>>((unsigned char*)h->flags.p, F, c0, c1, rows);
     ++h->launches;
     EMS_CUDA(h, cudaGetLastError());
     return EMS_OK;
@@ -450,7 +510,7 @@ ems_status ems_create(const ems_params* params, ems_handle** out) {
 ems_status ems_destroy(ems_handle* h) {
     if (!h) return EMS_ERR_INVALID_ARG;
     if (h->stream) cudaStreamSynchronize(h->stream);
-    for (DevBuf* b : {&h->acc, &h->carry, &h->ema_local, &h->ema_carry, &h->host_pcm,
+    for (DevBuf* b : {&h->acc, &h->flags, &h->carry, &h->ema_local, &h->ema_carry, &h->host_pcm,
                       &h->host_idx, &h->host_grid, &h->big_scratch})
         if (b->p) cudaFree(b->p);
     stream_free(h);
@@ -529,21 +589,22 @@ ems_status ems_scatter_points(ems_handle* h, const float* dt_cols, const float* 
     const int B = h->prm.n_fft / 2 + 1, C = h->prm.channels;
     const bool det = h->prm.flags & EMS_FLAG_DETERMINISTIC;
     const size_t cells = (size_t)C * F * B;
-    ems_status s = ensure(h, h->acc, cells * (det ? 8 : 4));
+    ems_status s = prepare_acc(h, cells, (size_t)C * F, B);
     if (s != EMS_OK) return s;
     if ((s = reset_carry(h)) != EMS_OK) return s;
     stage_begin(h, EMS_STAGE_SCATTER);
-    EMS_CUDA(h, cudaMemsetAsync(h->acc.p, 0, cells * (det ? 8 : 4), h->stream));
     long long blocks = (long long)((cells + 255) / 256);
     const long long cap = (long long)h->sm_count * 32;
     if (blocks > cap) blocks = cap;
     scatter_points_kernel<<<(unsigned)blocks, 256, 0, h->stream>>>(dt_cols, dk_bins, energy,
-                                                                  h->acc.p, det, F, B, C);
+                                                                  h->acc.p, det,
+                                                                  (unsigned char*)h->flags.p, F, B, C);
     ++h->launches;
     EMS_CUDA(h, cudaGetLastError());
     stage_end(h, EMS_STAGE_SCATTER);
     stage_begin(h, EMS_STAGE_POST);
     if ((s = run_post(h, make_post(h, F, grid, index))) != EMS_OK) return s;
+    h->acc_clean = true;
     stage_end(h, EMS_STAGE_POST);
     return finish(h);
 }
@@ -559,17 +620,17 @@ ems_status ems_process_grid(ems_handle* h, const float* pcm, size_t S, float* gr
     const int B = h->prm.n_fft / 2 + 1, C = h->prm.channels;
     const bool det = h->prm.flags & EMS_FLAG_DETERMINISTIC;
     const size_t cells = (size_t)C * F * B;
-    ems_status s = ensure(h, h->acc, cells * (det ? 8 : 4));
+    ems_status s = prepare_acc(h, cells, (size_t)C * F, B);
     if (s != EMS_OK) return s;
     if ((s = reset_carry(h)) != EMS_OK) return s;
     StftArgs a = make_args(h, pcm, S, F);
-    a.acc = h->acc.p; a.mode = det ? kDepositU64 : kDepositF32;
+    a.acc = h->acc.p; a.flags = (unsigned char*)h->flags.p; a.mode = det ? kDepositU64 : kDepositF32;
     stage_begin(h, EMS_STAGE_POINTS);
-    EMS_CUDA(h, cudaMemsetAsync(h->acc.p, 0, cells * (det ? 8 : 4), h->stream));
     if ((s = launch_stft(h, a)) != EMS_OK) return s;
     stage_end(h, EMS_STAGE_POINTS);
     stage_begin(h, EMS_STAGE_POST);
     if ((s = run_post(h, make_post(h, F, grid, index))) != EMS_OK) return s;
+    h->acc_clean = true;
     stage_end(h, EMS_STAGE_POST);
     return finish(h);
 }
@@ -587,14 +648,13 @@ ems_status ems_process_host(ems_handle* h, const float* pcm_host, size_t S, floa
     const size_t cells = (size_t)C * F * B;
     ems_status s;
     if ((s = ensure(h, h->host_pcm, (size_t)C * S * sizeof(float))) != EMS_OK) return s;
-    if ((s = ensure(h, h->acc, cells * (det ? 8 : 4))) != EMS_OK) return s;
+    if ((s = prepare_acc(h, cells, (size_t)C * F, B)) != EMS_OK) return s;
     if (index_host && (s = ensure(h, h->host_idx, cells)) != EMS_OK) return s;
     if (grid_host && (s = ensure(h, h->host_grid, cells * sizeof(float))) != EMS_OK) return s;
     if ((s = reset_carry(h)) != EMS_OK) return s;
     float* pcm_dev = (float*)h->host_pcm.p;
     uint8_t* idx_dev = index_host ? (uint8_t*)h->host_idx.p : nullptr;
     float* grid_dev = grid_host ? (float*)h->host_grid.p : nullptr;
-    EMS_CUDA(h, cudaMemsetAsync(h->acc.p, 0, cells * (det ? 8 : 4), h->stream));
 
     // Frame chunks: H2D of chunk c+1 overlaps the kernels of chunk c, whose finished
     // columns (those no later frame can reach: col < f_end - R) go back while c+1 runs.
@@ -631,7 +691,7 @@ ems_status ems_process_host(ems_handle* h, const float* pcm_host, size_t S, floa
         cudaStreamWaitEvent(h->stream, ev_in[c], 0);
         StftArgs a = make_args(h, pcm_dev, S, F);
         a.f_begin = f0; a.f_end = f1;
-        a.acc = h->acc.p; a.mode = det ? kDepositU64 : kDepositF32;
+        a.acc = h->acc.p; a.flags = (unsigned char*)h->flags.p; a.mode = det ? kDepositU64 : kDepositF32;
         if ((rs = launch_stft(h, a)) != EMS_OK) break;
         const long long col_end = (f1 == F) ? F : std::max(cols_done, f1 - R);
         PostArgs p = make_post(h, F, grid_dev, idx_dev);
@@ -659,6 +719,7 @@ ems_status ems_process_host(ems_handle* h, const float* pcm_host, size_t S, floa
     if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess)
         return fail(h, EMS_ERR_CUDA, "process_host: %s",
                     cudaGetErrorString(e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3)));
+    h->acc_clean = true;
     return EMS_OK;
 }
 

@@ -11,7 +11,7 @@ namespace ems {
 __global__ void __launch_bounds__(256)
 scatter_points_kernel(const float* __restrict__ dt_cols, const float* __restrict__ dk_bins,
                       const float* __restrict__ energy, void* __restrict__ acc, int acc_is_u64,
-                      long long F, int B, int channels) {
+                      unsigned char* __restrict__ flags, long long F, int B, int channels) {
     const long long total = (long long)channels * F * B;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
@@ -30,6 +30,7 @@ scatter_points_kernel(const float* __restrict__ dt_cols, const float* __restrict
                       __float2ull_rn(e * kFixScale));
         else
             atomicAdd(reinterpret_cast<float*>(acc) + o, e);
+        flags[flag_index((int)ch, F, B, col, row)] = 1;
     }
 }
 
@@ -49,21 +50,43 @@ __device__ __forceinline__ uint8_t colour_index(float E, const PostArgs& a) {
     return (uint8_t)fminf(fmaxf(v, 0.f), 255.f);
 }
 
+// Load a cell for the emit pass and leave it zero: the accumulator is clean again when the
+// post-pass has covered every column, so no call ever memsets it (22 GB at configs[2]).
+__device__ __forceinline__ float acc_take(void* acc, int is_u64, long long o) {
+    if (is_u64) {
+        unsigned long long* p = reinterpret_cast<unsigned long long*>(acc) + o;
+        const unsigned long long v = *p;
+        *p = 0ull;
+        return __double2float_rn(__ull2double_rn(v) * kFixScaleInv);
+    }
+    float* p = reinterpret_cast<float*>(acc) + o;
+    const float v = *p;
+    *p = 0.f;
+    return v;
+}
+
+__device__ __forceinline__ void acc_zero(void* acc, int is_u64, long long o) {
+    if (is_u64) reinterpret_cast<unsigned long long*>(acc)[o] = 0ull;
+    else reinterpret_cast<float*>(acc)[o] = 0.f;
+}
+
 constexpr int kPostChunk = 256;   // columns per thread in the EMA scan
+constexpr int kPostTile = 8;      // columns per thread when there is no recurrence along time
 
 // Smoothing pass A: per (channel, chunk, bin) the EMA of the chunk from a zero carry;
 // only the chunk's last value is kept.  local_end: [channels][n_chunks][B].
 __global__ void __launch_bounds__(128)
 post_ema_local_kernel(const PostArgs a, float* __restrict__ local_end, int n_chunks) {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    const int chunk = blockIdx.y, ch = blockIdx.z;
+    const int k = blockIdx.y * blockDim.x + threadIdx.x;
+    const int chunk = blockIdx.x, ch = blockIdx.z;
     if (k >= a.B) return;
     const long long c0 = a.col_begin + (long long)chunk * kPostChunk;
     const long long c1 = min(c0 + (long long)kPostChunk, a.col_end);
     const float w = a.weight[k], s = a.smoothing, oms = 1.0f - a.smoothing;
     float y = 0.f;
+    const unsigned char* fl = a.flags + ((long long)ch * a.NB + (k >> kFlagShift)) * a.F;
     for (long long c = c0; c < c1; ++c) {
-        const float E = acc_load(a.acc, a.acc_is_u64, ((long long)ch * a.F + c) * a.B + k) * w;
+        const float E = fl[c] ? acc_load(a.acc, a.acc_is_u64, ((long long)ch * a.F + c) * a.B + k) * w : 0.f;
         y = s * y + oms * E;
     }
     local_end[((long long)ch * n_chunks + chunk) * a.B + k] = y;
@@ -88,24 +111,103 @@ post_ema_carry_kernel(const PostArgs a, const float* __restrict__ local_end,
 }
 
 // Pass C (the only pass when smoothing == 0): grid fp32 and colour index.
-__global__ void __launch_bounds__(128)
-post_emit_kernel(const PostArgs a, const float* __restrict__ carry_in, int n_chunks) {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    const int chunk = blockIdx.y, ch = blockIdx.z;
+__global__ void __launch_bounds__(128, 8)
+post_emit_kernel(const PostArgs a, const float* __restrict__ carry_in, int n_chunks, int chunk_cols) {
+    const int k = blockIdx.y * blockDim.x + threadIdx.x;
+    const int chunk = blockIdx.x, ch = blockIdx.z;
     if (k >= a.B) return;
-    const long long c0 = a.col_begin + (long long)chunk * kPostChunk;
-    const long long c1 = min(c0 + (long long)kPostChunk, a.col_end);
+    const long long c0 = a.col_begin + (long long)chunk * chunk_cols;
+    const long long c1 = min(c0 + (long long)chunk_cols, a.col_end);
     const float w = a.weight[k], s = a.smoothing, oms = 1.0f - a.smoothing;
     float y = carry_in ? carry_in[((long long)ch * n_chunks + chunk) * a.B + k] : 0.f;
-    for (long long c = c0; c < c1; ++c) {
-        const long long o = ((long long)ch * a.F + c) * a.B + k;
-        const float G = acc_load(a.acc, a.acc_is_u64, o);
-        if (a.grid) a.grid[o] = G;
-        if (a.index) {
-            float E = G * w;
-            if (s > 0.f) { y = s * y + oms * E; E = y; }
-            a.index[o] = colour_index(E, a);
+    const unsigned char* fl = a.flags + ((long long)ch * a.NB + (k >> kFlagShift)) * a.F;
+    constexpr int kTile = kPostTile;   // columns whose flags and cells are fetched together
+    for (long long cb = c0; cb < c1; cb += kTile) {
+        const int nt = (int)min((long long)kTile, c1 - cb);
+        const long long o0 = ((long long)ch * a.F + cb) * a.B + k;
+        unsigned char f[kTile];
+#pragma unroll
+        for (int i = 0; i < kTile; ++i) f[i] = (i < nt) ? fl[cb + i] : 0;
+        float G[kTile];
+        // clean 64-bin blocks (no deposit since the last post-pass) are neither read nor cleared
+#pragma unroll
+        for (int i = 0; i < kTile; ++i)
+            G[i] = f[i] ? acc_take(a.acc, a.acc_is_u64, o0 + (long long)i * a.B) : 0.f;
+#pragma unroll
+        for (int i = 0; i < kTile; ++i) {
+            if (i < nt) {
+                const long long o = o0 + (long long)i * a.B;
+                if (a.grid) a.grid[o] = G[i];
+                if (a.index) {
+                    float E = G[i] * w;
+                    if (s > 0.f) { y = s * y + oms * E; E = y; }
+                    a.index[o] = colour_index(E, a);
+                }
+            }
         }
+    }
+}
+
+// Post-pass without smoothing: every cell is independent and the image is mostly empty, so
+// the outputs are zero-filled by memset and this kernel visits only the dirty 64-bin blocks.
+// One warp reads 32 consecutive column flags of a (channel, bin block) row; each flagged
+// block is then shaped by the whole warp (2 bins per lane, coalesced), its accumulator cells
+// and its flag are cleared.  grid: (ceil(ncols/256), channels*NB), 256 threads.
+__global__ void __launch_bounds__(256)
+post_sparse_kernel(const PostArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int r = blockIdx.y;                               // ch * NB + blk
+    const int ch = r / a.NB, blk = r - ch * a.NB;
+    const long long cw = a.col_begin + ((long long)blockIdx.x * 8 + (threadIdx.x >> 5)) * 32;
+    if (cw >= a.col_end) return;
+    unsigned char* fl = a.flags + (long long)r * a.F;
+    const long long c = cw + lane;
+    unsigned mask = __ballot_sync(0xffffffffu, c < a.col_end && fl[c] != 0);
+    const int k0 = (blk << kFlagShift) + lane, k1 = k0 + 32;
+    const float w0 = k0 < a.B ? a.weight[k0] : 0.f, w1 = k1 < a.B ? a.weight[k1] : 0.f;
+    constexpr int kBatch = 4;     // flagged blocks in flight per warp: 8 independent loads per lane
+    while (mask) {
+        int js[kBatch];
+#pragma unroll
+        for (int b = 0; b < kBatch; ++b) {
+            js[b] = mask ? __ffs(mask) - 1 : -1;
+            mask &= mask - 1;
+        }
+        float G0[kBatch], G1[kBatch];
+#pragma unroll
+        for (int b = 0; b < kBatch; ++b) {
+            const long long row = ((long long)ch * a.F + cw + max(js[b], 0)) * a.B;
+            const bool on = js[b] >= 0;
+            G0[b] = (on && k0 < a.B) ? acc_load(a.acc, a.acc_is_u64, row + k0) : 0.f;
+            G1[b] = (on && k1 < a.B) ? acc_load(a.acc, a.acc_is_u64, row + k1) : 0.f;
+        }
+#pragma unroll
+        for (int b = 0; b < kBatch; ++b) {
+            if (js[b] < 0) continue;
+            const long long row = ((long long)ch * a.F + cw + js[b]) * a.B;
+            if (k0 < a.B) {
+                acc_zero(a.acc, a.acc_is_u64, row + k0);
+                if (a.grid) a.grid[row + k0] = G0[b];
+                if (a.index) a.index[row + k0] = colour_index(G0[b] * w0, a);
+            }
+            if (k1 < a.B) {
+                acc_zero(a.acc, a.acc_is_u64, row + k1);
+                if (a.grid) a.grid[row + k1] = G1[b];
+                if (a.index) a.index[row + k1] = colour_index(G1[b] * w1, a);
+            }
+            if (lane == 0) fl[cw + js[b]] = 0;
+        }
+    }
+}
+
+// Clears the dirty flags of columns [c0, c1) of every (channel, bin block) row.
+__global__ void clear_flags_kernel(unsigned char* __restrict__ flags, long long F, long long c0,
+                                   long long c1, int rows) {
+    const long long n = c1 - c0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n * rows;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / n;
+        flags[r * F + c0 + (i - r * n)] = 0;
     }
 }
 

@@ -113,6 +113,7 @@ __device__ __forceinline__ void reassign_emit(const StftArgs& a, int ch,
                       __float2ull_rn(e * kFixScale));
         else
             atomicAdd(reinterpret_cast<float*>(a.acc) + o, e);
+        if (a.flags) a.flags[flag_index(ch, a.F, B, col, row)] = 1;
     }
 }
 

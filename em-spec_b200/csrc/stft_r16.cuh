@@ -228,6 +228,7 @@ __device__ __forceinline__ void bin_emit(const StftArgs& a, const FrameCtx& fc, 
             atomicAdd(reinterpret_cast<unsigned long long*>(a.acc) + o, __float2ull_rn(e * kFixScale));
         else
             atomicAdd(reinterpret_cast<float*>(a.acc) + o, e);
+        if (a.flags) a.flags[flag_index(fc.ch, a.F, B, fc.f + (long long)rc, k + (int)rintf(dk))] = 1;
     }
 }
 
