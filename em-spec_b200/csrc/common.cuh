@@ -39,6 +39,11 @@ struct StftArgs {
     float         inv_hop;
     int           mode;       // DepositMode
     int           reassign;   // 0: plain spectrogram columns
+    int           rows;       // output rows per column R (B, or display_rows)
+    int           warp_mode;  // 0: row = k + rint(dk); 1: linear axis resample; 2: log1p warp
+    float         warp_a;     // a = 10^(2 freq_scale) - 1
+    float         warp_c;     // (R-1)/log1p(a)  (mode 2)  or  (R-1)  (mode 1)
+    float         inv_half;   // 2 / n_fft
     long long     samp_off;   // frame f starts at sample f*hop + samp_off of its channel
     int           ring;       // > 0: the accumulator is a ring of `ring` columns per channel (streaming)
     int           stream_M;   // streaming: pushes per ring lap = ceil(n_fft / hop)
@@ -63,14 +68,23 @@ constexpr int kFlagShift = 6;                              // one dirty flag per
 __host__ __device__ constexpr int flag_blocks(int B) { return (B + 63) >> kFlagShift; }
 // Flags are column-contiguous per bin block ([channels][NB][F]) so the post-pass reads the
 // flags of 16 consecutive columns from one cache line.
-__device__ __forceinline__ long long flag_index(int ch, long long F, int B, long long col, int row) {
-    return ((long long)ch * flag_blocks(B) + (row >> kFlagShift)) * F + col;
+__device__ __forceinline__ long long flag_index(int ch, long long F, int rows, long long col, int row) {
+    return ((long long)ch * flag_blocks(rows) + (row >> kFlagShift)) * F + col;
 }
 
-// Accumulator cell of (channel, column, bin): linear [channels][F][B] or a column ring.
-__device__ __forceinline__ long long acc_cell(const StftArgs& a, int ch, long long col, int row, int B) {
-    return a.ring ? ((long long)ch * a.ring + (col % a.ring)) * B + row
-                  : ((long long)ch * a.F + col) * B + row;
+// Accumulator cell of (channel, column, row): linear [channels][F][R] or a column ring.
+__device__ __forceinline__ long long acc_cell(const StftArgs& a, int ch, long long col, int row) {
+    return a.ring ? ((long long)ch * a.ring + (col % a.ring)) * a.rows + row
+                  : ((long long)ch * a.F + col) * a.rows + row;
+}
+
+// Output row of a point at reassigned frequency wh = k + dk [bins]
+// ("Frequency Scale", /root/reference/README.md:48; oracle/reassign_oracle.py::output_row).
+__device__ __forceinline__ int out_row(int warp_mode, float warp_a, float warp_c, float inv_half,
+                                       int k, float dk, float wh) {
+    if (warp_mode == 0) return k + (int)rintf(dk);
+    const float x = wh * inv_half;
+    return (int)rintf((warp_mode == 2 ? log1pf(warp_a * x) : x) * warp_c);
 }
 
 struct PostArgs {
@@ -85,7 +99,7 @@ struct PostArgs {
     long long     F;
     long long     col_begin;
     long long     col_end;
-    int           B;
+    int           B;          // output rows per column R
     int           channels;
     float         smoothing;
     float         db_floor;   // TOP_DB - range

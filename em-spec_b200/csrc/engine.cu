@@ -101,25 +101,42 @@ static bool valid_params(const ems_params& p) {
     if (!(p.db_range > 0.f) || !(p.gain >= 0.f) || !(p.low_end_boost > 0.f)) return false;
     if (!(p.smoothing >= 0.f) || !(p.smoothing < 1.f)) return false;
     if (!std::isfinite(p.noise_gate_db)) return false;
+    if (p.display_rows < 0 || p.display_rows == 1 || p.display_rows > 65536) return false;
+    if (!(p.freq_scale >= 0.f) || !(p.freq_scale <= 4.f)) return false;
     return true;
 }
 
 static int ilog2(int n) { int l = 0; while ((1 << l) < n) ++l; return l; }
 
+static int rows_of(const ems_params& p);
+static double warp_a_of(const ems_params& p);
+
+// weight[r] = gain^2 * w_low(f_r), f_r = centre frequency of output row r
 static ems_status upload_display(ems_handle* h) {
-    const int B = h->prm.n_fft / 2 + 1;
-    std::vector<float> w(B);
+    const int R = rows_of(h->prm);
+    std::vector<float> w(R);
     const double g2 = (double)h->prm.gain * (double)h->prm.gain;
-    for (int k = 0; k < B; ++k) {
-        const double f = (double)k * (double)h->prm.sample_rate / (double)h->prm.n_fft;
-        const double r = f / kLowEndCornerHz;
-        w[k] = (float)(g2 * (1.0 + ((double)h->prm.low_end_boost - 1.0) / (1.0 + r * r)));
+    const double nyq = 0.5 * (double)h->prm.sample_rate, a = warp_a_of(h->prm);
+    for (int r = 0; r < R; ++r) {
+        double f;
+        if (h->prm.display_rows > 0) {
+            const double u = (double)r / (double)(R - 1);
+            f = nyq * (a > 1e-6 ? std::expm1(u * std::log1p(a)) / a : u);
+        } else {
+            f = (double)r * (double)h->prm.sample_rate / (double)h->prm.n_fft;
+        }
+        const double q = f / kLowEndCornerHz;
+        w[r] = (float)(g2 * (1.0 + ((double)h->prm.low_end_boost - 1.0) / (1.0 + q * q)));
     }
-    EMS_CUDA(h, cudaMemcpyAsync(h->weight, w.data(), B * sizeof(float), cudaMemcpyHostToDevice,
+    EMS_CUDA(h, cudaMemcpyAsync(h->weight, w.data(), R * sizeof(float), cudaMemcpyHostToDevice,
                                 h->stream));
     EMS_CUDA(h, cudaStreamSynchronize(h->stream));
     return EMS_OK;
 }
+
+// Output rows per column: one per bin, or display_rows on the warped frequency axis.
+static int rows_of(const ems_params& p) { return p.display_rows > 0 ? p.display_rows : p.n_fft / 2 + 1; }
+static double warp_a_of(const ems_params& p) { return std::pow(10.0, 2.0 * (double)p.freq_scale) - 1.0; }
 
 static long long frames_of(const ems_params& p, size_t S) {
     return S < (size_t)p.n_fft ? 0 : 1 + (long long)((S - (size_t)p.n_fft) / (size_t)p.hop);
@@ -214,6 +231,14 @@ static StftArgs make_args(ems_handle* h, const float* pcm, size_t S, long long F
     a.gate_lin = (float)std::pow(10.0, (double)h->prm.noise_gate_db / 10.0);
     a.inv_hop = 1.0f / (float)h->prm.hop;
     a.reassign = (h->prm.flags & EMS_FLAG_REASSIGN) ? 1 : 0;
+    a.rows = rows_of(h->prm);
+    a.inv_half = 2.0f / (float)h->prm.n_fft;
+    if (h->prm.display_rows > 0) {
+        const double wa = warp_a_of(h->prm);
+        a.warp_mode = wa > 1e-6 ? 2 : 1;
+        a.warp_a = (float)wa;
+        a.warp_c = (float)(wa > 1e-6 ? (a.rows - 1) / std::log1p(wa) : (double)(a.rows - 1));
+    }
     return a;
 }
 
@@ -221,12 +246,12 @@ static PostArgs make_post(ems_handle* h, long long F, float* grid, uint8_t* inde
     PostArgs p{};
     p.acc = h->acc.p;
     p.flags = (unsigned char*)h->flags.p;
-    p.NB = flag_blocks(h->prm.n_fft / 2 + 1);
+    p.NB = flag_blocks(rows_of(h->prm));
     p.acc_is_u64 = (h->prm.flags & EMS_FLAG_DETERMINISTIC) ? 1 : 0;
     p.grid = grid; p.index = index; p.weight = h->weight;
     p.carry = (float*)h->carry.p;
     p.F = F; p.col_begin = 0; p.col_end = F;
-    p.B = h->prm.n_fft / 2 + 1; p.channels = h->prm.channels;
+    p.B = rows_of(h->prm); p.channels = h->prm.channels;
     p.smoothing = h->prm.smoothing;
     p.db_floor = (float)(kTopDb - (double)h->prm.db_range);
     p.inv_range = 255.0f / h->prm.db_range;
@@ -322,7 +347,7 @@ static ems_status clear_flags(ems_handle* h, long long F, long long c0, long lon
 }
 
 static ems_status reset_carry(ems_handle* h) {
-    const size_t bytes = (size_t)h->prm.channels * (h->prm.n_fft / 2 + 1) * sizeof(float);
+    const size_t bytes = (size_t)h->prm.channels * rows_of(h->prm) * sizeof(float);
     ems_status s = ensure(h, h->carry, bytes);
     if (s != EMS_OK) return s;
     EMS_CUDA(h, cudaMemsetAsync(h->carry.p, 0, bytes, h->stream));
@@ -355,7 +380,7 @@ static void stream_free(ems_handle* h) {
 
 static ems_status stream_zero(ems_handle* h) {
     auto& st = h->st;
-    const int N = h->prm.n_fft, C = h->prm.channels, B = N / 2 + 1;
+    const int C = h->prm.channels, B = rows_of(h->prm);
     EMS_CUDA(h, cudaMemsetAsync(st.sstate, 0, sizeof(long long), h->stream));
     EMS_CUDA(h, cudaMemsetAsync(st.ring, 0, sizeof(float) * C * 2 * st.Lr, h->stream));
     EMS_CUDA(h, cudaMemsetAsync(st.acc, 0, st.acc_bytes, h->stream));
@@ -367,7 +392,7 @@ static ems_status stream_zero(ems_handle* h) {
 
 static ems_status stream_init(ems_handle* h) {
     auto& st = h->st;
-    const int N = h->prm.n_fft, H = h->prm.hop, C = h->prm.channels, B = N / 2 + 1;
+    const int N = h->prm.n_fft, H = h->prm.hop, C = h->prm.channels, B = rows_of(h->prm);
     const bool det = h->prm.flags & EMS_FLAG_DETERMINISTIC;
     st.M = (N + H - 1) / H;
     st.Lr = st.M * H;
@@ -384,7 +409,7 @@ static ems_status stream_init(ems_handle* h) {
     EMS_CUDA(h, cudaMallocHost(&st.out_pin, (size_t)C * B));
     ems_status s = stream_zero(h);
     if (s != EMS_OK) return s;
-    if (N == 32768 && (s = ensure(h, h->big_scratch, (size_t)h->sm_count * 2 * B * sizeof(float2))) != EMS_OK) return s;
+    if (N == 32768 && (s = ensure(h, h->big_scratch, (size_t)h->sm_count * 2 * (N / 2 + 1) * sizeof(float2))) != EMS_OK) return s;
     st.ready = true;
     return EMS_OK;
 }
@@ -394,7 +419,7 @@ static ems_status stream_init(ems_handle* h) {
 // counter advance, D2H of that column.
 static ems_status stream_capture(ems_handle* h) {
     auto& st = h->st;
-    const int N = h->prm.n_fft, H = h->prm.hop, C = h->prm.channels, B = N / 2 + 1;
+    const int H = h->prm.hop, C = h->prm.channels, B = rows_of(h->prm);
     const bool det = h->prm.flags & EMS_FLAG_DETERMINISTIC;
     StreamArgs sa{};
     sa.sstate = st.sstate; sa.in = st.in_dev; sa.ring = st.ring; sa.acc = st.acc;
@@ -457,6 +482,7 @@ ems_status ems_default_params(ems_params* p) {
     p->db_range = 58.f; p->gain = 3.5f; p->low_end_boost = 3.9f; p->smoothing = 0.f;
     p->noise_gate_db = -65.f;
     p->flags = EMS_FLAG_REASSIGN | EMS_FLAG_DETERMINISTIC;
+    p->display_rows = 0; p->freq_scale = 1.0f;
     return EMS_OK;
 }
 
@@ -484,10 +510,10 @@ ems_status ems_create(const ems_params* params, ems_handle** out) {
         for (auto& x : e)
             if (cudaEventCreate(&x) != cudaSuccess) return bail(EMS_ERR_CUDA);
 
-    const int N = params->n_fft, B = N / 2 + 1;
+    const int N = params->n_fft;
     if (cudaMalloc(&h->win, sizeof(float4) * N) != cudaSuccess ||
         cudaMalloc(&h->tw, sizeof(float2) * N) != cudaSuccess ||
-        cudaMalloc(&h->weight, sizeof(float) * B) != cudaSuccess)
+        cudaMalloc(&h->weight, sizeof(float) * rows_of(*params)) != cudaSuccess)
         return bail(EMS_ERR_NOMEM);
     std::vector<float4> win(N);
     std::vector<float2> tw(N);
@@ -530,8 +556,9 @@ ems_status ems_destroy(ems_handle* h) {
 ems_status ems_update_display(ems_handle* h, const ems_params* p) {
     if (!h || !p) return EMS_ERR_INVALID_ARG;
     if (!valid_params(*p) || p->n_fft != h->prm.n_fft || p->hop != h->prm.hop ||
-        p->channels != h->prm.channels || p->sample_rate != h->prm.sample_rate)
-        return fail(h, EMS_ERR_INVALID_ARG, "n_fft/hop/channels/sample_rate need a new handle");
+        p->channels != h->prm.channels || p->sample_rate != h->prm.sample_rate ||
+        p->display_rows != h->prm.display_rows || p->freq_scale != h->prm.freq_scale)
+        return fail(h, EMS_ERR_INVALID_ARG, "n_fft/hop/channels/sample_rate/display_rows/freq_scale need a new handle");
     h->prm = *p;
     if (h->st.graph) { cudaGraphExecDestroy(h->st.graph); h->st.graph = nullptr; }   // scalars are baked into the graph
     return upload_display(h);
@@ -552,6 +579,12 @@ ems_status ems_get_stream(ems_handle* h, void** s) {
 ems_status ems_synchronize(ems_handle* h) {
     if (!h) return EMS_ERR_INVALID_ARG;
     EMS_CUDA(h, cudaStreamSynchronize(h->stream));
+    return EMS_OK;
+}
+
+ems_status ems_output_rows(const ems_handle* h, size_t* rows) {
+    if (!h || !rows) return EMS_ERR_INVALID_ARG;
+    *rows = (size_t)rows_of(h->prm);
     return EMS_OK;
 }
 
@@ -586,19 +619,20 @@ ems_status ems_scatter_points(ems_handle* h, const float* dt_cols, const float* 
     if (!dt_cols || !dk_bins || !energy || (!grid && !index))
         return fail(h, EMS_ERR_INVALID_ARG, "null buffer");
     const long long F = (long long)n_frames;
-    const int B = h->prm.n_fft / 2 + 1, C = h->prm.channels;
+    const int B = h->prm.n_fft / 2 + 1, C = h->prm.channels, R = rows_of(h->prm);
     const bool det = h->prm.flags & EMS_FLAG_DETERMINISTIC;
-    const size_t cells = (size_t)C * F * B;
-    ems_status s = prepare_acc(h, cells, (size_t)C * F, B);
+    const size_t cells = (size_t)C * F * R, points = (size_t)C * F * B;
+    ems_status s = prepare_acc(h, cells, (size_t)C * F, R);
     if (s != EMS_OK) return s;
     if ((s = reset_carry(h)) != EMS_OK) return s;
     stage_begin(h, EMS_STAGE_SCATTER);
-    long long blocks = (long long)((cells + 255) / 256);
+    long long blocks = (long long)((points + 255) / 256);
     const long long cap = (long long)h->sm_count * 32;
     if (blocks > cap) blocks = cap;
-    scatter_points_kernel<<<(unsigned)blocks, 256, 0, h->stream>>>(dt_cols, dk_bins, energy,
-                                                                  h->acc.p, det,
-                                                                  (unsigned char*)h->flags.p, F, B, C);
+    const StftArgs wa = make_args(h, nullptr, 0, F);   // carries the frequency-axis warp
+    scatter_points_kernel<<<(unsigned)blocks, 256, 0, h->stream>>>(
+        dt_cols, dk_bins, energy, h->acc.p, det, (unsigned char*)h->flags.p, F, B, C, R,
+        wa.warp_mode, wa.warp_a, wa.warp_c, wa.inv_half);
     ++h->launches;
     EMS_CUDA(h, cudaGetLastError());
     stage_end(h, EMS_STAGE_SCATTER);
@@ -617,10 +651,10 @@ ems_status ems_process_grid(ems_handle* h, const float* pcm, size_t S, float* gr
     for (bool& v : h->ev_valid) v = false;
     if (F == 0) return EMS_OK;
     if (!pcm || (!grid && !index)) return fail(h, EMS_ERR_INVALID_ARG, "null buffer");
-    const int B = h->prm.n_fft / 2 + 1, C = h->prm.channels;
+    const int C = h->prm.channels, R = rows_of(h->prm);
     const bool det = h->prm.flags & EMS_FLAG_DETERMINISTIC;
-    const size_t cells = (size_t)C * F * B;
-    ems_status s = prepare_acc(h, cells, (size_t)C * F, B);
+    const size_t cells = (size_t)C * F * R;
+    ems_status s = prepare_acc(h, cells, (size_t)C * F, R);
     if (s != EMS_OK) return s;
     if ((s = reset_carry(h)) != EMS_OK) return s;
     StftArgs a = make_args(h, pcm, S, F);
@@ -643,7 +677,7 @@ ems_status ems_process_host(ems_handle* h, const float* pcm_host, size_t S, floa
     for (bool& v : h->ev_valid) v = false;
     if (F == 0) return EMS_OK;
     if (!pcm_host || (!grid_host && !index_host)) return fail(h, EMS_ERR_INVALID_ARG, "null buffer");
-    const int N = h->prm.n_fft, H = h->prm.hop, B = N / 2 + 1, C = h->prm.channels;
+    const int N = h->prm.n_fft, H = h->prm.hop, B = rows_of(h->prm), C = h->prm.channels;   // B: output rows
     const bool det = h->prm.flags & EMS_FLAG_DETERMINISTIC;
     const size_t cells = (size_t)C * F * B;
     ems_status s;
@@ -744,7 +778,7 @@ ems_status ems_stream_push(ems_handle* h, const float* pcm_host, uint8_t* column
     ems_status s;
     if (!st.ready && (s = stream_init(h)) != EMS_OK) return s;
     if (!st.graph && (s = stream_capture(h)) != EMS_OK) return s;
-    const int N = h->prm.n_fft, H = h->prm.hop, C = h->prm.channels, B = N / 2 + 1;
+    const int H = h->prm.hop, C = h->prm.channels, B = rows_of(h->prm);
     memcpy(st.in_pin, pcm_host, sizeof(float) * H * C);
     EMS_CUDA(h, cudaGraphLaunch(st.graph, h->stream));
     h->launches += 4;

@@ -11,7 +11,8 @@ namespace ems {
 __global__ void __launch_bounds__(256)
 scatter_points_kernel(const float* __restrict__ dt_cols, const float* __restrict__ dk_bins,
                       const float* __restrict__ energy, void* __restrict__ acc, int acc_is_u64,
-                      unsigned char* __restrict__ flags, long long F, int B, int channels) {
+                      unsigned char* __restrict__ flags, long long F, int B, int channels,
+                      int rows, int warp_mode, float warp_a, float warp_c, float inv_half) {
     const long long total = (long long)channels * F * B;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
@@ -22,15 +23,16 @@ scatter_points_kernel(const float* __restrict__ dt_cols, const float* __restrict
         const long long ch = row_id / F;
         const long long f = row_id - ch * F;
         const long long col = f + (long long)rintf(__ldg(dt_cols + i));
-        const int row = k + (int)rintf(__ldg(dk_bins + i));
-        if (col < 0 || col >= F || row < 0 || row >= B) continue;   // caller-made points
-        const long long o = (ch * F + col) * B + row;
+        const float dk = __ldg(dk_bins + i);
+        const int row = out_row(warp_mode, warp_a, warp_c, inv_half, k, dk, (float)k + dk);
+        if (col < 0 || col >= F || row < 0 || row >= rows) continue;   // caller-made points
+        const long long o = (ch * F + col) * rows + row;
         if (acc_is_u64)
             atomicAdd(reinterpret_cast<unsigned long long*>(acc) + o,
                       __float2ull_rn(e * kFixScale));
         else
             atomicAdd(reinterpret_cast<float*>(acc) + o, e);
-        flags[flag_index((int)ch, F, B, col, row)] = 1;
+        flags[flag_index((int)ch, F, rows, col, row)] = 1;
     }
 }
 

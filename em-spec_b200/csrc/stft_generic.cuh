@@ -87,16 +87,15 @@ __device__ __forceinline__ void reassign_emit(const StftArgs& a, int ch,
     float dtc = 0.f, dk = 0.f;
     bool ok = e > a.gate_lin;
     long long col = f;
-    int row = k;
+    float wh = (float)k;
     if (a.reassign && ok) {
         const float inv = 1.0f / p2;
         const float dts = (B2.x * A2.x + B2.y * A2.y) * inv * (float)(N / 2);   // samples
         dk = (D2.y * A2.x - D2.x * A2.y) * inv * -0.5f;                          // bins
         dtc = dts * a.inv_hop;
-        const float wh = (float)k + dk;
+        wh = (float)k + dk;
         const float rc = rintf(dtc);
         col = f + (long long)rc;
-        row = k + (int)rintf(dk);
         ok = (fabsf(dts) <= (float)(N / 2)) && (wh >= 0.f) && (wh <= (float)(N / 2)) &&
              (col >= 0) && (col < a.F);
         if (!ok) { dtc = 0.f; dk = 0.f; }
@@ -107,13 +106,14 @@ __device__ __forceinline__ void reassign_emit(const StftArgs& a, int ch,
         a.dk_bins[o] = dk;
         a.energy[o] = ok ? e : 0.f;
     } else if (ok) {
-        const long long o = acc_cell(a, ch, col, row, B);
+        const int row = out_row(a.warp_mode, a.warp_a, a.warp_c, a.inv_half, k, dk, wh);
+        const long long o = acc_cell(a, ch, col, row);
         if (a.mode == kDepositU64)
             atomicAdd(reinterpret_cast<unsigned long long*>(a.acc) + o,
                       __float2ull_rn(e * kFixScale));
         else
             atomicAdd(reinterpret_cast<float*>(a.acc) + o, e);
-        if (a.flags) a.flags[flag_index(ch, a.F, B, col, row)] = 1;
+        if (a.flags) a.flags[flag_index(ch, a.F, a.rows, col, row)] = 1;
     }
 }
 

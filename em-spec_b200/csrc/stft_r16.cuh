@@ -191,7 +191,6 @@ template <int MODE>
 __device__ __forceinline__ void bin_emit(const StftArgs& a, const FrameCtx& fc, bool owner, int k,
                                          float kf, float2 zk, float2 zn, float2 yk, float2 yn,
                                          float2 w) {
-    constexpr int B = N / 2 + 1;
     const float2 A2 = make_float2(zk.x + zn.x, zk.y - zn.y);           // 2 X_h
     const float p2 = A2.x * A2.x + A2.y * A2.y;
     const float e = p2 * (float)(4.0 / ((double)N * (double)N));
@@ -201,7 +200,7 @@ __device__ __forceinline__ void bin_emit(const StftArgs& a, const FrameCtx& fc, 
         return;
     }
     bool ok = live;
-    float dtc = 0.f, dk = 0.f, rc = 0.f;
+    float dtc = 0.f, dk = 0.f, rc = 0.f, wh = kf;
     if (a.reassign) {
         const float2 B2 = make_float2(zk.y + zn.y, zn.x - zk.x);       // 2 X_th'
         const float2 E2 = make_float2(yk.x + yn.x, yk.y - yn.y);
@@ -213,7 +212,7 @@ __device__ __forceinline__ void bin_emit(const StftArgs& a, const FrameCtx& fc, 
         dk = (D2.y * A2.x - D2.x * A2.y) * inv * -0.5f;                          // bins
         dtc = dts * a.inv_hop;
         rc = rintf(dtc);
-        const float wh = kf + dk;
+        wh = kf + dk;
         ok = live && (fabsf(dts) <= (float)(N / 2)) && (wh >= 0.f) && (wh <= (float)(N / 2)) &&
              (rc >= fc.lo) && (rc <= fc.hi);
         dtc = ok ? dtc : 0.f;
@@ -222,13 +221,14 @@ __device__ __forceinline__ void bin_emit(const StftArgs& a, const FrameCtx& fc, 
     if (MODE == kStorePoints) {
         if (owner) { fc.pd[k] = dtc; fc.pk[k] = dk; fc.pe[k] = ok ? e : 0.f; }
     } else if (ok && owner) {
-        const long long o = a.ring ? acc_cell(a, fc.ch, fc.f + (long long)rc, k + (int)rintf(dk), B)
-                                   : fc.acc_row + (long long)((int)rc * B + k + (int)rintf(dk));
+        const int row = out_row(a.warp_mode, a.warp_a, a.warp_c, a.inv_half, k, dk, wh);
+        const long long col = fc.f + (long long)rc;
+        const long long o = acc_cell(a, fc.ch, col, row);
         if (MODE == kDepositU64)
             atomicAdd(reinterpret_cast<unsigned long long*>(a.acc) + o, __float2ull_rn(e * kFixScale));
         else
             atomicAdd(reinterpret_cast<float*>(a.acc) + o, e);
-        if (a.flags) a.flags[flag_index(fc.ch, a.F, B, fc.f + (long long)rc, k + (int)rintf(dk))] = 1;
+        if (a.flags) a.flags[flag_index(fc.ch, a.F, a.rows, col, row)] = 1;
     }
 }
 

@@ -34,6 +34,7 @@ class Params(C.Structure):
         ("channels", C.c_int32), ("db_range", C.c_float), ("gain", C.c_float),
         ("low_end_boost", C.c_float), ("smoothing", C.c_float),
         ("noise_gate_db", C.c_float), ("flags", C.c_uint32),
+        ("display_rows", C.c_int32), ("freq_scale", C.c_float),
     ]
 
 
@@ -50,6 +51,7 @@ _SIG = {
     "ems_set_stream": (C.c_int, [_VP, _VP]),
     "ems_get_stream": (C.c_int, [_VP, C.POINTER(_VP)]),
     "ems_synchronize": (C.c_int, [_VP]),
+    "ems_output_rows": (C.c_int, [_VP, C.POINTER(C.c_size_t)]),
     "ems_frame_count": (C.c_int, [_VP, C.c_size_t, C.POINTER(C.c_size_t)]),
     "ems_process_points": (C.c_int, [_VP, _FP, C.c_size_t, _FP, _FP, _FP, C.POINTER(C.c_size_t)]),
     "ems_process_grid": (C.c_int, [_VP, _FP, C.c_size_t, _FP, _U8P, C.POINTER(C.c_size_t)]),
@@ -128,6 +130,13 @@ class Engine:
     def n_bins(self) -> int:
         return self.params.n_fft // 2 + 1
 
+    @property
+    def n_rows(self) -> int:
+        """Output rows per column of grid / index / streamed columns (n_bins or display_rows)."""
+        n = C.c_size_t()
+        self._check(self.lib.ems_output_rows(self.h, C.byref(n)))
+        return n.value
+
     def frame_count(self, n_samples: int) -> int:
         n = C.c_size_t()
         self._check(self.lib.ems_frame_count(self.h, n_samples, C.byref(n)))
@@ -186,7 +195,7 @@ class Engine:
         pcm = self._pcm(pcm)
         S = pcm.shape[1]
         F = self.frame_count(S)
-        shape = (self.params.channels, F, self.n_bins)
+        shape = (self.params.channels, F, self.n_rows)
         if out is None:
             grid = torch.empty(shape, dtype=torch.float32, device=pcm.device) if want_grid else None
             idx = torch.empty(shape, dtype=torch.uint8, device=pcm.device) if want_index else None
@@ -199,7 +208,7 @@ class Engine:
     def scatter_points(self, dt, dk, en, want_grid=True, want_index=True):
         import torch
         F = en.shape[-2]
-        shape = (self.params.channels, F, self.n_bins)
+        shape = (self.params.channels, F, self.n_rows)
         grid = torch.empty(shape, dtype=torch.float32, device=en.device) if want_grid else None
         idx = torch.empty(shape, dtype=torch.uint8, device=en.device) if want_index else None
         self._check(self.lib.ems_scatter_points(self.h, _ptr(dt), _ptr(dk), _ptr(en), F,
@@ -214,7 +223,7 @@ class Engine:
         assert (not pcm_host.is_cuda) and pcm_host.dtype == torch.float32 and pcm_host.is_contiguous()
         S = pcm_host.shape[1]
         F = self.frame_count(S)
-        shape = (self.params.channels, F, self.n_bins)
+        shape = (self.params.channels, F, self.n_rows)
         pin = torch.cuda.is_available()
         if index_out is None:
             index_out = torch.empty(shape, dtype=torch.uint8, pin_memory=pin)
@@ -230,7 +239,7 @@ class Engine:
         self._check(self.lib.ems_stream_reset(self.h))
 
     def stream_push(self, pcm_host, column_host):
-        """pcm_host: CPU fp32 [hop*channels] interleaved; column_host: CPU u8 [channels][B].
+        """pcm_host: CPU fp32 [hop*channels] interleaved; column_host: CPU u8 [channels][n_rows].
         -> (ready: bool, column_index: int)"""
         ready, idx = C.c_int(0), C.c_int64(-1)
         self._check(self.lib.ems_stream_push(self.h, _ptr(pcm_host), _ptr(column_host),

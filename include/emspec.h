@@ -18,7 +18,8 @@
  *   - there is no CPU fallback: without a CUDA device ems_create fails with
  *     EMS_ERR_CUDA.
  *
- * Geometry: N = n_fft, H = hop, B = N/2+1 bins,
+ * Geometry: N = n_fft, H = hop, B = N/2+1 bins, R = output rows per column
+ *   (B, or display_rows when that is set),
  *   F = 0 if S < N else 1 + (S-N)/H frames per channel for S samples per channel.
  *   Frame f covers samples [f*H, f*H+N); column f of every output is centred there.
  */
@@ -32,7 +33,7 @@
 extern "C" {
 #endif
 
-#define EMS_ABI_VERSION 1
+#define EMS_ABI_VERSION 2
 
 typedef enum ems_status {
     EMS_OK = 0,
@@ -63,6 +64,12 @@ typedef struct ems_params {
     float    smoothing;     /* "Smoothing" README.md:50; EMA coefficient in [0,1)     (0.0)  */
     float    noise_gate_db; /* "Noise Gate" README.md:51; dB re full-scale sine       (-65)  */
     uint32_t flags;         /* EMS_FLAG_*                                                     */
+    int32_t  display_rows;  /* 0: one output row per bin (R = n_fft/2+1).  > 0: energy is
+                               scattered straight onto R = display_rows rows of a warped
+                               frequency axis (assets/spectrogram.png is 546 px high)  (0)    */
+    float    freq_scale;    /* "Frequency Scale" README.md:48, used when display_rows > 0:
+                               row = (R-1) * log1p(a x) / log1p(a), x = f / Nyquist,
+                               a = 10^(2*freq_scale) - 1; 0 = linear axis             (1.0)  */
 } ems_params;
 
 typedef struct ems_handle ems_handle;
@@ -97,6 +104,9 @@ ems_status ems_set_stream(ems_handle* h, void* cuda_stream);
 ems_status ems_get_stream(ems_handle* h, void** cuda_stream);
 ems_status ems_synchronize(ems_handle* h);
 
+/* Output rows per column R of this handle (n_fft/2+1, or display_rows). */
+ems_status ems_output_rows(const ems_handle* h, size_t* rows);
+
 /* F for n_samples_per_ch samples with this handle's n_fft / hop. */
 ems_status ems_frame_count(const ems_handle* h, size_t n_samples_per_ch, size_t* n_frames);
 
@@ -110,8 +120,8 @@ ems_status ems_process_points(ems_handle* h, const float* pcm_dev, size_t n_samp
                               size_t* n_frames);
 
 /* a1-a5: the picture the app draws (/root/reference/assets/spectrogram.png).
- * grid_dev : fp32 [channels][F][B] accumulated energy, or NULL;
- * index_dev: u8   [channels][F][B] colour index 0..255, or NULL (not both NULL). */
+ * grid_dev : fp32 [channels][F][R] accumulated energy, or NULL;
+ * index_dev: u8   [channels][F][R] colour index 0..255, or NULL (not both NULL). */
 ems_status ems_process_grid(ems_handle* h, const float* pcm_dev, size_t n_samples_per_ch,
                             float* grid_dev, uint8_t* index_dev, size_t* n_frames);
 
@@ -136,8 +146,8 @@ ems_status ems_launch_count(const ems_handle* h, uint64_t* launches);
 
 /* Streaming mode ("start visualizing your system audio", /root/reference/README.md:36).
  * pcm_host: hop*channels fp32 samples, interleaved.  Once the ring holds n_fft samples
- * every push analyses one new frame per channel.  A column is final R = ceil(n_fft/(2 hop))
- * pushes after its own frame; then *column_ready = 1, column_host (u8 [channels][B], pinned
+ * every push analyses one new frame per channel.  A column is final ceil(n_fft/(2 hop))
+ * pushes after its own frame; then *column_ready = 1, column_host (u8 [channels][R], pinned
  * recommended) holds it and *column_index (nullable) its frame index.  Synchronous. */
 ems_status ems_stream_push(ems_handle* h, const float* pcm_host, uint8_t* column_host,
                            int* column_ready, int64_t* column_index);

@@ -62,10 +62,20 @@ class Params:
     smoothing: float = 0.0       # README.md:50
     noise_gate_db: float = -65.0 # README.md:51
     flags: int = FLAG_REASSIGN | FLAG_DETERMINISTIC
+    display_rows: int = 0        # 0: one row per bin; > 0: rows of the warped frequency axis
+    freq_scale: float = 1.0      # README.md:48 "Frequency Scale" (used when display_rows > 0)
 
     @property
     def n_bins(self) -> int:
         return self.n_fft // 2 + 1
+
+    @property
+    def n_rows(self) -> int:
+        return self.display_rows if self.display_rows > 0 else self.n_bins
+
+    @property
+    def warp_a(self) -> float:
+        return 10.0 ** (2.0 * self.freq_scale) - 1.0
 
     @property
     def gate_lin(self) -> float:
@@ -152,19 +162,45 @@ def reassign_points(x: np.ndarray, prm: Params, chunk: int = 256, workers: int =
     return dcol, dbin, en
 
 
-def scatter_grid(dcol, dbin, energy) -> np.ndarray:
-    """a4: G[f + rint(dt_cols), k + rint(dk_bins)] += e over kept (e > 0) points; fp64 [F][B]."""
+def output_row(k, dk, prm: Params):
+    """Row of a point at reassigned frequency k + dk [bins].  Without display_rows: the
+    nearest bin.  With it ("Frequency Scale", README.md:48; stand-in shape): rows of a
+    log1p-warped axis, row = rint((R-1) log1p(a x)/log1p(a)), x = (k+dk)/(N/2),
+    a = 10^(2 freq_scale) - 1 (a -> 0: linear)."""
+    if prm.display_rows <= 0:
+        return k + np.rint(dk).astype(np.int64)
+    x = (k + dk) / (prm.n_fft / 2)
+    a = prm.warp_a
+    u = np.log1p(a * x) / np.log1p(a) if a > 1e-6 else x
+    return np.rint(u * (prm.display_rows - 1)).astype(np.int64)
+
+
+def row_frequencies(prm: Params) -> np.ndarray:
+    """Centre frequency [Hz] of every output row."""
+    if prm.display_rows <= 0:
+        return np.arange(prm.n_bins, dtype=np.float64) * prm.sample_rate / prm.n_fft
+    u = np.arange(prm.display_rows, dtype=np.float64) / (prm.display_rows - 1)
+    a = prm.warp_a
+    x = np.expm1(u * np.log1p(a)) / a if a > 1e-6 else u
+    return x * prm.sample_rate / 2
+
+
+def scatter_grid(dcol, dbin, energy, prm: Params | None = None) -> np.ndarray:
+    """a4: G[f + rint(dt_cols), output_row(k + dk_bins)] += e over kept (e > 0) points; fp64 [F][R]."""
     F, B = energy.shape
+    if prm is None:
+        prm = Params(n_fft=2 * (B - 1))
+    R = prm.n_rows
     f, k = np.nonzero(energy > 0.0)
     col = f + np.rint(dcol[f, k]).astype(np.int64)
-    row = k + np.rint(dbin[f, k]).astype(np.int64)
-    flat = np.bincount(col * B + row, weights=energy[f, k], minlength=F * B)
-    return flat.reshape(F, B)
+    row = output_row(k, dbin[f, k], prm)
+    flat = np.bincount(col * R + row, weights=energy[f, k], minlength=F * R)
+    return flat.reshape(F, R)
 
 
 def low_end_weight(prm: Params) -> np.ndarray:
-    """w_low(k) = 1 + (boost-1)/(1 + (f_k/200 Hz)^2): `boost` at DC, -> 1 at high f."""
-    f = np.arange(prm.n_bins, dtype=np.float64) * prm.sample_rate / prm.n_fft
+    """w_low = 1 + (boost-1)/(1 + (f/200 Hz)^2) per output row: `boost` at DC, -> 1 at high f."""
+    f = row_frequencies(prm)
     return 1.0 + (prm.low_end_boost - 1.0) / (1.0 + (f / LOW_END_CORNER_HZ) ** 2)
 
 
@@ -197,7 +233,7 @@ def postpass(grid: np.ndarray, prm: Params) -> np.ndarray:
 def process(x: np.ndarray, prm: Params, workers: int = 1):
     """Whole path for one channel: (grid fp64 [F][B], index u8 [F][B])."""
     dcol, dbin, en = reassign_points(x, prm, workers=workers)
-    grid = scatter_grid(dcol, dbin, en)
+    grid = scatter_grid(dcol, dbin, en, prm)
     return grid, postpass(grid, prm)
 
 

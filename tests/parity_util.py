@@ -92,6 +92,25 @@ def check_grid(grid_gpu, x: np.ndarray, prm: orc.Params):
     return err, grid_o, idx_o
 
 
+def check_grid_rows(grid_gpu, x: np.ndarray, prm: orc.Params):
+    """Warped display axis: rows can be a fraction of a bin wide, so the fp32 error of w^
+    (1e-5 bin) can move a point sitting on a row boundary to the neighbouring row.  The
+    criterion is transport, not per-cell L2: every column keeps its energy (1e-6) and the
+    energy that has to move, times the rows it moves (Wasserstein-1 along the rows), stays
+    under 1e-3 of the total.  Most columns must still match to 1e-4 rel-L2 outright."""
+    grid_o, _ = orc.process(x, prm)
+    g = np.asarray(grid_gpu, np.float64)
+    tot = grid_o.sum()
+    assert np.abs(g.sum(1) - grid_o.sum(1)).max() <= 1e-6 * max(tot, 1e-30)
+    w1 = np.abs(np.cumsum(g - grid_o, axis=1)).sum()
+    assert w1 <= 1e-3 * tot, f"row transport {w1 / tot}"
+    num = np.linalg.norm(g - grid_o, axis=1)
+    den = np.maximum(np.linalg.norm(grid_o, axis=1), 1e-30)
+    exact = (num <= ENERGY_TOL * den) | (grid_o.sum(1) == 0)
+    assert exact.mean() >= 0.97, f"only {exact.mean()} of the columns match to 1e-4"
+    return w1 / tot, grid_o
+
+
 def check_index(idx_gpu, grid_o: np.ndarray, prm: orc.Params):
     """u8 colour index: a quantised float -> +-1 at rounding boundaries, flips allowed only
     for cells whose level sits on the gate."""

@@ -28,7 +28,7 @@ def test_header_symbols_all_exported(lib_built):
 def test_abi_version_and_status_strings(lib_built):
     import emspec
     lib = emspec.load()
-    assert lib.ems_abi_version() == 1
+    assert lib.ems_abi_version() == 2
     assert lib.ems_status_str(0) == b"ok"
     for s in range(1, 6):
         assert len(lib.ems_status_str(s)) > 0
@@ -41,6 +41,7 @@ def test_default_params_are_the_settings_png_preset(lib_built):
     assert abs(p.db_range - 58) < 1e-6 and abs(p.gain - 3.5) < 1e-6
     assert abs(p.low_end_boost - 3.9) < 1e-6 and p.smoothing == 0 and p.noise_gate_db == -65
     assert p.flags & emspec.FLAG_REASSIGN and p.flags & emspec.FLAG_DETERMINISTIC
+    assert p.display_rows == 0 and abs(p.freq_scale - 1.0) < 1e-6
 
 
 def test_invalid_arguments_rejected_before_any_cuda_call(lib_built):
@@ -49,7 +50,8 @@ def test_invalid_arguments_rejected_before_any_cuda_call(lib_built):
     h = ctypes.c_void_p()
     assert lib.ems_create(None, ctypes.byref(h)) == emspec.ERR_INVALID_ARG
     for bad in (dict(n_fft=1000), dict(n_fft=128), dict(n_fft=65536), dict(hop=0),
-                dict(hop=8192), dict(channels=0), dict(smoothing=1.0), dict(db_range=0.0)):
+                dict(hop=8192), dict(channels=0), dict(smoothing=1.0), dict(db_range=0.0),
+                dict(display_rows=1), dict(display_rows=-3), dict(freq_scale=-1.0)):
         p = emspec.default_params()
         for k, v in bad.items():
             setattr(p, k, v)

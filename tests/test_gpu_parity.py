@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 import reassign_oracle as orc
-from parity_util import check_grid, check_index, check_points, rel_l2
+from parity_util import check_grid, check_grid_rows, check_index, check_points, rel_l2
 
 torch = pytest.importorskip("torch")
 pytestmark = pytest.mark.gpu
@@ -38,6 +38,7 @@ def run_grid(m, x, prm, want_grid=True):
     eng = m.Engine(n_fft=prm.n_fft, hop=prm.hop, noise_gate_db=prm.noise_gate_db,
                    db_range=prm.db_range, gain=prm.gain, low_end_boost=prm.low_end_boost,
                    smoothing=prm.smoothing, sample_rate=prm.sample_rate,
+                   display_rows=prm.display_rows, freq_scale=prm.freq_scale,
                    flags=prm.flags | m.FLAG_SYNC)
     g, i = eng.process_grid(torch.from_numpy(x).cuda(), want_grid=want_grid)
     eng.close()
@@ -140,6 +141,40 @@ def test_nfft_sweep_display_controls(emspec, n_fft):
     g, idx = run_grid(emspec, x, prm)
     err, grid_o, _ = check_grid(g, x, prm)
     check_index(idx, grid_o, prm)
+
+
+@pytest.mark.parametrize("n_fft,hop,rows,scale", [
+    (4096, 128, 546, 1.0), (2048, 512, 256, 0.5), (4096, 256, 1080, 0.0), (1024, 128, 64, 1.5),
+])
+def test_frequency_scale_display_rows(emspec, n_fft, hop, rows, scale):
+    """energy scattered straight onto display rows of the warped frequency
+    axis ("Frequency Scale", README.md:48) — grid, index, scatter-from-points and streaming."""
+    x = orc.synth_signal(SR, SR, seed=13)
+    prm = orc.Params(n_fft=n_fft, hop=hop, display_rows=rows, freq_scale=scale, smoothing=0.0)
+    g, idx = run_grid(emspec, x, prm)
+    assert g.shape[1] == rows
+    # a point sitting on a row boundary of the warped axis may land one row over in fp32: the
+    # grid is judged by transport distance, the post-pass on the grid it was actually given
+    check_grid_rows(g, x, prm)
+    check_index(idx, g.astype(np.float64), prm)
+    eng = emspec.Engine(n_fft=n_fft, hop=hop, display_rows=rows, freq_scale=scale,
+                        flags=prm.flags | emspec.FLAG_SYNC)
+    xd = torch.from_numpy(x).cuda()
+    pts = eng.process_points(xd)
+    assert pts[0].shape[2] == n_fft // 2 + 1               # points stay per bin
+    g2, i2 = eng.scatter_points(*pts)
+    assert torch.equal(g2[0].cpu(), torch.from_numpy(g)) and torch.equal(i2[0].cpu(), torch.from_numpy(idx))
+    # streaming emits the same rows
+    col = torch.empty((1, rows), dtype=torch.uint8).pin_memory()
+    S = (len(x) // hop) * hop
+    n_ok = 0
+    for i in range(S // hop):
+        ready, ci = eng.stream_push(torch.from_numpy(x[i * hop:(i + 1) * hop]).contiguous(), col)
+        if ready and ci < idx.shape[0]:
+            assert (col.numpy()[0] == idx[ci]).all()
+            n_ok += 1
+    assert n_ok > 10
+    eng.close()
 
 
 def test_display_controls(emspec):

@@ -134,3 +134,25 @@ def test_synth_signal_is_deterministic():
     assert np.abs(a).max() < 1.0
     c = orc.synth_signal(4800, SR, clip_index=3)
     assert not (a == c).all()
+
+
+def test_frequency_scale_rows():
+    """Warped display axis: monotone, end points pinned, energy conserved,
+    freq_scale 0 is a linear resample, larger scale gives the bass more rows."""
+    prm = orc.Params(n_fft=4096, hop=128, display_rows=546, freq_scale=1.0)
+    k = np.arange(2049)
+    rows = orc.output_row(k, np.zeros(2049), prm)
+    assert rows[0] == 0 and rows[-1] == 545 and (np.diff(rows) >= 0).all()
+    lin = orc.output_row(k, np.zeros(2049), orc.Params(n_fft=4096, display_rows=546, freq_scale=0.0))
+    assert np.abs(lin - np.rint(k / 2048 * 545)).max() == 0
+    assert rows[k == 100][0] > lin[k == 100][0]                   # 1.17 kHz sits higher on the warped axis
+    f = orc.row_frequencies(prm)
+    assert f[0] == 0 and abs(f[-1] - 24000) < 1e-6 and (np.diff(f) > 0).all()
+    back = orc.output_row(f / (48000 / 4096), np.zeros(546), prm)  # row centres map back to their rows
+    assert (back == np.arange(546)).all()
+    x = orc.synth_signal(24000, SR, seed=3)
+    dt, dk, e = orc.reassign_points(x, prm)
+    g = orc.scatter_grid(dt, dk, e, prm)
+    assert g.shape == (e.shape[0], 546) and abs(g.sum() - e.sum()) < 1e-9 * e.sum()
+    w = orc.low_end_weight(prm)
+    assert w.shape == (546,) and abs(w[0] - prm.low_end_boost) < 1e-12
