@@ -40,7 +40,7 @@ struct ems_handle {
     float4* win = nullptr;              // [N]
     float2* tw = nullptr;               // [N]
     float*  weight = nullptr;           // [B]
-    ems::DevBuf acc, flags, carry, ema_local, ema_carry, host_pcm, host_idx, host_grid, big_scratch;
+    ems::DevBuf acc, flags, carry, ema_local, ema_carry, host_pcm, host_i16, host_idx, host_grid, big_scratch;
     bool acc_clean = false;             // accumulator and dirty flags are all zero (kept so by the post-pass)
     cudaEvent_t ev[EMS_STAGE_COUNT][2]{};
     bool ev_valid[EMS_STAGE_COUNT]{};
@@ -536,7 +536,7 @@ ems_status ems_create(const ems_params* params, ems_handle** out) {
 ems_status ems_destroy(ems_handle* h) {
     if (!h) return EMS_ERR_INVALID_ARG;
     if (h->stream) cudaStreamSynchronize(h->stream);
-    for (DevBuf* b : {&h->acc, &h->flags, &h->carry, &h->ema_local, &h->ema_carry, &h->host_pcm,
+    for (DevBuf* b : {&h->acc, &h->flags, &h->carry, &h->ema_local, &h->ema_carry, &h->host_pcm, &h->host_i16,
                       &h->host_idx, &h->host_grid, &h->big_scratch})
         if (b->p) cudaFree(b->p);
     stream_free(h);
@@ -669,9 +669,12 @@ ems_status ems_process_grid(ems_handle* h, const float* pcm, size_t S, float* gr
     return finish(h);
 }
 
-ems_status ems_process_host(ems_handle* h, const float* pcm_host, size_t S, float* grid_host,
-                            uint8_t* index_host, size_t* n_frames) {
+// Shared body of ems_process_host (fp32 planar) and ems_process_host_i16 (int16 interleaved).
+static ems_status process_host_impl(ems_handle* h, const void* pcm_host_v, bool is_i16, size_t S,
+                                    float* grid_host, uint8_t* index_host, size_t* n_frames) {
     if (!h) return EMS_ERR_INVALID_ARG;
+    const float* pcm_host = (const float*)pcm_host_v;
+    const int16_t* pcm_i16 = (const int16_t*)pcm_host_v;
     const long long F = frames_of(h->prm, S);
     if (n_frames) *n_frames = (size_t)F;
     for (bool& v : h->ev_valid) v = false;
@@ -682,6 +685,7 @@ ems_status ems_process_host(ems_handle* h, const float* pcm_host, size_t S, floa
     const size_t cells = (size_t)C * F * B;
     ems_status s;
     if ((s = ensure(h, h->host_pcm, (size_t)C * S * sizeof(float))) != EMS_OK) return s;
+    if (is_i16 && (s = ensure(h, h->host_i16, (size_t)C * S * sizeof(int16_t))) != EMS_OK) return s;
     if ((s = prepare_acc(h, cells, (size_t)C * F, B)) != EMS_OK) return s;
     if (index_host && (s = ensure(h, h->host_idx, cells)) != EMS_OK) return s;
     if (grid_host && (s = ensure(h, h->host_grid, cells * sizeof(float))) != EMS_OK) return s;
@@ -716,13 +720,27 @@ ems_status ems_process_host(ems_handle* h, const float* pcm_host, size_t S, floa
     for (int c = 0; c < n_chunks && rs == EMS_OK; ++c) {
         const long long f0 = (long long)c * chunk, f1 = std::min(F, f0 + chunk);
         const long long need = (f1 == F) ? (long long)S : (f1 - 1) * H + N;   // samples needed
-        for (int ch = 0; ch < C; ++ch)
-            cudaMemcpyAsync(pcm_dev + (size_t)ch * S + sent, pcm_host + (size_t)ch * S + sent,
-                            (size_t)(need - sent) * sizeof(float), cudaMemcpyHostToDevice,
-                            h->copy_in);
-        sent = need;
+        if (is_i16) {
+            int16_t* stage = (int16_t*)h->host_i16.p;
+            cudaMemcpyAsync(stage + (size_t)sent * C, pcm_i16 + (size_t)sent * C,
+                            (size_t)(need - sent) * C * sizeof(int16_t), cudaMemcpyHostToDevice, h->copy_in);
+        } else {
+            for (int ch = 0; ch < C; ++ch)
+                cudaMemcpyAsync(pcm_dev + (size_t)ch * S + sent, pcm_host + (size_t)ch * S + sent,
+                                (size_t)(need - sent) * sizeof(float), cudaMemcpyHostToDevice,
+                                h->copy_in);
+        }
         cudaEventRecord(ev_in[c], h->copy_in);
         cudaStreamWaitEvent(h->stream, ev_in[c], 0);
+        if (is_i16) {
+            const long long n = (need - sent) * C;
+            long long blocks = (n + 255) / 256;
+            if (blocks > 8192) blocks = 8192;
+            pcm_i16_to_planar_kernel<<<(unsigned)blocks, 256, 0, h->stream>>>(
+                (const int16_t*)h->host_i16.p, pcm_dev, (long long)S, C, sent, need);
+            ++h->launches;
+        }
+        sent = need;
         StftArgs a = make_args(h, pcm_dev, S, F);
         a.f_begin = f0; a.f_end = f1;
         a.acc = h->acc.p; a.flags = (unsigned char*)h->flags.p; a.mode = det ? kDepositU64 : kDepositF32;
@@ -755,6 +773,16 @@ ems_status ems_process_host(ems_handle* h, const float* pcm_host, size_t S, floa
                     cudaGetErrorString(e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3)));
     h->acc_clean = true;
     return EMS_OK;
+}
+
+ems_status ems_process_host(ems_handle* h, const float* pcm_host, size_t S, float* grid_host,
+                            uint8_t* index_host, size_t* n_frames) {
+    return process_host_impl(h, pcm_host, false, S, grid_host, index_host, n_frames);
+}
+
+ems_status ems_process_host_i16(ems_handle* h, const int16_t* pcm_host, size_t S, float* grid_host,
+                                uint8_t* index_host, size_t* n_frames) {
+    return process_host_impl(h, pcm_host, true, S, grid_host, index_host, n_frames);
 }
 
 ems_status ems_stage_ms(ems_handle* h, int stage, float* ms) {

@@ -202,6 +202,20 @@ post_sparse_kernel(const PostArgs a) {
     }
 }
 
+// Capture-side format: int16 PCM, interleaved [S][channels] ->
+// fp32 planar [channels][S], full scale 32768, samples [s0, s1) of every channel.
+__global__ void pcm_i16_to_planar_kernel(const int16_t* __restrict__ in, float* __restrict__ out,
+                                         long long S, int channels, long long s0, long long s1) {
+    const long long n = (s1 - s0) * channels;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long e = s0 * channels + i;
+        const long long smp = e / channels;
+        const int ch = (int)(e - smp * channels);
+        out[(long long)ch * S + smp] = (float)in[e] * (1.0f / 32768.0f);
+    }
+}
+
 // Clears the dirty flags of columns [c0, c1) of every (channel, bin block) row.
 __global__ void clear_flags_kernel(unsigned char* __restrict__ flags, long long F, long long c0,
                                    long long c1, int rows) {

@@ -57,6 +57,7 @@ _SIG = {
     "ems_process_grid": (C.c_int, [_VP, _FP, C.c_size_t, _FP, _U8P, C.POINTER(C.c_size_t)]),
     "ems_scatter_points": (C.c_int, [_VP, _FP, _FP, _FP, C.c_size_t, _FP, _U8P]),
     "ems_process_host": (C.c_int, [_VP, _FP, C.c_size_t, _FP, _U8P, C.POINTER(C.c_size_t)]),
+    "ems_process_host_i16": (C.c_int, [_VP, _FP, C.c_size_t, _FP, _U8P, C.POINTER(C.c_size_t)]),
     "ems_stage_ms": (C.c_int, [_VP, C.c_int, C.POINTER(C.c_float)]),
     "ems_launch_count": (C.c_int, [_VP, C.POINTER(C.c_uint64)]),
     "ems_stream_push": (C.c_int, [_VP, _FP, _U8P, C.POINTER(C.c_int), C.POINTER(C.c_int64)]),
@@ -232,6 +233,26 @@ class Engine:
         n = C.c_size_t()
         self._check(self.lib.ems_process_host(self.h, _ptr(pcm_host), S, _ptr(grid_out),
                                               _ptr(index_out), C.byref(n)))
+        return grid_out, index_out
+
+    def process_host_i16(self, pcm_i16, want_grid=False, index_out=None, grid_out=None):
+        """Host int16 tensor [S][channels] (interleaved) -> (grid | None, index) CPU tensors."""
+        import torch
+        if pcm_i16.dim() == 1:
+            pcm_i16 = pcm_i16[:, None]
+        assert (not pcm_i16.is_cuda) and pcm_i16.dtype == torch.int16 and pcm_i16.is_contiguous()
+        assert pcm_i16.shape[1] == self.params.channels
+        S = pcm_i16.shape[0]
+        F = self.frame_count(S)
+        shape = (self.params.channels, F, self.n_rows)
+        pin = torch.cuda.is_available()
+        if index_out is None:
+            index_out = torch.empty(shape, dtype=torch.uint8, pin_memory=pin)
+        if want_grid and grid_out is None:
+            grid_out = torch.empty(shape, dtype=torch.float32, pin_memory=pin)
+        n = C.c_size_t()
+        self._check(self.lib.ems_process_host_i16(self.h, _ptr(pcm_i16), S, _ptr(grid_out),
+                                                  _ptr(index_out), C.byref(n)))
         return grid_out, index_out
 
     # ------------------------------------------------------------------ streaming

@@ -138,6 +138,12 @@ ems_status ems_scatter_points(ems_handle* h, const float* dt_cols, const float* 
 ems_status ems_process_host(ems_handle* h, const float* pcm_host, size_t n_samples_per_ch,
                             float* grid_host, uint8_t* index_host, size_t* n_frames);
 
+/* Capture-side input format (/root/reference/README.md:36 "system audio"):
+ * int16 PCM, interleaved [n_samples_per_ch][channels], full scale 32768; otherwise as
+ * ems_process_host (half the host-to-device bytes). */
+ems_status ems_process_host_i16(ems_handle* h, const int16_t* pcm_host, size_t n_samples_per_ch,
+                                float* grid_host, uint8_t* index_host, size_t* n_frames);
+
 /* Device milliseconds of a stage of the last offline call on this handle (after the
  * stream has been synchronised); EMS_ERR_STATE if that stage did not run. */
 ems_status ems_stage_ms(ems_handle* h, int stage, float* ms);
