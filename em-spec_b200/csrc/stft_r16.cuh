@@ -1,23 +1,30 @@
 // stft_r16.cuh — tuned fused frame gather + 3-window STFT + reassignment for n_fft = 4096.
 //
+// ONE complex FFT per frame.  Z = FFT_4096(x + j*x*th'), th' = th*(2/N): the real part is the
+// *unwindowed* frame, so the untangle gives the rectangular-window spectrum X and X_th'.
+// Hann and its derivative are three-tap stencils of X in frequency
+//     X_h[k]   = X[k]/2 - (X[k-1] + X[k+1])/4          (h  = 0.5 - 0.5 cos(2 pi n/N))
+//     X_dh'[k] = (X[k-1] - X[k+1]) / (2j)              (dh' = sin(2 pi n/N))
+// which replaces the second FFT of the x*dh window (a third of the flops and 40 % of the
+// shared-memory traffic).  fp32 accuracy is that of the three-FFT form: only t*h needs a time
+// window (an unwindowed ramp is what breaks the all-stencil variant SURVEY.md §7 rejected);
+// probed against the float64 oracle: <= 4.3e-5 col / 5.2e-6 bin within 40 dB of the peak.
+//
 // Layout of the work (DESIGN.md "K1-K3"):
 //   * persistent CTAs, one per SM, 3 workers x 128 threads; a CTA walks tiles of T
 //     consecutive frames whose samples ((T-1)*hop + 4096 floats) sit once in shared memory,
 //     double-buffered with cp.async so the next tile lands while this one is analysed;
-//   * a worker analyses one frame at a time, entirely on-chip:
-//       Z = FFT_4096(x*h + j*x*th')   as 16 x 16 x 16   (two radix-16 butterflies / thread / pass)
-//       Y = FFT_2048(w[2n] + j*w[2n+1]), w = x*dh'  as 16 x 16 x 8
-//     in-place decimation-in-frequency in the worker's private buffers, one named barrier
-//     per exchange (3 per frame); every access pattern is bank-conflict-free through the
-//     paddings padZ(a) = a + (a >> 8), padY(a) = a + (a >> 7)  (tools/bank_sim.py);
-//   * windows are not stored: cos/sin of the sample angle come from the thread's base
-//     angle rotated by compile-time constants;
-//   * the last pass is arranged so that thread p owns output residues t = p and 256 - p:
-//     Z[k], Z[N-k], Y[k], Y[N/2-k] of its 16 bins are then all in its own registers and the
-//     untangle + Auger-Flandrin epilogue needs no further exchange; X_h, X_th, X_dh never
-//     exist outside registers.  Residues 0 and 128 (self-paired, 17 bins) go through a
-//     48-entry scratch handled by 17 lanes of warp 0.
-// Semantics are identical to stft_generic.cuh (same reassign_emit).
+//   * a worker analyses one frame at a time, entirely on-chip: Z as 16 x 16 x 16, two radix-16
+//     butterflies per thread per pass in packed fp32x2 arithmetic, in-place
+//     decimation-in-frequency in the worker's private buffer, padding padZ(a) = a + (a >> 8)
+//     makes every exchange bank-conflict-free (tools/bank_sim.py);
+//   * th' is not stored: cos(2 pi n/N) comes from the thread's base angle rotated by immediates;
+//   * the last pass gives thread p the output residues t = p and 256 - p, so Z[k] and Z[N-k] of
+//     its 16 bins are in its own registers: untangle in registers, X (16 KB) goes to shared
+//     memory once so that each bin can read its two neighbours, then the Auger-Flandrin
+//     epilogue runs on the thread's own bins.  3 named barriers per frame.  Residues 0 and 128
+//     pair with themselves (17 bins): one thread untangles them, 17 lanes of its warp finish them.
+// Decisions (gate, drop rule, deposit) are those of stft_generic.cuh::reassign_emit.
 #pragma once
 #include "common.cuh"
 #include "stft_generic.cuh"
@@ -33,13 +40,12 @@ constexpr int kWorkers = 3;
 constexpr int kWorkerThreads = 128;
 constexpr int kThreads = kWorkers * kWorkerThreads;
 constexpr int kZBuf = 4112;            // float2, padZ(4095) = 4110
-constexpr int kYBuf = 2064;            // float2, padY(2047) = 2062
+constexpr int kXBuf = 2052;            // float2: 2 X[k] at index k + 1, mirrors at 0 and 2050
 constexpr int kZtab = 15 * 256;        // W_4096^{b i}, i = 1..15, b < 256
 constexpr int kT2 = 15 * 16;           // W_256^{p2 i}
-constexpr int kT2Y = 15 * 8;           // W_128^{p2 i}
-constexpr int kScratch = 48;           // thread-0 self-paired residues
-constexpr int kTabFloat2 = kZtab + kT2 + kT2Y;
-constexpr int kFixedBytes = (kWorkers * (kZBuf + kYBuf + kScratch) + kTabFloat2) * 8;
+constexpr int kScratch = 20;           // 2 X_th' of the 17 self-paired bins
+constexpr int kTabFloat2 = kZtab + kT2;
+constexpr int kFixedBytes = (kWorkers * (kZBuf + kXBuf + kScratch) + kTabFloat2) * 8;
 constexpr int kMaxSmem = 232448;       // 227 KB
 constexpr int kTileFloats = ((kMaxSmem - kFixedBytes) / 8) & ~3;   // per buffer, two buffers
 
@@ -130,22 +136,6 @@ __device__ __forceinline__ void dft16(float2 (&a)[16]) {
     for (int i0 = 0; i0 < 4; ++i0) dft4(a[4 * i0], a[4 * i0 + 1], a[4 * i0 + 2], a[4 * i0 + 3]);
 }
 
-// forward DFT-8 in registers.  Output i sits in a[o8(i)].
-__host__ __device__ constexpr int o8(int i) { return 2 * (i & 3) + (i >> 2); }
-
-__device__ __forceinline__ void dft8(float2 (&a)[8]) {
-    dft4(a[0], a[2], a[4], a[6]);
-    dft4(a[1], a[3], a[5], a[7]);
-    // a[j0 + 2 i0]: the odd half takes W8^{i0} = W16^{2 i0}
-    a[3] = mul_w16<2>(a[3]); a[5] = mul_w16<4>(a[5]); a[7] = mul_w16<6>(a[7]);
-#pragma unroll
-    for (int i0 = 0; i0 < 4; ++i0) {
-        const float2 u0 = a[2 * i0], u1 = a[2 * i0 + 1];
-        a[2 * i0] = u0 + u1;
-        a[2 * i0 + 1] = u0 - u1;
-    }
-}
-
 __device__ __forceinline__ void worker_bar(int w) {
     asm volatile("bar.sync %0, %1;" ::"r"(w + 1), "r"(kWorkerThreads) : "memory");
 }
@@ -171,7 +161,6 @@ struct FrameCtx {
     float* pd;           // row (chan, f) of dt_cols / dk_bins / energy (store mode)
     float* pk;
     float* pe;
-    long long acc_row;   // (chan*F + f) * B   (linear accumulator / stored points)
     long long f;         // frame index in its channel
     int ch;
 };
@@ -182,16 +171,15 @@ __device__ __forceinline__ float rcp_approx(float x) {
     return r;
 }
 
-// One bin of the epilogue: untangle the packed spectra, apply the Auger-Flandrin operators
-// and emit — same decisions as reassign_emit (stft_generic.cuh), arranged to be cheap:
-// a whole warp under the gate leaves after 8 instructions, everything else is predicated.
-//   zk = Z[k], zn = Z[N-k], yk = Y[k mod N/2], yn = Y[(N/2-k) mod N/2], w = W_N^k
+// One bin of the epilogue: Hann / Hann-derivative stencils of the rectangular spectrum, the
+// Auger-Flandrin operators and the emit — same decisions as reassign_emit (stft_generic.cuh).
+//   xk, xm, xp = 2 X[k], 2 X[k-1], 2 X[k+1];  t2 = 2 X_th'[k]
+// A whole warp under the gate leaves after the stencil; everything else is predicated.
 // Must be reached by all 32 lanes of the warp (`owner` masks lanes that only tag along).
 template <int MODE>
 __device__ __forceinline__ void bin_emit(const StftArgs& a, const FrameCtx& fc, bool owner, int k,
-                                         float kf, float2 zk, float2 zn, float2 yk, float2 yn,
-                                         float2 w) {
-    const float2 A2 = make_float2(zk.x + zn.x, zk.y - zn.y);           // 2 X_h
+                                         float kf, float2 xk, float2 xm, float2 xp, float2 t2) {
+    const float2 A2 = fma2(xm + xp, make_float2(-0.25f, -0.25f), mul2(xk, make_float2(0.5f, 0.5f)));   // 2 X_h
     const float p2 = A2.x * A2.x + A2.y * A2.y;
     const float e = p2 * (float)(4.0 / ((double)N * (double)N));
     const bool live = e > a.gate_lin;
@@ -202,13 +190,10 @@ __device__ __forceinline__ void bin_emit(const StftArgs& a, const FrameCtx& fc, 
     bool ok = live;
     float dtc = 0.f, dk = 0.f, rc = 0.f, wh = kf;
     if (a.reassign) {
-        const float2 B2 = make_float2(zk.y + zn.y, zn.x - zk.x);       // 2 X_th'
-        const float2 E2 = make_float2(yk.x + yn.x, yk.y - yn.y);
-        const float2 O2 = make_float2(yk.y + yn.y, yn.x - yk.x);
-        const float2 D2 = make_float2(E2.x + (w.x * O2.x - w.y * O2.y),
-                                      E2.y + (w.x * O2.y + w.y * O2.x));   // 2 X_dh'
+        const float2 d = xm - xp;                                        // 2 X_dh' = d / (2j)
+        const float2 D2 = make_float2(0.5f * d.y, -0.5f * d.x);
         const float inv = rcp_approx(p2);
-        const float dts = (B2.x * A2.x + B2.y * A2.y) * inv * (float)(N / 2);   // samples
+        const float dts = (t2.x * A2.x + t2.y * A2.y) * inv * (float)(N / 2);   // samples
         dk = (D2.y * A2.x - D2.x * A2.y) * inv * -0.5f;                          // bins
         dtc = dts * a.inv_hop;
         rc = rintf(dtc);
@@ -232,6 +217,9 @@ __device__ __forceinline__ void bin_emit(const StftArgs& a, const FrameCtx& fc, 
     }
 }
 
+// conj(a)
+__device__ __forceinline__ float2 cj(float2 a) { return make_float2(a.x, -a.y); }
+
 template <int MODE>
 __global__ void __launch_bounds__(kThreads, 1)
 stft_reassign_r16(const StftArgs a_in, const int tile_T) {
@@ -241,45 +229,38 @@ stft_reassign_r16(const StftArgs a_in, const int tile_T) {
     float2* sm = reinterpret_cast<float2*>(smem_raw);
     float2* Ztab = sm;                         // [15][256]
     float2* T2 = Ztab + kZtab;                 // [15][16]
-    float2* T2Y = T2 + kT2;                    // [15][8]
-    float2* wbuf = T2Y + kT2Y;                 // per worker: Z, Y, scratch
-    float* tile0 = reinterpret_cast<float*>(wbuf + kWorkers * (kZBuf + kYBuf + kScratch));   // 2 x kTileFloats
+    float2* wbuf = T2 + kT2;                   // per worker: Z, X, scratch
+    float* tile0 = reinterpret_cast<float*>(wbuf + kWorkers * (kZBuf + kXBuf + kScratch));   // 2 x kTileFloats
 
     const int tid = threadIdx.x;
     const int w = tid >> 7;                    // worker
     // role of this thread inside its worker; rotated by one warp per worker so that the warp
-    // carrying the extra self-paired bins lands on a different scheduler in each worker
+    // carrying the self-paired bins lands on a different scheduler in each worker
     const int p = (tid + 32 * w) & 127;
-    float2* Zb = wbuf + w * (kZBuf + kYBuf + kScratch);
-    float2* Yb = Zb + kZBuf;
-    float2* Sc = Yb + kYBuf;
+    float2* Zb = wbuf + w * (kZBuf + kXBuf + kScratch);
+    float2* Xs = Zb + kZBuf;                   // 2 X[k] at Xs[k + 1]
+    float2* Sc = Xs + kXBuf;
 
     // ---- twiddle tables (once per CTA)
     for (int e = tid; e < kZtab; e += kThreads) { const int i = e / 256 + 1, b = e % 256; Ztab[e] = __ldg(&a.tw[b * i]); }
     for (int e = tid; e < kT2; e += kThreads) { const int i = e / 16 + 1, q = e % 16; T2[e] = __ldg(&a.tw[16 * q * i]); }
-    for (int e = tid; e < kT2Y; e += kThreads) { const int i = e / 8 + 1, q = e % 8; T2Y[e] = __ldg(&a.tw[32 * q * i]); }
 
     // ---- per-thread constants
     const float2 twp = __ldg(&a.tw[p]);                    // (cos, -sin)(2 pi p / 4096)
     const float cp = twp.x, sp = -twp.y;
     const float rp = (float)(p - N / 2) * (1.0f / (N / 2)); // ramp of th' at n = p
     const int tA = p, tB = p ? 256 - p : 128;              // output residues of this thread
-    const float2 wA = twp;                                  // W_N^{tA}
-    const float2 wB = __ldg(&a.tw[tB]);                     // W_N^{tB}
     const int zA = 257 * (tA & 15) + 16 * (tA >> 4), zB = 257 * (tB & 15) + 16 * (tB >> 4);
-    const int yA = 129 * (tA & 15) + 8 * (tA >> 4), yB = 129 * (tB & 15) + 8 * (tB >> 4);
     const int i1 = p & 15, q2 = p >> 4;                    // pass-2 butterfly coordinates
     const bool owner = p != 0;                              // thread 0's residues pair with themselves
+    const float tAf = (float)tA, tBf = (float)tB;
     // self-paired bins (residues 0 and 128): lane l <= 8 takes bin 256 l, lanes 9..16 bins 128 + 256 (l - 9)
     const int ls = min(p, 16);
     const int ks = ls <= 8 ? 256 * ls : 128 + 256 * (ls - 9);
-    const float2 ws = __ldg(&a.tw[ks]);                     // W_N^{ks}
-    const float tAf = (float)tA, tBf = (float)tB;
 
     const long long per_ch = a.f_end - a.f_begin;
     const long long tiles_per_ch = (per_ch + tile_T - 1) / tile_T;
     const long long n_tiles = tiles_per_ch * a.channels;
-    const bool hop_even = (a.hop & 1) == 0;
     constexpr int B = N / 2 + 1;
 
     // Tiles are double-buffered: while the workers analyse tile i, cp.async brings the
@@ -313,7 +294,7 @@ stft_reassign_r16(const StftArgs a_in, const int tile_T) {
             const float* xs = tile + fi * a.hop;
             const long long f = f0 + fi;
 
-            // ================= pass 1 of Z: butterflies b = p, p + 128
+            // ================= pass 1: butterflies b = p, p + 128 on z[n] = x[n] (1 + j th'[n])
 #pragma unroll 1
             for (int u = 0; u < 2; ++u) {
                 const int b = p + 128 * u;
@@ -328,47 +309,20 @@ stft_reassign_r16(const StftArgs a_in, const int tile_T) {
                     const float x = xs[b + 256 * j];
                     const float cs = cb * cq - sb * sq;                // cos(2 pi n / N)
                     const float h = 0.5f - 0.5f * cs;
-                    const float re = x * h;
-                    v[j] = make_float2(re, re * (rb + rq));
+                    v[j] = make_float2(x, (x * h) * (rb + rq));        // th' = ramp * h
                 });
                 dft16(v);
                 Zb[b] = v[o16(0)];
 #pragma unroll
                 for (int i = 1; i < 16; ++i) Zb[b + 257 * i] = cmul2(v[o16(i)], Ztab[(i - 1) * 256 + b]);
             }
-            // ================= pass 1 of Y: butterfly b = p on w = x * sin(2 pi n / N)
-            {
-                const float c2 = cp * cp - sp * sp, s2 = 2.0f * sp * cp;   // angle of sample 2p
-                constexpr float cd = 0.99999882345170188f, sd = 0.0015339801862847655f;   // 2 pi / 4096
-                float2 v[16];
-                if (hop_even) {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) v[j] = *reinterpret_cast<const float2*>(xs + 2 * p + 256 * j);
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) v[j] = make_float2(xs[2 * p + 256 * j], xs[2 * p + 256 * j + 1]);
-                }
-                static_for<16>([&](auto jc) {
-                    constexpr int j = decltype(jc)::value;
-                    constexpr float cq = c32(2 * j), sq = s32(2 * j);
-                    const float se = s2 * cq + c2 * sq;
-                    const float ce = c2 * cq - s2 * sq;
-                    v[j] = make_float2(v[j].x * se, v[j].y * (se * cd + ce * sd));
-                });
-                dft16(v);
-                Yb[p] = v[o16(0)];
-#pragma unroll
-                for (int i = 1; i < 16; ++i) Yb[p + 129 * i] = cmul2(v[o16(i)], Ztab[(i - 1) * 256 + 2 * p]);   // W_2048^{p i}
-            }
             worker_bar(w);
 
-            // ================= pass 2: Z sub-FFTs of length 256, butterflies (i1, q2), (i1, q2 + 8);
-            // Y sub-FFTs of length 128, butterfly (i1, q2).  Software-pipelined by hand: the
-            // loads of the next butterfly are in flight while the current one is computed.
+            // ================= pass 2: sub-FFTs of length 256, butterflies (i1, q2), (i1, q2 + 8),
+            // software-pipelined by hand: the second butterfly's loads fly while the first computes
             {
                 float2* bz0 = Zb + 257 * i1 + q2;
                 float2* bz1 = bz0 + 8;
-                float2* by = Yb + 129 * i1 + q2;
                 float2 v0[16], v1[16];
 #pragma unroll
                 for (int j = 0; j < 16; ++j) v0[j] = bz0[16 * j];
@@ -378,65 +332,68 @@ stft_reassign_r16(const StftArgs a_in, const int tile_T) {
                 bz0[0] = v0[o16(0)];
 #pragma unroll
                 for (int i = 1; i < 16; ++i) bz0[16 * i] = cmul2(v0[o16(i)], T2[(i - 1) * 16 + q2]);
-#pragma unroll
-                for (int j = 0; j < 16; ++j) v0[j] = by[8 * j];
                 dft16(v1);
                 bz1[0] = v1[o16(0)];
 #pragma unroll
                 for (int i = 1; i < 16; ++i) bz1[16 * i] = cmul2(v1[o16(i)], T2[(i - 1) * 16 + q2 + 8]);
-                dft16(v0);
-                by[0] = v0[o16(0)];
-#pragma unroll
-                for (int i = 1; i < 16; ++i) by[8 * i] = cmul2(v0[o16(i)], T2Y[(i - 1) * 8 + q2]);
             }
             worker_bar(w);
 
-            // ================= pass 3: residues tA, tB of Y (radix 8) and Z (radix 16)
-            float2 ya[8], yb[8], za[16], zb[16];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) { ya[j] = Yb[yA + j]; yb[j] = Yb[yB + j]; }
+            // ================= pass 3: residues tA, tB; untangle; X to shared memory
+            float2 za[16], zb[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) { za[j] = Zb[zA + j]; zb[j] = Zb[zB + j]; }
-            // the buffers are dead from here: warps that finish early start the next frame's
-            // pass 1 while the others are still in the epilogue
-            worker_bar(w);
-            dft8(ya); dft8(yb);
             dft16(za); dft16(zb);
+            // 2 X[k] = Z[k] + conj Z[N-k],  2 X_th'[k] = (Z[k] - conj Z[N-k]) / j
+            float2 xa[8], xb[8], ta[8], tb[8];     // bins tA + 256 c and tB + 256 c, c = 0..7
+            if (p != 0) {
+                static_for<8>([&](auto cc) {
+                    constexpr int c = decltype(cc)::value;
+                    const float2 za_c = za[o16(c)], zb_n = cj(zb[o16(15 - c)]);
+                    const float2 zb_c = zb[o16(c)], za_n = cj(za[o16(15 - c)]);
+                    xa[c] = za_c + zb_n; ta[c] = mulmj(za_c - zb_n);
+                    xb[c] = zb_c + za_n; tb[c] = mulmj(zb_c - za_n);
+                    Xs[1 + tA + 256 * c] = xa[c];
+                    Xs[1 + tB + 256 * c] = xb[c];
+                });
+                if (p == 1) {      // Hermitian mirrors: X[-1] = conj X[1], X[N/2+1] = conj X[N/2-1]
+                    Xs[0] = cj(xa[0]);
+                    Xs[2050] = cj(xb[7]);
+                }
+            } else {
+                // residues 0 (bins 256 c, c = 0..8) and 128 (bins 128 + 256 c) pair with themselves
+                static_for<9>([&](auto cc) {
+                    constexpr int c = decltype(cc)::value;
+                    const float2 z = za[o16(c & 15)], zn = cj(za[o16((16 - c) & 15)]);
+                    Xs[1 + 256 * c] = z + zn;
+                    Sc[c] = mulmj(z - zn);
+                });
+                static_for<8>([&](auto cc) {
+                    constexpr int c = decltype(cc)::value;
+                    const float2 z = zb[o16(c)], zn = cj(zb[o16(15 - c)]);
+                    Xs[1 + 128 + 256 * c] = z + zn;
+                    Sc[9 + c] = mulmj(z - zn);
+                    xa[c] = z; xb[c] = z; ta[c] = z; tb[c] = z;        // placeholders, never stored
+                });
+            }
+            worker_bar(w);      // X visible; the Z buffer is free for the next frame's pass 1
 
-            // ================= epilogue
+            // ================= epilogue on the thread's own bins
             FrameCtx fc;
             fc.lo = (float)max(-f, -1048576LL);
             fc.hi = (float)min(a.F - 1 - f, 1048576LL);
-            fc.acc_row = (chan_off + f) * B;
             fc.f = f; fc.ch = ch;
-            fc.pd = a.dt_cols + fc.acc_row; fc.pk = a.dk_bins + fc.acc_row; fc.pe = a.energy + fc.acc_row;
-            // bins tA + 256 c and tB + 256 c, c = 0..7 (thread 0 tags along, its bins come below)
+            const long long row0 = (chan_off + f) * B;
+            fc.pd = a.dt_cols + row0; fc.pk = a.dk_bins + row0; fc.pe = a.energy + row0;
             static_for<8>([&](auto cc) {
                 constexpr int c = decltype(cc)::value;
-                bin_emit<MODE>(a, fc, owner, tA + 256 * c, tAf + (float)(256 * c), za[o16(c)],
-                               zb[o16(15 - c)], ya[o8(c)], yb[o8(7 - c)], mul_w16<c>(wA));
-                bin_emit<MODE>(a, fc, owner, tB + 256 * c, tBf + (float)(256 * c), zb[o16(c)],
-                               za[o16(15 - c)], yb[o8(c)], ya[o8(7 - c)], mul_w16<c>(wB));
+                bin_emit<MODE>(a, fc, owner, tA + 256 * c, tAf + (float)(256 * c), xa[c],
+                               Xs[tA + 256 * c], Xs[tA + 256 * c + 2], ta[c]);
+                bin_emit<MODE>(a, fc, owner, tB + 256 * c, tBf + (float)(256 * c), xb[c],
+                               Xs[tB + 256 * c], Xs[tB + 256 * c + 2], tb[c]);
             });
-            if (p < 32) {
-                // residues 0 and 128 pair with themselves: 17 bins through the scratch
-                if (p == 0) {
-#pragma unroll
-                    for (int c = 0; c < 16; ++c) { Sc[c] = za[o16(c)]; Sc[16 + c] = zb[o16(c)]; }
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) { Sc[32 + c] = ya[o8(c)]; Sc[40 + c] = yb[o8(c)]; }
-                }
-                __syncwarp();
-                const int l = ls;
-                float2 zk, zn, yk, yn;
-                if (l <= 8) {
-                    zk = Sc[l]; zn = Sc[(16 - l) & 15]; yk = Sc[32 + (l & 7)]; yn = Sc[32 + ((8 - l) & 7)];
-                } else {
-                    const int c = l - 9;
-                    zk = Sc[16 + c]; zn = Sc[16 + 15 - c]; yk = Sc[40 + c]; yn = Sc[40 + 7 - c];
-                }
-                bin_emit<MODE>(a, fc, p <= 16, ks, (float)ks, zk, zn, yk, yn, ws);
-            }
+            if (p < 32)   // the 17 self-paired bins, one per lane (the rest of the warp tags along)
+                bin_emit<MODE>(a, fc, p <= 16, ks, (float)ks, Xs[ks + 1], Xs[ks], Xs[ks + 2], Sc[ls]);
         }
     }
 }
