@@ -147,7 +147,7 @@ template <int LOG2N>
 static ems_status launch_generic(ems_handle* h, const StftArgs& a) {
     constexpr int N = 1 << LOG2N;
     constexpr int THREADS = 256;
-    const size_t smem = (size_t)N * 12;
+    const size_t smem = (size_t)N * 8;
     auto kern = stft_reassign_generic<LOG2N, THREADS>;
     EMS_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
@@ -174,7 +174,7 @@ static ems_status launch_big(ems_handle* h, const StftArgs& a) {
     long long grid = h->sm_count;
     if (grid > total) grid = total;
     if (grid < 1) return EMS_OK;
-    const size_t need = (size_t)h->sm_count * 2 * (N / 2 + 1) * sizeof(float2);
+    const size_t need = (size_t)h->sm_count * (N / 2 + 3) * sizeof(float2);
     if (h->big_scratch.bytes < need) {     // never reallocated inside a stream capture: sized for all SMs
         ems_status s = ensure(h, h->big_scratch, need);
         if (s != EMS_OK) return s;
@@ -409,7 +409,7 @@ static ems_status stream_init(ems_handle* h) {
     EMS_CUDA(h, cudaMallocHost(&st.out_pin, (size_t)C * B));
     ems_status s = stream_zero(h);
     if (s != EMS_OK) return s;
-    if (N == 32768 && (s = ensure(h, h->big_scratch, (size_t)h->sm_count * 2 * (N / 2 + 1) * sizeof(float2))) != EMS_OK) return s;
+    if (N == 32768 && (s = ensure(h, h->big_scratch, (size_t)h->sm_count * (N / 2 + 3) * sizeof(float2))) != EMS_OK) return s;
     st.ready = true;
     return EMS_OK;
 }

@@ -1,13 +1,15 @@
 // stft_generic.cuh — generic-N fused frame gather + 3-window STFT + reassignment.
 //
-// One CTA analyses one frame at a time (persistent, frame-strided grid).  Per frame:
-//   Z = FFT_N( x*h + j*x*th' )           th' = th*(2/N)     (two real FFTs in one complex)
-//   Y = FFT_{N/2}( w[2n] + j*w[2n+1] )   w = x*dh', dh' = dh*(N/pi) = sin(2 pi n/N)
-// Both run in shared memory as in-place radix-4 decimation-in-frequency passes (one
-// radix-2 pass if log2 is odd); results sit in digit-reversed order and the epilogue
-// reads Z[k], Z[N-k], Y[k], Y[N/2-k] to untangle X_h, X_th, X_dh and applies the
-// Auger-Flandrin operators (oracle/reassign_oracle.py::reassign_operators).
-// X_h, X_th, X_dh never leave the SM.  Used for every n_fft without a tuned kernel.
+// One CTA analyses one frame at a time (persistent, frame-strided grid).  Per frame ONE FFT:
+//   Z = FFT_N( x + j*x*th' ),  th' = th*(2/N)      (rectangular-window X and X_th' packed)
+// in shared memory as in-place radix-4 decimation-in-frequency passes (one radix-2 pass if
+// log2 is odd); results sit in digit-reversed order.  The epilogue untangles
+//   2 X[k] = Z[k] + conj Z[N-k],   2 X_th'[k] = (Z[k] - conj Z[N-k]) / j
+// and applies Hann and its derivative as three-tap stencils in frequency
+//   X_h[k] = X[k]/2 - (X[k-1] + X[k+1])/4,   X_dh'[k] = (X[k-1] - X[k+1]) / (2j)
+// (see stft_r16.cuh for the accuracy argument), then the Auger-Flandrin operators
+// (oracle/reassign_oracle.py::reassign_operators).  X_h, X_th, X_dh never leave the SM.
+// Used for every n_fft without a tuned kernel.
 #pragma once
 #include "common.cuh"
 
@@ -117,6 +119,17 @@ __device__ __forceinline__ void reassign_emit(const StftArgs& a, int ch,
     }
 }
 
+// 2 X[k] for any k in [-1, N/2+1] from the digit-reversed packed spectrum (Hermitian wrap)
+template <int LOG2N>
+__device__ __forceinline__ float2 rect2(const float2* __restrict__ Z, int k) {
+    constexpr int N = 1 << LOG2N;
+    const int kk = k < 0 ? -k : (k > N / 2 ? N - k : k);          // X[-k] = X[N-k] = conj X[k]
+    const float2 zk = Z[dif_pos<LOG2N>(kk)];
+    const float2 zn = Z[dif_pos<LOG2N>((N - kk) & (N - 1))];
+    const float2 x = make_float2(zk.x + zn.x, zk.y - zn.y);
+    return kk == k ? x : make_float2(x.x, -x.y);
+}
+
 template <int LOG2N, int THREADS>
 __global__ void __launch_bounds__(THREADS)
 stft_reassign_generic(const StftArgs a_in) {
@@ -125,8 +138,6 @@ stft_reassign_generic(const StftArgs a_in) {
     if (!stream_decode(a)) return;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* Z = reinterpret_cast<float2*>(smem_raw);          // [N]
-    float2* Y = Z + N;                                         // [N/2]
-    float* Yf = reinterpret_cast<float*>(Y);                   // w[n] interleaved = Y packed
     const int tid = threadIdx.x;
     const long long per_ch = a.f_end - a.f_begin;
     const long long total = per_ch * a.channels;
@@ -137,36 +148,30 @@ stft_reassign_generic(const StftArgs a_in) {
         const float* x = a.pcm + (long long)ch * a.S + f * a.hop + a.samp_off;
         for (int n = tid; n < N; n += THREADS) {
             const float v = __ldg(x + n);
-            const float4 w = __ldg(&a.win[n]);
-            Z[n] = make_float2(v * w.x, v * w.y);
-            Yf[n] = v * w.z;
+            Z[n] = make_float2(v, v * __ldg(&a.win[n]).y);
         }
         __syncthreads();
         fft_inplace_dif<LOG2N>(Z, a.tw, 0, tid, THREADS);
-        fft_inplace_dif<LOG2N - 1>(Y, a.tw, 1, tid, THREADS);
 
         for (int k = tid; k <= N / 2; k += THREADS) {
             const float2 zk = Z[dif_pos<LOG2N>(k)];
             const float2 zn = Z[dif_pos<LOG2N>((N - k) & (N - 1))];
-            const float2 yk = Y[dif_pos<LOG2N - 1>(k & (N / 2 - 1))];
-            const float2 yn = Y[dif_pos<LOG2N - 1>((N / 2 - k) & (N / 2 - 1))];
-            const float2 A2 = make_float2(zk.x + zn.x, zk.y - zn.y);
-            const float2 B2 = make_float2(zk.y + zn.y, zn.x - zk.x);
-            const float2 E2 = make_float2(yk.x + yn.x, yk.y - yn.y);
-            const float2 O2 = make_float2(yk.y + yn.y, yn.x - yk.x);
-            const float2 w = __ldg(&a.tw[k]);                  // W_N^k = (cos, -sin)
-            const float2 D2 = make_float2(E2.x + (w.x * O2.x - w.y * O2.y),
-                                          E2.y + (w.x * O2.y + w.y * O2.x));
+            const float2 xk = make_float2(zk.x + zn.x, zk.y - zn.y);          // 2 X[k]
+            const float2 B2 = make_float2(zk.y + zn.y, zn.x - zk.x);          // 2 X_th'[k]
+            const float2 xm = rect2<LOG2N>(Z, k - 1), xp = rect2<LOG2N>(Z, k + 1);
+            const float2 A2 = make_float2(0.5f * xk.x - 0.25f * (xm.x + xp.x),
+                                          0.5f * xk.y - 0.25f * (xm.y + xp.y));   // 2 X_h
+            const float2 D2 = make_float2(0.5f * (xm.y - xp.y), -0.5f * (xm.x - xp.x));   // 2 X_dh'
             reassign_emit<N>(a, ch, f, k, A2, B2, D2);
         }
         __syncthreads();
     }
 }
 
-// n_fft too large for Z and Y to share the SM (32768: 384 KB): the three real FFTs run one
-// after another as half-size complex FFTs (N/2 points, 4N bytes of shared memory), X_h and
-// X_th wait in an L2-resident per-CTA scratch until X_dh is ready.  Same arithmetic and
-// decisions as the kernel above; only used where that one cannot be launched.
+// n_fft whose packed spectrum does not fit the SM (32768: 256 KB): the two real FFTs (x and
+// x*th') run one after another as half-size complex FFTs (N/2 points, 4N bytes of shared
+// memory); 2 X waits in an L2-resident per-CTA scratch until X_th' is ready.  Same
+// arithmetic and decisions as the kernel above; only used where that one cannot be launched.
 template <int LOG2N, int THREADS>
 __global__ void __launch_bounds__(THREADS)
 stft_reassign_big(const StftArgs a_in, float2* __restrict__ scratch_all) {
@@ -176,7 +181,7 @@ stft_reassign_big(const StftArgs a_in, float2* __restrict__ scratch_all) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* Y = reinterpret_cast<float2*>(smem_raw);          // [N/2]
     float* Yf = reinterpret_cast<float*>(Y);
-    float2* scratch = scratch_all + (size_t)blockIdx.x * 2 * B;   // [2][B]: 2 X_h, 2 X_th'
+    float2* X2 = scratch_all + (size_t)blockIdx.x * (B + 2) + 1;   // 2 X[k], k = -1 .. N/2+1
     const int tid = threadIdx.x;
     const long long per_ch = a.f_end - a.f_begin;
     const long long total = per_ch * a.channels;
@@ -186,25 +191,33 @@ stft_reassign_big(const StftArgs a_in, float2* __restrict__ scratch_all) {
         const long long f = a.f_begin + (it - (long long)ch * per_ch);
         const float* x = a.pcm + (long long)ch * a.S + f * a.hop + a.samp_off;
 #pragma unroll 1
-        for (int wi = 0; wi < 3; ++wi) {
-            for (int n = tid; n < N; n += THREADS) {
-                const float4 w = __ldg(&a.win[n]);
-                Yf[n] = __ldg(x + n) * (wi == 0 ? w.x : wi == 1 ? w.y : w.z);
-            }
+        for (int wi = 0; wi < 2; ++wi) {
+            for (int n = tid; n < N; n += THREADS)
+                Yf[n] = wi == 0 ? __ldg(x + n) : __ldg(x + n) * __ldg(&a.win[n]).y;
             __syncthreads();
             fft_inplace_dif<LOG2N - 1>(Y, a.tw, 1, tid, THREADS);
+            // real FFT of length N from the N/2-point FFT of its even/odd samples
             for (int k = tid; k <= H2; k += THREADS) {
                 const float2 yk = Y[dif_pos<LOG2N - 1>(k & (H2 - 1))];
                 const float2 yn = Y[dif_pos<LOG2N - 1>((H2 - k) & (H2 - 1))];
                 const float2 E2 = make_float2(yk.x + yn.x, yk.y - yn.y);
                 const float2 O2 = make_float2(yk.y + yn.y, yn.x - yk.x);
                 const float2 w = __ldg(&a.tw[k]);
-                const float2 X2 = make_float2(E2.x + (w.x * O2.x - w.y * O2.y),
+                const float2 R2 = make_float2(E2.x + (w.x * O2.x - w.y * O2.y),
                                               E2.y + (w.x * O2.y + w.y * O2.x));
-                if (wi < 2) scratch[wi * B + k] = X2;
-                else reassign_emit<N>(a, ch, f, k, scratch[k], scratch[B + k], X2);
+                if (wi == 0) {
+                    X2[k] = R2;
+                    if (k == 1) X2[-1] = make_float2(R2.x, -R2.y);
+                    if (k == H2 - 1) X2[H2 + 1] = make_float2(R2.x, -R2.y);
+                } else {
+                    const float2 xk = X2[k], xm = X2[k - 1], xp = X2[k + 1];
+                    const float2 A2 = make_float2(0.5f * xk.x - 0.25f * (xm.x + xp.x),
+                                                  0.5f * xk.y - 0.25f * (xm.y + xp.y));
+                    const float2 D2 = make_float2(0.5f * (xm.y - xp.y), -0.5f * (xm.x - xp.x));
+                    reassign_emit<N>(a, ch, f, k, A2, R2, D2);
+                }
             }
-            __syncthreads();
+            __syncthreads();     // also orders the scratch writes of pass 0 before pass 1 reads them
         }
     }
 }
