@@ -246,9 +246,17 @@ stft_reassign_r16(const StftArgs a_in, const int tile_T) {
     for (int e = tid; e < kT2; e += kThreads) { const int i = e / 16 + 1, q = e % 16; T2[e] = __ldg(&a.tw[16 * q * i]); }
 
     // ---- per-thread constants
-    const float2 twp = __ldg(&a.tw[p]);                    // (cos, -sin)(2 pi p / 4096)
-    const float cp = twp.x, sp = -twp.y;
-    const float rp = (float)(p - N / 2) * (1.0f / (N / 2)); // ramp of th' at n = p
+    // th'[n] = ((n - N/2) / (N/2)) * (0.5 - 0.5 cos(2 pi n / N)) at this thread's 32 pass-1
+    // samples n = p + 128 u + 256 j: frame-independent, so they live in registers for the whole
+    // persistent loop (cos from the table entry of n, exact to fp32 rounding)
+    float thw[2][16];
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const int n = p + 128 * u + 256 * j;
+            thw[u][j] = (float)(n - N / 2) * (1.0f / (N / 2)) * (0.5f - 0.5f * __ldg(&a.tw[n]).x);
+        }
     const int tA = p, tB = p ? 256 - p : 128;              // output residues of this thread
     const int zA = 257 * (tA & 15) + 16 * (tA >> 4), zB = 257 * (tB & 15) + 16 * (tB >> 4);
     const int i1 = p & 15, q2 = p >> 4;                    // pass-2 butterfly coordinates
@@ -295,27 +303,20 @@ stft_reassign_r16(const StftArgs a_in, const int tile_T) {
             const long long f = f0 + fi;
 
             // ================= pass 1: butterflies b = p, p + 128 on z[n] = x[n] (1 + j th'[n])
-#pragma unroll 1
-            for (int u = 0; u < 2; ++u) {
+            static_for<2>([&](auto uc) {
+                constexpr int u = decltype(uc)::value;
                 const int b = p + 128 * u;
-                // base angle of sample b: theta_p (+ pi/16 for the second butterfly)
-                const float cb = u ? cp * c32(1) - sp * s32(1) : cp;
-                const float sb = u ? sp * c32(1) + cp * s32(1) : sp;
-                const float rb = rp + (float)u * (1.0f / 16.0f);
                 float2 v[16];
-                static_for<16>([&](auto jc) {
-                    constexpr int j = decltype(jc)::value;             // n = b + 256 j
-                    constexpr float cq = c32(2 * j), sq = s32(2 * j), rq = (float)j * (1.0f / 8.0f);
-                    const float x = xs[b + 256 * j];
-                    const float cs = cb * cq - sb * sq;                // cos(2 pi n / N)
-                    const float h = 0.5f - 0.5f * cs;
-                    v[j] = make_float2(x, (x * h) * (rb + rq));        // th' = ramp * h
-                });
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const float x = xs[b + 256 * j];                   // n = b + 256 j
+                    v[j] = make_float2(x, x * thw[u][j]);
+                }
                 dft16(v);
                 Zb[b] = v[o16(0)];
 #pragma unroll
                 for (int i = 1; i < 16; ++i) Zb[b + 257 * i] = cmul2(v[o16(i)], Ztab[(i - 1) * 256 + b]);
-            }
+            });
             worker_bar(w);
 
             // ================= pass 2: sub-FFTs of length 256, butterflies (i1, q2), (i1, q2 + 8),
