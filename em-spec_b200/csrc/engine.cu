@@ -40,7 +40,7 @@ struct ems_handle {
     float4* win = nullptr;              // [N]
     float2* tw = nullptr;               // [N]
     float*  weight = nullptr;           // [B]
-    ems::DevBuf acc, flags, carry, ema_local, ema_carry, host_pcm, host_i16, host_idx, host_grid, big_scratch;
+    ems::DevBuf acc, flags, carry, ema_local, ema_carry, host_pcm, host_i16, host_idx, host_grid, big_scratch, lut;
     bool acc_clean = false;             // accumulator and dirty flags are all zero (kept so by the post-pass)
     cudaEvent_t ev[EMS_STAGE_COUNT][2]{};
     bool ev_valid[EMS_STAGE_COUNT]{};
@@ -536,7 +536,7 @@ ems_status ems_create(const ems_params* params, ems_handle** out) {
 ems_status ems_destroy(ems_handle* h) {
     if (!h) return EMS_ERR_INVALID_ARG;
     if (h->stream) cudaStreamSynchronize(h->stream);
-    for (DevBuf* b : {&h->acc, &h->flags, &h->carry, &h->ema_local, &h->ema_carry, &h->host_pcm, &h->host_i16,
+    for (DevBuf* b : {&h->acc, &h->flags, &h->carry, &h->ema_local, &h->ema_carry, &h->host_pcm, &h->host_i16, &h->lut,
                       &h->host_idx, &h->host_grid, &h->big_scratch})
         if (b->p) cudaFree(b->p);
     stream_free(h);
@@ -783,6 +783,23 @@ ems_status ems_process_host(ems_handle* h, const float* pcm_host, size_t S, floa
 ems_status ems_process_host_i16(ems_handle* h, const int16_t* pcm_host, size_t S, float* grid_host,
                                 uint8_t* index_host, size_t* n_frames) {
     return process_host_impl(h, pcm_host, true, S, grid_host, index_host, n_frames);
+}
+
+ems_status ems_colorize(ems_handle* h, const uint8_t* index_dev, size_t n_cells,
+                        const uint32_t* lut_host, uint32_t* rgba_dev) {
+    if (!h) return EMS_ERR_INVALID_ARG;
+    if (n_cells == 0) return EMS_OK;
+    if (!index_dev || !lut_host || !rgba_dev) return fail(h, EMS_ERR_INVALID_ARG, "null buffer");
+    ems_status s = ensure(h, h->lut, 256 * sizeof(uint32_t));
+    if (s != EMS_OK) return s;
+    EMS_CUDA(h, cudaMemcpyAsync(h->lut.p, lut_host, 256 * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
+    size_t blocks = (n_cells / 16 + 255) / 256 + 1;
+    const size_t cap = (size_t)h->sm_count * 16;
+    if (blocks > cap) blocks = cap;
+    colorize_kernel<<<(unsigned)blocks, 256, 0, h->stream>>>(index_dev, rgba_dev, n_cells, (const uint32_t*)h->lut.p);
+    ++h->launches;
+    EMS_CUDA(h, cudaGetLastError());
+    return finish(h);
 }
 
 ems_status ems_stage_ms(ems_handle* h, int stage, float* ms) {

@@ -216,6 +216,34 @@ __global__ void pcm_i16_to_planar_kernel(const int16_t* __restrict__ in, float* 
     }
 }
 
+// Colour map: rgba[i] = lut[index[i]].  HBM-bound (1 B read, 4 B written per cell): the body
+// moves 16 indices -> four 16-byte stores per thread; head/tail cells keep any alignment legal.
+__global__ void __launch_bounds__(256)
+colorize_kernel(const uint8_t* __restrict__ index, uint32_t* __restrict__ rgba, size_t n,
+                const uint32_t* __restrict__ lut_dev) {
+    __shared__ uint32_t lut[256];
+    lut[threadIdx.x] = lut_dev[threadIdx.x];
+    __syncthreads();
+    const size_t head = min(n, (size_t)((16 - ((uintptr_t)index & 15)) & 15));   // to 16-byte alignment of index
+    const size_t nvec = (n - head) / 16;
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = tid; i < head; i += nth) rgba[i] = lut[index[i]];
+    const uint4* iv = reinterpret_cast<const uint4*>(index + head);
+    for (size_t v = tid; v < nvec; v += nth) {
+        const uint4 q = __ldg(iv + v);
+        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+        uint32_t* o = rgba + head + v * 16;          // 4-byte aligned, stores as 32-bit words
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            o[4 * j + 0] = lut[w[j] & 255];
+            o[4 * j + 1] = lut[(w[j] >> 8) & 255];
+            o[4 * j + 2] = lut[(w[j] >> 16) & 255];
+            o[4 * j + 3] = lut[w[j] >> 24];
+        }
+    }
+    for (size_t i = head + nvec * 16 + tid; i < n; i += nth) rgba[i] = lut[index[i]];
+}
+
 // Clears the dirty flags of columns [c0, c1) of every (channel, bin block) row.
 __global__ void clear_flags_kernel(unsigned char* __restrict__ flags, long long F, long long c0,
                                    long long c1, int rows) {

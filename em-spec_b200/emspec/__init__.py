@@ -58,6 +58,7 @@ _SIG = {
     "ems_scatter_points": (C.c_int, [_VP, _FP, _FP, _FP, C.c_size_t, _FP, _U8P]),
     "ems_process_host": (C.c_int, [_VP, _FP, C.c_size_t, _FP, _U8P, C.POINTER(C.c_size_t)]),
     "ems_process_host_i16": (C.c_int, [_VP, _FP, C.c_size_t, _FP, _U8P, C.POINTER(C.c_size_t)]),
+    "ems_colorize": (C.c_int, [_VP, _U8P, C.c_size_t, _VP, _VP]),
     "ems_stage_ms": (C.c_int, [_VP, C.c_int, C.POINTER(C.c_float)]),
     "ems_launch_count": (C.c_int, [_VP, C.POINTER(C.c_uint64)]),
     "ems_stream_push": (C.c_int, [_VP, _FP, _U8P, C.POINTER(C.c_int), C.POINTER(C.c_int64)]),
@@ -254,6 +255,18 @@ class Engine:
         self._check(self.lib.ems_process_host_i16(self.h, _ptr(pcm_i16), S, _ptr(grid_out),
                                                   _ptr(index_out), C.byref(n)))
         return grid_out, index_out
+
+    def colorize(self, index, lut_rgba):
+        """index: CUDA u8 tensor (any shape); lut_rgba: 256 uint32 (numpy / CPU tensor, 0xAABBGGRR)
+        -> CUDA int32 tensor of the same shape holding the packed pixels."""
+        import numpy as np
+        import torch
+        lut = np.ascontiguousarray(np.asarray(lut_rgba, dtype=np.uint32))
+        assert lut.size == 256 and index.is_cuda and index.dtype == torch.uint8 and index.is_contiguous()
+        out = torch.empty(index.shape, dtype=torch.int32, device=index.device)
+        self._check(self.lib.ems_colorize(self.h, _ptr(index), index.numel(),
+                                          C.c_void_p(lut.ctypes.data), _ptr(out)))
+        return out
 
     # ------------------------------------------------------------------ streaming
     def stream_reset(self):

@@ -144,6 +144,13 @@ ems_status ems_process_host(ems_handle* h, const float* pcm_host, size_t n_sampl
 ems_status ems_process_host_i16(ems_handle* h, const int16_t* pcm_host, size_t n_samples_per_ch,
                                 float* grid_host, uint8_t* index_host, size_t* n_frames);
 
+/* Colour map ("Color Map", /root/reference/README.md:15,45): applies a
+ * 256-entry RGBA table (HOST pointer, packed 0xAABBGGRR like a byte-wise R,G,B,A store) to
+ * n_cells colour indices on the device; rgba_dev receives n_cells 32-bit pixels in the same
+ * [channels][F][R] order, ready to blit as columns. */
+ems_status ems_colorize(ems_handle* h, const uint8_t* index_dev, size_t n_cells,
+                        const uint32_t* lut_rgba_host, uint32_t* rgba_dev);
+
 /* Device milliseconds of a stage of the last offline call on this handle (after the
  * stream has been synchronised); EMS_ERR_STATE if that stage did not run. */
 ems_status ems_stage_ms(ems_handle* h, int stage, float* ms);

@@ -249,6 +249,26 @@ def test_int16_interleaved_ingest(emspec):
         check_grid(g16[c].numpy(), xf[c], prm)
 
 
+def test_colour_map_lut_is_bit_exact(emspec):
+    """256-entry RGBA table lookup (README.md:15,45), integer work -> bit-exact,
+    any alignment and length (head / 16-byte body / tail paths)."""
+    rng = np.random.default_rng(5)
+    lut = rng.integers(0, 2 ** 32, 256, dtype=np.uint64).astype(np.uint32)
+    eng = emspec.Engine(n_fft=1024, hop=256, flags=emspec.FLAG_REASSIGN | emspec.FLAG_DETERMINISTIC | emspec.FLAG_SYNC)
+    base = torch.from_numpy(rng.integers(0, 256, 100003, dtype=np.uint8)).cuda()
+    for off, n in ((0, 100003), (1, 100000), (7, 15), (13, 4099), (16, 64), (3, 0)):
+        idx = base[off:off + n]
+        out = eng.colorize(idx.contiguous() if n == 0 else idx, lut)
+        want = lut[idx.cpu().numpy()].astype(np.uint32)
+        assert (out.cpu().numpy().view(np.uint32) == want).all()
+    # on a real image
+    x = torch.from_numpy(orc.synth_signal(SR // 2, SR, seed=16)).cuda()
+    _, img = eng.process_grid(x, want_grid=False)
+    rgba = eng.colorize(img, lut)
+    assert (rgba.cpu().numpy().view(np.uint32) == lut[img.cpu().numpy()]).all()
+    eng.close()
+
+
 def test_golden_fixture(emspec):
     """Committed fixture (tests/golden/make_golden.py): CUDA path vs stored oracle output."""
     z = np.load(os.path.join(GOLD, "reassign_n512_h128.npz"))
