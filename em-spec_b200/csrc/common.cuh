@@ -105,6 +105,9 @@ struct PostArgs {
     float         db_floor;   // TOP_DB - range
     float         inv_range;  // 255 / range
     float         gate_db;
+    float*        colscale;   // AGC: [channels][F] level^-strength per column (peaks while measuring), or null
 };
+
+constexpr float kAgcReleaseSeconds = 1.0f;
 
 }  // namespace ems

@@ -40,7 +40,7 @@ struct ems_handle {
     float4* win = nullptr;              // [N]
     float2* tw = nullptr;               // [N]
     float*  weight = nullptr;           // [B]
-    ems::DevBuf acc, flags, carry, ema_local, ema_carry, host_pcm, host_i16, host_idx, host_grid, big_scratch, lut;
+    ems::DevBuf acc, flags, carry, ema_local, ema_carry, host_pcm, host_i16, host_idx, host_grid, big_scratch, lut, colscale, agc_level;
     bool acc_clean = false;             // accumulator and dirty flags are all zero (kept so by the post-pass)
     cudaEvent_t ev[EMS_STAGE_COUNT][2]{};
     bool ev_valid[EMS_STAGE_COUNT]{};
@@ -55,6 +55,8 @@ struct ems_handle {
         void* acc = nullptr;             // [channels][ring_cols][B]
         float* carry = nullptr;          // [channels][B]
         uint8_t* out_dev = nullptr;      // [channels][B]
+        float* etmp = nullptr;           // [channels][B]
+        float* agc = nullptr;            // [2][channels]
         float* in_pin = nullptr;         // pinned staging
         uint8_t* out_pin = nullptr;
         int M = 0, Lr = 0, R = 0, ring_cols = 0;
@@ -103,6 +105,7 @@ static bool valid_params(const ems_params& p) {
     if (!std::isfinite(p.noise_gate_db)) return false;
     if (p.display_rows < 0 || p.display_rows == 1 || p.display_rows > 65536) return false;
     if (!(p.freq_scale >= 0.f) || !(p.freq_scale <= 4.f)) return false;
+    if (!(p.agc_strength >= 0.f) || !(p.agc_strength <= 1.f)) return false;
     return true;
 }
 
@@ -206,8 +209,15 @@ static ems_status launch_r16(ems_handle* h, const StftArgs& a, int tile_T) {
 
 static ems_status launch_stft(ems_handle* h, const StftArgs& a) {
     if (h->prm.n_fft == 4096 && !h->force_generic) {
-        const int tile_T = r16::tile_frames(a.hop);
-        if (tile_T >= r16::kWorkers) return launch_r16(h, a, tile_T);
+        int tile_T = r16::tile_frames(a.hop);
+        if (tile_T >= r16::kWorkers) {
+            // short inputs: smaller tiles so that every SM gets one
+            const long long per_ch = a.f_end - a.f_begin;
+            const long long want = (per_ch * a.channels + h->sm_count - 1) / h->sm_count;
+            const long long t = ((want + r16::kWorkers - 1) / r16::kWorkers) * r16::kWorkers;
+            if (t < tile_T) tile_T = (int)std::max<long long>(t, r16::kWorkers);
+            return launch_r16(h, a, tile_T);
+        }
     }
     switch (ilog2(h->prm.n_fft)) {
         case 8:  return launch_generic<8>(h, a);
@@ -267,6 +277,23 @@ static ems_status run_post(ems_handle* h, PostArgs p) {
     const long long ncols = p.col_end - p.col_begin;
     if (ncols <= 0) return EMS_OK;
     const bool ema = p.smoothing > 0.f && p.index;
+    const bool agc = h->prm.agc_strength > 0.f && p.index;
+    const float lambda = std::exp(-(float)h->prm.hop / (h->prm.sample_rate * kAgcReleaseSeconds));
+    p.colscale = nullptr;
+    if (agc) {      // column peaks are accumulated into colscale, then turned into level^-strength
+        ems_status s = ensure(h, h->colscale, (size_t)p.channels * p.F * sizeof(float));
+        if (s != EMS_OK) return s;
+        p.colscale = (float*)h->colscale.p;
+        for (int ch = 0; ch < p.channels; ++ch)
+            EMS_CUDA(h, cudaMemsetAsync(p.colscale + (size_t)ch * p.F + p.col_begin, 0,
+                                        (size_t)ncols * sizeof(float), h->stream));
+    }
+    auto agc_scan = [&]() {
+        agc_scan_kernel<<<p.channels, 1024, 0, h->stream>>>(p.colscale, (float*)h->agc_level.p, p.F,
+                                                            p.col_begin, p.col_end, lambda,
+                                                            h->prm.agc_strength);
+        ++h->launches;
+    };
     if (!ema) {
         // no recurrence along time: zero-fill the outputs, then visit only the dirty blocks
         for (int ch = 0; ch < p.channels; ++ch) {
@@ -275,39 +302,43 @@ static ems_status run_post(ems_handle* h, PostArgs p) {
             if (p.grid) EMS_CUDA(h, cudaMemsetAsync(p.grid + off, 0, cnt * sizeof(float), h->stream));
         }
         const dim3 g((unsigned)((ncols + 255) / 256), p.channels * p.NB);
-        post_sparse_kernel<<<g, 256, 0, h->stream>>>(p);
+        if (agc) {
+            post_sparse_kernel<<<g, 256, 0, h->stream>>>(p, 1);
+            ++h->launches;
+            agc_scan();
+        }
+        post_sparse_kernel<<<g, 256, 0, h->stream>>>(p, 0);
         ++h->launches;
         EMS_CUDA(h, cudaGetLastError());
         return EMS_OK;
     }
     // With smoothing the EMA runs along time: 256-column chunks, local pass + carries + emit,
     // then the flags of the covered columns are cleared.
-    const int chunk_cols = ema ? kPostChunk : kPostTile;
+    const int chunk_cols = kPostChunk;
     const long long n_chunks = (ncols + chunk_cols - 1) / chunk_cols;
     const dim3 blk(128);
     const dim3 grd((unsigned)n_chunks, (p.B + 127) / 128, p.channels);
-    const float* carry_in = nullptr;
-    if (ema) {
-        const size_t bytes = (size_t)p.channels * n_chunks * p.B * sizeof(float);
-        ems_status s;
-        if ((s = ensure(h, h->ema_local, bytes)) != EMS_OK) return s;
-        if ((s = ensure(h, h->ema_carry, bytes)) != EMS_OK) return s;
-        p.carry = (float*)h->carry.p;
-        post_ema_local_kernel<<<grd, blk, 0, h->stream>>>(p, (float*)h->ema_local.p, (int)n_chunks);
-        const long long last = ncols - (n_chunks - 1) * kPostChunk;
-        post_ema_carry_kernel<<<dim3((p.B + 127) / 128, p.channels), blk, 0, h->stream>>>(
-            p, (const float*)h->ema_local.p, (float*)h->ema_carry.p, (int)n_chunks,
-            (float)std::pow((double)p.smoothing, (double)kPostChunk),
-            (float)std::pow((double)p.smoothing, (double)last));
-        h->launches += 2;
-        carry_in = (const float*)h->ema_carry.p;
+    const size_t bytes = (size_t)p.channels * n_chunks * p.B * sizeof(float);
+    ems_status s;
+    if ((s = ensure(h, h->ema_local, bytes)) != EMS_OK) return s;
+    if ((s = ensure(h, h->ema_carry, bytes)) != EMS_OK) return s;
+    p.carry = (float*)h->carry.p;
+    post_ema_local_kernel<<<grd, blk, 0, h->stream>>>(p, (float*)h->ema_local.p, (int)n_chunks);
+    const long long last = ncols - (n_chunks - 1) * kPostChunk;
+    post_ema_carry_kernel<<<dim3((p.B + 127) / 128, p.channels), blk, 0, h->stream>>>(
+        p, (const float*)h->ema_local.p, (float*)h->ema_carry.p, (int)n_chunks,
+        (float)std::pow((double)p.smoothing, (double)kPostChunk),
+        (float)std::pow((double)p.smoothing, (double)last));
+    h->launches += 2;
+    const float* carry_in = (const float*)h->ema_carry.p;
+    if (agc) {
+        post_emit_kernel<<<grd, blk, 0, h->stream>>>(p, carry_in, (int)n_chunks, chunk_cols, 1);
+        ++h->launches;
+        agc_scan();
     }
-    post_emit_kernel<<<grd, blk, 0, h->stream>>>(p, carry_in, (int)n_chunks, chunk_cols);
+    post_emit_kernel<<<grd, blk, 0, h->stream>>>(p, carry_in, (int)n_chunks, chunk_cols, 0);
     ++h->launches;
-    {
-        ems_status s = clear_flags(h, p.F, p.col_begin, p.col_end, p.B);
-        if (s != EMS_OK) return s;
-    }
+    if ((s = clear_flags(h, p.F, p.col_begin, p.col_end, p.B)) != EMS_OK) return s;
     EMS_CUDA(h, cudaGetLastError());
     return EMS_OK;
 }
@@ -351,6 +382,8 @@ static ems_status reset_carry(ems_handle* h) {
     ems_status s = ensure(h, h->carry, bytes);
     if (s != EMS_OK) return s;
     EMS_CUDA(h, cudaMemsetAsync(h->carry.p, 0, bytes, h->stream));
+    if ((s = ensure(h, h->agc_level, (size_t)h->prm.channels * sizeof(float))) != EMS_OK) return s;
+    EMS_CUDA(h, cudaMemsetAsync(h->agc_level.p, 0, (size_t)h->prm.channels * sizeof(float), h->stream));
     return EMS_OK;
 }
 
@@ -371,7 +404,7 @@ static void stream_free(ems_handle* h) {
     auto& st = h->st;
     if (st.graph) cudaGraphExecDestroy(st.graph);
     for (void* p : {(void*)st.sstate, (void*)st.in_dev, (void*)st.ring, st.acc, (void*)st.carry,
-                    (void*)st.out_dev})
+                    (void*)st.out_dev, (void*)st.etmp, (void*)st.agc})
         if (p) cudaFree(p);
     if (st.in_pin) cudaFreeHost(st.in_pin);
     if (st.out_pin) cudaFreeHost(st.out_pin);
@@ -385,6 +418,7 @@ static ems_status stream_zero(ems_handle* h) {
     EMS_CUDA(h, cudaMemsetAsync(st.ring, 0, sizeof(float) * C * 2 * st.Lr, h->stream));
     EMS_CUDA(h, cudaMemsetAsync(st.acc, 0, st.acc_bytes, h->stream));
     EMS_CUDA(h, cudaMemsetAsync(st.carry, 0, sizeof(float) * C * B, h->stream));
+    EMS_CUDA(h, cudaMemsetAsync(st.agc, 0, sizeof(float) * 2 * C, h->stream));
     EMS_CUDA(h, cudaStreamSynchronize(h->stream));
     st.pushes = 0;
     return EMS_OK;
@@ -405,6 +439,8 @@ static ems_status stream_init(ems_handle* h) {
     EMS_CUDA(h, cudaMalloc(&st.acc, st.acc_bytes));
     EMS_CUDA(h, cudaMalloc(&st.carry, sizeof(float) * C * B));
     EMS_CUDA(h, cudaMalloc(&st.out_dev, (size_t)C * B));
+    EMS_CUDA(h, cudaMalloc(&st.etmp, sizeof(float) * C * B));
+    EMS_CUDA(h, cudaMalloc(&st.agc, sizeof(float) * 2 * C));
     EMS_CUDA(h, cudaMallocHost(&st.in_pin, sizeof(float) * H * C));
     EMS_CUDA(h, cudaMallocHost(&st.out_pin, (size_t)C * B));
     ems_status s = stream_zero(h);
@@ -430,6 +466,8 @@ static ems_status stream_capture(ems_handle* h) {
     sa.db_floor = (float)(kTopDb - (double)h->prm.db_range);
     sa.inv_range = 255.0f / h->prm.db_range;
     sa.gate_db = h->prm.noise_gate_db;
+    sa.etmp = st.etmp; sa.agc = st.agc; sa.agc_strength = h->prm.agc_strength;
+    sa.agc_lambda = std::exp(-(float)H / (h->prm.sample_rate * kAgcReleaseSeconds));
     StftArgs a = make_args(h, st.ring, (size_t)2 * st.Lr, /*F=*/(long long)1 << 60);
     a.f_begin = 0; a.f_end = 1;                       // grid sizing; the kernel decodes the real frame
     a.acc = st.acc; a.mode = det ? kDepositU64 : kDepositF32;
@@ -440,8 +478,9 @@ static ems_status stream_capture(ems_handle* h) {
     cudaMemcpyAsync(st.in_dev, st.in_pin, sizeof(float) * H * C, cudaMemcpyHostToDevice, h->stream);
     stream_ingest_kernel<<<(H * C + 255) / 256, 256, 0, h->stream>>>(sa);
     ems_status ls = launch_stft(h, a);
-    stream_post_kernel<<<(B * C + 255) / 256, 256, 0, h->stream>>>(sa);
-    stream_advance_kernel<<<1, 1, 0, h->stream>>>(st.sstate);
+    stream_shape_kernel<<<(B * C + 255) / 256, 256, 0, h->stream>>>(sa);
+    stream_emit_kernel<<<(B * C + 255) / 256, 256, 0, h->stream>>>(sa);
+    stream_advance_kernel<<<1, 1, 0, h->stream>>>(sa);
     cudaMemcpyAsync(st.out_pin, st.out_dev, (size_t)C * B, cudaMemcpyDeviceToHost, h->stream);
     cudaError_t ce = cudaStreamEndCapture(h->stream, &g);
     h->launches -= 1;                                  // counted per push below, not at capture
@@ -482,7 +521,7 @@ ems_status ems_default_params(ems_params* p) {
     p->db_range = 58.f; p->gain = 3.5f; p->low_end_boost = 3.9f; p->smoothing = 0.f;
     p->noise_gate_db = -65.f;
     p->flags = EMS_FLAG_REASSIGN | EMS_FLAG_DETERMINISTIC;
-    p->display_rows = 0; p->freq_scale = 1.0f;
+    p->display_rows = 0; p->freq_scale = 1.0f; p->agc_strength = 0.0f;
     return EMS_OK;
 }
 
@@ -536,7 +575,7 @@ ems_status ems_create(const ems_params* params, ems_handle** out) {
 ems_status ems_destroy(ems_handle* h) {
     if (!h) return EMS_ERR_INVALID_ARG;
     if (h->stream) cudaStreamSynchronize(h->stream);
-    for (DevBuf* b : {&h->acc, &h->flags, &h->carry, &h->ema_local, &h->ema_carry, &h->host_pcm, &h->host_i16, &h->lut,
+    for (DevBuf* b : {&h->acc, &h->flags, &h->carry, &h->ema_local, &h->ema_carry, &h->host_pcm, &h->host_i16, &h->lut, &h->colscale, &h->agc_level,
                       &h->host_idx, &h->host_grid, &h->big_scratch})
         if (b->p) cudaFree(b->p);
     stream_free(h);
@@ -826,7 +865,7 @@ ems_status ems_stream_push(ems_handle* h, const float* pcm_host, uint8_t* column
     const int H = h->prm.hop, C = h->prm.channels, B = rows_of(h->prm);
     memcpy(st.in_pin, pcm_host, sizeof(float) * H * C);
     EMS_CUDA(h, cudaGraphLaunch(st.graph, h->stream));
-    h->launches += 4;
+    h->launches += 5;
     EMS_CUDA(h, cudaStreamSynchronize(h->stream));
     const long long cf = st.pushes + 1 - st.M - st.R;   // column finalised by this push
     ++st.pushes;

@@ -44,12 +44,30 @@ __device__ __forceinline__ float acc_load(const void* acc, int is_u64, long long
     return reinterpret_cast<const float*>(acc)[o];
 }
 
+// E: shaped energy (the noise gate sees it); scale: AGC factor level^-strength of the column
+__device__ __forceinline__ uint8_t colour_index(float E, float scale, const PostArgs& a) {
+    if (!(E > 0.f)) return 0;
+    if (10.0f * log10f(E) < a.gate_db) return 0;
+    const float db = 10.0f * log10f(E * scale);
+    const float v = rintf((db - a.db_floor) * a.inv_range);
+    return (uint8_t)fminf(fmaxf(v, 0.f), 255.f);
+}
 __device__ __forceinline__ uint8_t colour_index(float E, const PostArgs& a) {
     if (!(E > 0.f)) return 0;
     const float db = 10.0f * log10f(E);
     if (db < a.gate_db) return 0;
     const float v = rintf((db - a.db_floor) * a.inv_range);
     return (uint8_t)fminf(fmaxf(v, 0.f), 255.f);
+}
+
+// Column peak for the AGC: E >= 0, so float order = integer order of the bit patterns.
+__device__ __forceinline__ void peak_max(float* colpeak, long long i, float E) {
+    atomicMax(reinterpret_cast<int*>(colpeak) + i, __float_as_int(E));
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int d = 16; d; d >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, d));
+    return v;
 }
 
 // Load a cell for the emit pass and leave it zero: the accumulator is clean again when the
@@ -113,11 +131,15 @@ post_ema_carry_kernel(const PostArgs a, const float* __restrict__ local_end,
 }
 
 // Pass C (the only pass when smoothing == 0): grid fp32 and colour index.
+// measure = 1 (AGC first pass): nothing is written or cleared, the per-column maximum of the
+// shaped, smoothed energy goes to a.colscale.
 __global__ void __launch_bounds__(128, 8)
-post_emit_kernel(const PostArgs a, const float* __restrict__ carry_in, int n_chunks, int chunk_cols) {
-    const int k = blockIdx.y * blockDim.x + threadIdx.x;
+post_emit_kernel(const PostArgs a, const float* __restrict__ carry_in, int n_chunks, int chunk_cols,
+                 int measure) {
+    const int k = min(blockIdx.y * blockDim.x + threadIdx.x, a.B - 1);   // tail lanes shadow the last row (warp_max)
+    const bool tail = blockIdx.y * blockDim.x + threadIdx.x >= a.B;
     const int chunk = blockIdx.x, ch = blockIdx.z;
-    if (k >= a.B) return;
+    if (tail && !measure) return;
     const long long c0 = a.col_begin + (long long)chunk * chunk_cols;
     const long long c1 = min(c0 + (long long)chunk_cols, a.col_end);
     const float w = a.weight[k], s = a.smoothing, oms = 1.0f - a.smoothing;
@@ -133,18 +155,25 @@ post_emit_kernel(const PostArgs a, const float* __restrict__ carry_in, int n_chu
         float G[kTile];
         // clean 64-bin blocks (no deposit since the last post-pass) are neither read nor cleared
 #pragma unroll
-        for (int i = 0; i < kTile; ++i)
-            G[i] = f[i] ? acc_take(a.acc, a.acc_is_u64, o0 + (long long)i * a.B) : 0.f;
+        for (int i = 0; i < kTile; ++i) {
+            const long long o = o0 + (long long)i * a.B;
+            G[i] = !f[i] ? 0.f : measure ? acc_load(a.acc, a.acc_is_u64, o) : acc_take(a.acc, a.acc_is_u64, o);
+        }
 #pragma unroll
         for (int i = 0; i < kTile; ++i) {
             if (i < nt) {
                 const long long o = o0 + (long long)i * a.B;
-                if (a.grid) a.grid[o] = G[i];
-                if (a.index) {
-                    float E = G[i] * w;
-                    if (s > 0.f) { y = s * y + oms * E; E = y; }
-                    a.index[o] = colour_index(E, a);
+                float E = G[i] * w;
+                if (s > 0.f) { y = s * y + oms * E; E = y; }
+                if (measure) {
+                    const float m = warp_max(E);           // 32 rows of this column
+                    if ((threadIdx.x & 31) == 0 && m > 0.f) peak_max(a.colscale, (long long)ch * a.F + cb + i, m);
+                    continue;
                 }
+                if (a.grid) a.grid[o] = G[i];
+                if (a.index)
+                    a.index[o] = a.colscale ? colour_index(E, a.colscale[(long long)ch * a.F + cb + i], a)
+                                            : colour_index(E, a);
             }
         }
     }
@@ -155,8 +184,9 @@ post_emit_kernel(const PostArgs a, const float* __restrict__ carry_in, int n_chu
 // One warp reads 32 consecutive column flags of a (channel, bin block) row; each flagged
 // block is then shaped by the whole warp (2 bins per lane, coalesced), its accumulator cells
 // and its flag are cleared.  grid: (ceil(ncols/256), channels*NB), 256 threads.
+// measure = 1 (AGC first pass): only the per-column peak of the shaped energy is produced.
 __global__ void __launch_bounds__(256)
-post_sparse_kernel(const PostArgs a) {
+post_sparse_kernel(const PostArgs a, int measure) {
     const int lane = threadIdx.x & 31;
     const int r = blockIdx.y;                               // ch * NB + blk
     const int ch = r / a.NB, blk = r - ch * a.NB;
@@ -183,19 +213,29 @@ post_sparse_kernel(const PostArgs a) {
             G0[b] = (on && k0 < a.B) ? acc_load(a.acc, a.acc_is_u64, row + k0) : 0.f;
             G1[b] = (on && k1 < a.B) ? acc_load(a.acc, a.acc_is_u64, row + k1) : 0.f;
         }
+        if (measure) {
+#pragma unroll
+            for (int b = 0; b < kBatch; ++b) {
+                if (js[b] < 0) continue;
+                const float m = warp_max(fmaxf(G0[b] * w0, G1[b] * w1));
+                if (lane == 0 && m > 0.f) peak_max(a.colscale, (long long)ch * a.F + cw + js[b], m);
+            }
+            continue;
+        }
 #pragma unroll
         for (int b = 0; b < kBatch; ++b) {
             if (js[b] < 0) continue;
             const long long row = ((long long)ch * a.F + cw + js[b]) * a.B;
+            const float sc = a.colscale ? a.colscale[(long long)ch * a.F + cw + js[b]] : 1.0f;
             if (k0 < a.B) {
                 acc_zero(a.acc, a.acc_is_u64, row + k0);
                 if (a.grid) a.grid[row + k0] = G0[b];
-                if (a.index) a.index[row + k0] = colour_index(G0[b] * w0, a);
+                if (a.index) a.index[row + k0] = a.colscale ? colour_index(G0[b] * w0, sc, a) : colour_index(G0[b] * w0, a);
             }
             if (k1 < a.B) {
                 acc_zero(a.acc, a.acc_is_u64, row + k1);
                 if (a.grid) a.grid[row + k1] = G1[b];
-                if (a.index) a.index[row + k1] = colour_index(G1[b] * w1, a);
+                if (a.index) a.index[row + k1] = a.colscale ? colour_index(G1[b] * w1, sc, a) : colour_index(G1[b] * w1, a);
             }
             if (lane == 0) fl[cw + js[b]] = 0;
         }
@@ -213,6 +253,40 @@ __global__ void pcm_i16_to_planar_kernel(const int16_t* __restrict__ in, float* 
         const long long smp = e / channels;
         const int ch = (int)(e - smp * channels);
         out[(long long)ch * S + smp] = (float)in[e] * (1.0f / 32768.0f);
+    }
+}
+
+// AGC level scan over columns [c0, c1) of one channel per block: colscale holds the column
+// peaks on entry and level^-strength on exit.  level[m] = max(peak[m], lambda * level[m-1]);
+// `level_carry[ch]` enters c0 and leaves with the level after c1 - 1.  The operator is
+// associative (max-plus with decay), so each thread scans a chunk and thread 0 chains them.
+__global__ void __launch_bounds__(1024)
+agc_scan_kernel(float* __restrict__ colscale, float* __restrict__ level_carry, long long F,
+                long long c0, long long c1, float lambda, float strength) {
+    __shared__ float s_end[1024];
+    __shared__ float s_in[1024];
+    const int ch = blockIdx.x, t = threadIdx.x;
+    float* cs = colscale + (long long)ch * F;
+    const long long n = c1 - c0, per = (n + 1023) / 1024;
+    const long long a0 = c0 + (long long)t * per, a1 = min(a0 + per, c1);
+    float lv = 0.f;
+    for (long long m = a0; m < a1; ++m) lv = fmaxf(cs[m], lambda * lv);
+    s_end[t] = lv;
+    __syncthreads();
+    if (t == 0) {
+        float c = level_carry[ch];
+        for (int j = 0; j < 1024; ++j) {
+            s_in[j] = c;
+            const long long b0 = c0 + (long long)j * per, len = max(0LL, min(b0 + per, c1) - b0);
+            c = fmaxf(s_end[j], c * powf(lambda, (float)len));
+        }
+        level_carry[ch] = c;
+    }
+    __syncthreads();
+    lv = s_in[t];
+    for (long long m = a0; m < a1; ++m) {
+        lv = fmaxf(cs[m], lambda * lv);
+        cs[m] = lv > 0.f ? powf(lv, -strength) : 1.0f;
     }
 }
 

@@ -16,8 +16,10 @@ struct StreamArgs {
     float*       carry;      // [channels][B] EMA state
     const float* weight;     // [B]
     uint8_t*     out;        // [channels][B] colour index of the final column
+    float*       etmp;       // [channels][B] shaped energy of the final column
+    float*       agc;        // [2][channels]: column peak, running level
     int hop, channels, M, Lr, R, ring_cols, B, acc_is_u64;
-    float smoothing, db_floor, inv_range, gate_db;
+    float smoothing, db_floor, inv_range, gate_db, agc_strength, agc_lambda;
 };
 
 // De-interleaves the hop and writes it twice (pos and pos + Lr) so that any n_fft-long
@@ -35,15 +37,13 @@ __global__ void stream_ingest_kernel(const StreamArgs s) {
     }
 }
 
-// Column cf = f - R can no longer receive energy once frame f is in: shape it, emit the
-// colour index, and clear its slot for column cf + ring_cols.
-__global__ void stream_post_kernel(const StreamArgs s) {
+// Column cf = f - R can no longer receive energy once frame f is in: shape it (weights, EMA),
+// keep its peak for the AGC, and clear its slot for column cf + ring_cols.
+__global__ void stream_shape_kernel(const StreamArgs s) {
     const long long f = s.sstate[0] + 1 - s.M;
     const long long cf = f - s.R;
     if (cf < 0) return;
     const int slot = (int)(cf % s.ring_cols);
-    PostArgs pa{};
-    pa.db_floor = s.db_floor; pa.inv_range = s.inv_range; pa.gate_db = s.gate_db;
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < s.B * s.channels;
          e += gridDim.x * blockDim.x) {
         const int ch = e / s.B, k = e - ch * s.B;
@@ -53,12 +53,37 @@ __global__ void stream_post_kernel(const StreamArgs s) {
             E = s.smoothing * s.carry[e] + (1.0f - s.smoothing) * E;
             s.carry[e] = E;
         }
-        s.out[e] = colour_index(E, pa);
-        if (s.acc_is_u64) reinterpret_cast<unsigned long long*>(s.acc)[o] = 0ull;
-        else reinterpret_cast<float*>(s.acc)[o] = 0.f;
+        s.etmp[e] = E;
+        if (s.agc_strength > 0.f && E > 0.f) peak_max(s.agc, ch, E);
+        acc_zero(s.acc, s.acc_is_u64, o);
     }
 }
 
-__global__ void stream_advance_kernel(long long* sstate) { sstate[0] += 1; }
+// Colour index of the final column, drawn at E / level^strength when the AGC is on.
+__global__ void stream_emit_kernel(const StreamArgs s) {
+    if (s.sstate[0] + 1 - s.M - s.R < 0) return;
+    PostArgs pa{};
+    pa.db_floor = s.db_floor; pa.inv_range = s.inv_range; pa.gate_db = s.gate_db;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < s.B * s.channels;
+         e += gridDim.x * blockDim.x) {
+        const int ch = e / s.B;
+        if (s.agc_strength > 0.f) {
+            const float lv = fmaxf(s.agc[ch], s.agc_lambda * s.agc[s.channels + ch]);
+            s.out[e] = colour_index(s.etmp[e], lv > 0.f ? powf(lv, -s.agc_strength) : 1.0f, pa);
+        } else {
+            s.out[e] = colour_index(s.etmp[e], pa);
+        }
+    }
+}
+
+// End of a push: AGC level recurrence, then the counter.
+__global__ void stream_advance_kernel(const StreamArgs s) {
+    if (s.sstate[0] + 1 - s.M - s.R >= 0)
+        for (int ch = 0; ch < s.channels; ++ch) {
+            s.agc[s.channels + ch] = fmaxf(s.agc[ch], s.agc_lambda * s.agc[s.channels + ch]);
+            s.agc[ch] = 0.f;
+        }
+    s.sstate[0] += 1;
+}
 
 }  // namespace ems

@@ -34,7 +34,7 @@ class Params(C.Structure):
         ("channels", C.c_int32), ("db_range", C.c_float), ("gain", C.c_float),
         ("low_end_boost", C.c_float), ("smoothing", C.c_float),
         ("noise_gate_db", C.c_float), ("flags", C.c_uint32),
-        ("display_rows", C.c_int32), ("freq_scale", C.c_float),
+        ("display_rows", C.c_int32), ("freq_scale", C.c_float), ("agc_strength", C.c_float),
     ]
 
 

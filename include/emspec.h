@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define EMS_ABI_VERSION 2
+#define EMS_ABI_VERSION 3
 
 typedef enum ems_status {
     EMS_OK = 0,
@@ -70,6 +70,10 @@ typedef struct ems_params {
     float    freq_scale;    /* "Frequency Scale" README.md:48, used when display_rows > 0:
                                row = (R-1) * log1p(a x) / log1p(a), x = f / Nyquist,
                                a = 10^(2*freq_scale) - 1; 0 = linear axis             (1.0)  */
+    float    agc_strength;  /* "AGC Strength" / "Auto Gain" README.md:14, settings.png; 0 = off.
+                               level[m] = max(peak[m], lambda*level[m-1]), peak = loudest shaped
+                               cell of column m, lambda = exp(-hop/(sample_rate * 1 s)); cells are
+                               drawn at E / level^strength (the gate still sees E)      (0.0)  */
 } ems_params;
 
 typedef struct ems_handle ems_handle;
@@ -94,7 +98,7 @@ ems_status ems_create(const ems_params* params, ems_handle** out);
 ems_status ems_destroy(ems_handle* h);
 
 /* Live display controls (README.md:41 "changes are applied in real-time"): updates
- * db_range, gain, low_end_boost, smoothing, noise_gate_db and flags; n_fft / hop /
+ * db_range, gain, low_end_boost, smoothing, noise_gate_db, agc_strength and flags; n_fft / hop /
  * channels changes require a new handle (EMS_ERR_INVALID_ARG). */
 ems_status ems_update_display(ems_handle* h, const ems_params* params);
 

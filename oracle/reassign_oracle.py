@@ -41,6 +41,7 @@ import math
 import numpy as np
 import scipy.fft
 
+AGC_RELEASE_SECONDS = 1.0   # stand-in release time of the automatic gain control
 LOW_END_CORNER_HZ = 200.0  # stand-in shape constant of the low-end boost weight
 TOP_DB = 0.0               # display ceiling; floor = TOP_DB - db_range
 
@@ -64,6 +65,7 @@ class Params:
     flags: int = FLAG_REASSIGN | FLAG_DETERMINISTIC
     display_rows: int = 0        # 0: one row per bin; > 0: rows of the warped frequency axis
     freq_scale: float = 1.0      # README.md:48 "Frequency Scale" (used when display_rows > 0)
+    agc_strength: float = 0.0    # README.md:14 "AGC" / settings.png "AGC Strength"; 0 = off
 
     @property
     def n_bins(self) -> int:
@@ -218,15 +220,32 @@ def shaped_energy(grid: np.ndarray, prm: Params) -> np.ndarray:
     return E
 
 
+def agc_scale(E: np.ndarray, prm: Params) -> np.ndarray:
+    """Automatic gain (README.md:14; SURVEY.md §8f-2, stand-in semantics): per column m
+    level[m] = max(peak[m], lambda level[m-1]), peak[m] = max_r E[m, r], level[-1] = 0,
+    lambda = exp(-hop / (sample_rate * 1 s)); cells are drawn at E / level^strength."""
+    lam = math.exp(-prm.hop / (prm.sample_rate * AGC_RELEASE_SECONDS))
+    peak = E.max(axis=1) if E.shape[1] else np.zeros(E.shape[0])
+    scale = np.ones(E.shape[0])
+    lv = 0.0
+    for m in range(E.shape[0]):
+        lv = max(peak[m], lam * lv)
+        if lv > 0.0:
+            scale[m] = lv ** (-prm.agc_strength)
+    return scale
+
+
 def postpass(grid: np.ndarray, prm: Params) -> np.ndarray:
-    """a5: shaped energy -> dB -> gate -> u8 colour index [F][B]."""
+    """a5: shaped energy -> (AGC) -> dB -> gate -> u8 colour index [F][R]."""
     E = shaped_energy(grid, prm)
+    Ed = E * agc_scale(E, prm)[:, None] if prm.agc_strength > 0.0 else E
     with np.errstate(divide="ignore"):
-        db = 10.0 * np.log10(E)
+        db_gate = 10.0 * np.log10(E)
+        db = 10.0 * np.log10(Ed)
     floor = TOP_DB - prm.db_range
     v = np.rint(255.0 * (db - floor) / prm.db_range)
     v = np.clip(v, 0.0, 255.0)
-    v = np.where((E > 0.0) & (db >= prm.noise_gate_db), v, 0.0)
+    v = np.where((E > 0.0) & (db_gate >= prm.noise_gate_db), v, 0.0)
     return v.astype(np.uint8)
 
 

@@ -28,7 +28,7 @@ def test_header_symbols_all_exported(lib_built):
 def test_abi_version_and_status_strings(lib_built):
     import emspec
     lib = emspec.load()
-    assert lib.ems_abi_version() == 2
+    assert lib.ems_abi_version() == 3
     assert lib.ems_status_str(0) == b"ok"
     for s in range(1, 6):
         assert len(lib.ems_status_str(s)) > 0
@@ -51,7 +51,7 @@ def test_invalid_arguments_rejected_before_any_cuda_call(lib_built):
     assert lib.ems_create(None, ctypes.byref(h)) == emspec.ERR_INVALID_ARG
     for bad in (dict(n_fft=1000), dict(n_fft=128), dict(n_fft=65536), dict(hop=0),
                 dict(hop=8192), dict(channels=0), dict(smoothing=1.0), dict(db_range=0.0),
-                dict(display_rows=1), dict(display_rows=-3), dict(freq_scale=-1.0)):
+                dict(display_rows=1), dict(display_rows=-3), dict(freq_scale=-1.0), dict(agc_strength=1.5)):
         p = emspec.default_params()
         for k, v in bad.items():
             setattr(p, k, v)

@@ -39,7 +39,7 @@ def run_grid(m, x, prm, want_grid=True):
                    db_range=prm.db_range, gain=prm.gain, low_end_boost=prm.low_end_boost,
                    smoothing=prm.smoothing, sample_rate=prm.sample_rate,
                    display_rows=prm.display_rows, freq_scale=prm.freq_scale,
-                   flags=prm.flags | m.FLAG_SYNC)
+                   agc_strength=prm.agc_strength, flags=prm.flags | m.FLAG_SYNC)
     g, i = eng.process_grid(torch.from_numpy(x).cuda(), want_grid=want_grid)
     eng.close()
     return (g[0].cpu().numpy() if g is not None else None), i[0].cpu().numpy()
@@ -174,6 +174,38 @@ def test_frequency_scale_display_rows(emspec, n_fft, hop, rows, scale):
             assert (col.numpy()[0] == idx[ci]).all()
             n_ok += 1
     assert n_ok > 10
+    eng.close()
+
+
+@pytest.mark.parametrize("smoothing,strength,rows", [(0.0, 1.0, 0), (0.6, 0.5, 0), (0.0, 0.7, 300)])
+def test_auto_gain_control(emspec, smoothing, strength, rows):
+    """AGC (README.md:14) — column peak, max-with-release level recurrence,
+    cells drawn at E / level^strength; offline (sparse and EMA post-pass), host-chunked and
+    streaming paths agree with the oracle / with each other."""
+    t = np.arange(2 * SR) / SR
+    env = 0.02 + 0.9 * (np.sin(2 * np.pi * 0.7 * t) > 0)            # loud / quiet alternation
+    x = (env * (0.5 * np.sin(2 * np.pi * 1234.5 * t) + 0.2 * np.sin(2 * np.pi * 5000.25 * t))).astype(np.float32)
+    x += orc.synth_signal(2 * SR, SR, seed=17) * 0.05
+    prm = orc.Params(n_fft=2048, hop=128, smoothing=smoothing, agc_strength=strength,
+                     display_rows=rows, gain=1.0, db_range=50.0)
+    g, idx = run_grid(emspec, x, prm)
+    check_index(idx, g.astype(np.float64), prm)
+    off = orc.postpass(g.astype(np.float64), orc.Params(**{**prm.__dict__, "agc_strength": 0.0}))
+    assert (idx.astype(int) != off.astype(int)).mean() > 1e-3          # the AGC really changes the picture
+    eng = emspec.Engine(n_fft=2048, hop=128, smoothing=smoothing, agc_strength=strength, display_rows=rows,
+                        gain=1.0, db_range=50.0, flags=prm.flags | emspec.FLAG_SYNC)
+    _, i_host = eng.process_host(torch.from_numpy(x).pin_memory())
+    assert (np.abs(i_host[0].numpy().astype(int) - idx.astype(int)) <= 1).all()
+    R = idx.shape[1]
+    col = torch.empty((1, R), dtype=torch.uint8).pin_memory()
+    worst = 0
+    n = 0
+    for i in range(len(x) // 128):
+        ready, ci = eng.stream_push(torch.from_numpy(x[i * 128:(i + 1) * 128]).contiguous(), col)
+        if ready and ci < idx.shape[0]:
+            worst = max(worst, np.abs(col.numpy()[0].astype(int) - idx[ci].astype(int)).max())
+            n += 1
+    assert n > 100 and worst <= 1, (n, worst)
     eng.close()
 
 

@@ -156,3 +156,22 @@ def test_frequency_scale_rows():
     assert g.shape == (e.shape[0], 546) and abs(g.sum() - e.sum()) < 1e-9 * e.sum()
     w = orc.low_end_weight(prm)
     assert w.shape == (546,) and abs(w[0] - prm.low_end_boost) < 1e-12
+
+
+def test_agc_level_recurrence():
+    """AGC: peak hold with exponential release; strength 1 pins the loudest
+    recent cell at 0 dB; strength 0 is the identity."""
+    prm = orc.Params(n_fft=512, hop=128, gain=1.0, low_end_boost=1.0, agc_strength=1.0, db_range=60.0,
+                     noise_gate_db=-90.0)
+    grid = np.zeros((6, 257))
+    grid[0, 5] = 1e-3
+    grid[1, 7] = 1e-2
+    grid[2:, 9] = 1e-4
+    sc = orc.agc_scale(grid, prm)
+    lam = np.exp(-128 / 48000.0)
+    assert np.allclose(sc[:3], [1e3, 1e2, 1 / (1e-2 * lam)])
+    assert np.allclose(1 / sc[3:], [1e-2 * lam ** 2, 1e-2 * lam ** 3, 1e-2 * lam ** 4])
+    idx = orc.postpass(grid, prm)
+    assert idx[0, 5] == 255 and idx[1, 7] == 255 and idx[2, 9] < 255
+    off = orc.postpass(grid, orc.Params(**{**prm.__dict__, "agc_strength": 0.0}))
+    assert off[1, 7] == int(np.rint(255 * 40 / 60))
