@@ -473,8 +473,17 @@ static ems_status stream_capture(ems_handle* h) {
     a.acc = st.acc; a.mode = det ? kDepositU64 : kDepositF32;
     a.ring = st.ring_cols; a.stream_M = st.M; a.sstate = st.sstate;
 
+    // Recorded on the handle's own stream (a caller-provided stream may be the legacy default
+    // stream, which cannot be captured); the graph is launched on whatever stream is current.
     cudaGraph_t g = nullptr;
-    EMS_CUDA(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+    cudaStream_t user = h->stream;
+    EMS_CUDA(h, cudaStreamSynchronize(user));
+    h->stream = h->own_stream;
+    cudaError_t be = cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal);
+    if (be != cudaSuccess) {
+        h->stream = user;
+        return fail(h, EMS_ERR_CUDA, "stream capture: %s", cudaGetErrorString(be));
+    }
     cudaMemcpyAsync(st.in_dev, st.in_pin, sizeof(float) * H * C, cudaMemcpyHostToDevice, h->stream);
     stream_ingest_kernel<<<(H * C + 255) / 256, 256, 0, h->stream>>>(sa);
     ems_status ls = launch_stft(h, a);
@@ -483,6 +492,7 @@ static ems_status stream_capture(ems_handle* h) {
     stream_advance_kernel<<<1, 1, 0, h->stream>>>(sa);
     cudaMemcpyAsync(st.out_pin, st.out_dev, (size_t)C * B, cudaMemcpyDeviceToHost, h->stream);
     cudaError_t ce = cudaStreamEndCapture(h->stream, &g);
+    h->stream = user;
     h->launches -= 1;                                  // counted per push below, not at capture
     if (ls != EMS_OK) { if (g) cudaGraphDestroy(g); return ls; }
     if (ce != cudaSuccess) return fail(h, EMS_ERR_CUDA, "stream capture: %s", cudaGetErrorString(ce));
@@ -598,8 +608,13 @@ ems_status ems_update_display(ems_handle* h, const ems_params* p) {
         p->channels != h->prm.channels || p->sample_rate != h->prm.sample_rate ||
         p->display_rows != h->prm.display_rows || p->freq_scale != h->prm.freq_scale)
         return fail(h, EMS_ERR_INVALID_ARG, "n_fft/hop/channels/sample_rate/display_rows/freq_scale need a new handle");
+    const bool acc_type_changed = (p->flags ^ h->prm.flags) & EMS_FLAG_DETERMINISTIC;
     h->prm = *p;
     if (h->st.graph) { cudaGraphExecDestroy(h->st.graph); h->st.graph = nullptr; }   // scalars are baked into the graph
+    if (acc_type_changed && h->st.ready) {   // the rolling accumulator changes element type: start over
+        EMS_CUDA(h, cudaStreamSynchronize(h->stream));
+        stream_free(h);
+    }
     return upload_display(h);
 }
 

@@ -281,6 +281,34 @@ def test_int16_interleaved_ingest(emspec):
         check_grid(g16[c].numpy(), xf[c], prm)
 
 
+def test_streaming_on_callers_stream_and_live_controls(emspec):
+    """Streaming works when the handle runs on torch's (legacy default) stream, and
+    ems_update_display takes effect between pushes, including a change of accumulator type."""
+    hop, n_fft = 256, 2048
+    x = orc.synth_signal(SR // 2, SR, seed=21)
+    eng = emspec.Engine(n_fft=n_fft, hop=hop, flags=emspec.FLAG_REASSIGN | emspec.FLAG_DETERMINISTIC)
+    eng.use_torch_stream()
+    col = torch.empty((1, n_fft // 2 + 1), dtype=torch.uint8).pin_memory()
+    ref = emspec.Engine(n_fft=n_fft, hop=hop, gain=7.0, flags=emspec.FLAG_REASSIGN | emspec.FLAG_DETERMINISTIC | emspec.FLAG_SYNC)
+    _, want = ref.process_grid(torch.from_numpy(x).cuda(), want_grid=False)
+    want = want[0].cpu().numpy()
+    ref.close()
+    eng.update_display(gain=7.0)
+    n = 0
+    for i in range(len(x) // hop):
+        if i == 40:
+            eng.update_display(db_range=58.0)                       # re-captures the graph mid-stream
+        ready, ci = eng.stream_push(torch.from_numpy(x[i * hop:(i + 1) * hop]).contiguous(), col)
+        if ready and ci < want.shape[0]:
+            assert (col.numpy()[0] == want[ci]).all()
+            n += 1
+    assert n > 50
+    eng.update_display(flags=emspec.FLAG_REASSIGN)                   # fp32 accumulator: streaming state restarts
+    ready, ci = eng.stream_push(torch.from_numpy(x[:hop]).contiguous(), col)
+    assert not ready and ci < 0
+    eng.close()
+
+
 def test_colour_map_lut_is_bit_exact(emspec):
     """256-entry RGBA table lookup (README.md:15,45), integer work -> bit-exact,
     any alignment and length (head / 16-byte body / tail paths)."""
