@@ -329,6 +329,35 @@ def test_colour_map_lut_is_bit_exact(emspec):
     eng.close()
 
 
+@pytest.mark.parametrize("hop", [125, 129, 333])
+def test_tuned_kernel_odd_hops(emspec, hop):
+    """n_fft = 4096 tuned kernel with hops that are odd / not multiples of 4 (tile copies are
+    4-byte cp.async, frames start at any sample)."""
+    x = orc.synth_signal(SR // 2, SR, seed=18)
+    prm = orc.Params(n_fft=4096, hop=hop)
+    check_points(run_points(emspec, x, prm), x, prm)
+
+
+def test_host_chunking_with_tuned_kernel(emspec, monkeypatch):
+    """ems_process_host in many small chunks (frame ranges f_begin..f_end of the tuned kernel,
+    per-chunk post-pass, EMA and AGC carries across chunks) equals the one-shot device call."""
+    monkeypatch.setenv("EMS_HOST_CHUNK_FRAMES", "1100")
+    x = orc.synth_signal(12 * SR, SR, seed=19)
+    eng = emspec.Engine(n_fft=4096, hop=128, channels=2, smoothing=0.4, agc_strength=0.8,
+                        flags=emspec.FLAG_REASSIGN | emspec.FLAG_DETERMINISTIC | emspec.FLAG_SYNC)
+    pcm = torch.from_numpy(np.stack([x, x[::-1].copy()]))
+    g_dev, i_dev = eng.process_grid(pcm.cuda())
+    g_host, i_host = eng.process_host(pcm.pin_memory(), want_grid=True)
+    assert torch.equal(g_host, g_dev.cpu())
+    d = (i_host.int() - i_dev.cpu().int()).abs()
+    assert d.max() <= 1 and (d > 0).float().mean() < 1e-4
+    eng.update_display(smoothing=0.0, agc_strength=0.0)
+    g2, i2 = eng.process_host(pcm.pin_memory(), want_grid=True)
+    g3, i3 = eng.process_grid(pcm.cuda())
+    assert torch.equal(g2, g3.cpu()) and torch.equal(i2, i3.cpu())
+    eng.close()
+
+
 def test_golden_fixture(emspec):
     """Committed fixture (tests/golden/make_golden.py): CUDA path vs stored oracle output."""
     z = np.load(os.path.join(GOLD, "reassign_n512_h128.npz"))
