@@ -894,6 +894,84 @@ ems_status ems_stream_push(ems_handle* h, const float* pcm_host, uint8_t* column
     return EMS_OK;
 }
 
+// ---- stream checkpoint: header + [pushes][ring][acc][carry][agc]
+namespace {
+struct StreamBlobHeader {
+    uint32_t magic, abi;
+    int32_t n_fft, hop, channels, rows, det;
+    int64_t pushes;
+    uint64_t ring_bytes, acc_bytes, carry_bytes, agc_bytes;
+};
+constexpr uint32_t kBlobMagic = 0x53534d45u;   // "EMSS"
+
+StreamBlobHeader blob_header(const ems_handle* h) {
+    const auto& st = h->st;
+    StreamBlobHeader b{};
+    b.magic = kBlobMagic; b.abi = EMS_ABI_VERSION;
+    b.n_fft = h->prm.n_fft; b.hop = h->prm.hop; b.channels = h->prm.channels;
+    b.rows = rows_of(h->prm); b.det = (h->prm.flags & EMS_FLAG_DETERMINISTIC) ? 1 : 0;
+    b.pushes = st.pushes;
+    b.ring_bytes = sizeof(float) * (size_t)b.channels * 2 * st.Lr;
+    b.acc_bytes = st.acc_bytes;
+    b.carry_bytes = sizeof(float) * (size_t)b.channels * b.rows;
+    b.agc_bytes = sizeof(float) * 2 * (size_t)b.channels;
+    return b;
+}
+size_t blob_size(const StreamBlobHeader& b) {
+    return sizeof(b) + b.ring_bytes + b.acc_bytes + b.carry_bytes + b.agc_bytes;
+}
+}  // namespace
+
+ems_status ems_stream_state_size(ems_handle* h, size_t* bytes) {
+    if (!h || !bytes) return EMS_ERR_INVALID_ARG;
+    ems_status s;
+    if (!h->st.ready && (s = stream_init(h)) != EMS_OK) return s;
+    *bytes = blob_size(blob_header(h));
+    return EMS_OK;
+}
+
+ems_status ems_stream_save(ems_handle* h, void* blob, size_t bytes) {
+    if (!h || !blob) return EMS_ERR_INVALID_ARG;
+    ems_status s;
+    if (!h->st.ready && (s = stream_init(h)) != EMS_OK) return s;
+    const StreamBlobHeader b = blob_header(h);
+    if (bytes < blob_size(b)) return fail(h, EMS_ERR_INVALID_ARG, "blob too small");
+    auto& st = h->st;
+    EMS_CUDA(h, cudaStreamSynchronize(h->stream));
+    char* p = (char*)blob;
+    memcpy(p, &b, sizeof(b)); p += sizeof(b);
+    EMS_CUDA(h, cudaMemcpy(p, st.ring, b.ring_bytes, cudaMemcpyDeviceToHost)); p += b.ring_bytes;
+    EMS_CUDA(h, cudaMemcpy(p, st.acc, b.acc_bytes, cudaMemcpyDeviceToHost)); p += b.acc_bytes;
+    EMS_CUDA(h, cudaMemcpy(p, st.carry, b.carry_bytes, cudaMemcpyDeviceToHost)); p += b.carry_bytes;
+    EMS_CUDA(h, cudaMemcpy(p, st.agc, b.agc_bytes, cudaMemcpyDeviceToHost));
+    return EMS_OK;
+}
+
+ems_status ems_stream_load(ems_handle* h, const void* blob, size_t bytes) {
+    if (!h || !blob || bytes < sizeof(StreamBlobHeader)) return EMS_ERR_INVALID_ARG;
+    ems_status s;
+    if (!h->st.ready && (s = stream_init(h)) != EMS_OK) return s;
+    StreamBlobHeader b;
+    memcpy(&b, blob, sizeof(b));
+    const StreamBlobHeader mine = blob_header(h);
+    if (b.magic != kBlobMagic || b.abi != mine.abi || b.n_fft != mine.n_fft || b.hop != mine.hop ||
+        b.channels != mine.channels || b.rows != mine.rows || b.det != mine.det ||
+        b.ring_bytes != mine.ring_bytes || b.acc_bytes != mine.acc_bytes || bytes < blob_size(b) ||
+        b.pushes < 0)
+        return fail(h, EMS_ERR_INVALID_ARG, "stream blob does not match this handle");
+    auto& st = h->st;
+    EMS_CUDA(h, cudaStreamSynchronize(h->stream));
+    const char* p = (const char*)blob + sizeof(b);
+    const long long pushes = b.pushes;
+    EMS_CUDA(h, cudaMemcpy(st.sstate, &pushes, sizeof(long long), cudaMemcpyHostToDevice));
+    EMS_CUDA(h, cudaMemcpy(st.ring, p, b.ring_bytes, cudaMemcpyHostToDevice)); p += b.ring_bytes;
+    EMS_CUDA(h, cudaMemcpy(st.acc, p, b.acc_bytes, cudaMemcpyHostToDevice)); p += b.acc_bytes;
+    EMS_CUDA(h, cudaMemcpy(st.carry, p, b.carry_bytes, cudaMemcpyHostToDevice)); p += b.carry_bytes;
+    EMS_CUDA(h, cudaMemcpy(st.agc, p, b.agc_bytes, cudaMemcpyHostToDevice));
+    st.pushes = pushes;
+    return EMS_OK;
+}
+
 ems_status ems_stream_reset(ems_handle* h) {
     if (!h) return EMS_ERR_INVALID_ARG;
     if (!h->st.ready) return EMS_OK;

@@ -63,6 +63,9 @@ _SIG = {
     "ems_launch_count": (C.c_int, [_VP, C.POINTER(C.c_uint64)]),
     "ems_stream_push": (C.c_int, [_VP, _FP, _U8P, C.POINTER(C.c_int), C.POINTER(C.c_int64)]),
     "ems_stream_reset": (C.c_int, [_VP]),
+    "ems_stream_state_size": (C.c_int, [_VP, C.POINTER(C.c_size_t)]),
+    "ems_stream_save": (C.c_int, [_VP, _VP, C.c_size_t]),
+    "ems_stream_load": (C.c_int, [_VP, _VP, C.c_size_t]),
 }
 SYMBOLS = tuple(_SIG)
 
@@ -271,6 +274,17 @@ class Engine:
     # ------------------------------------------------------------------ streaming
     def stream_reset(self):
         self._check(self.lib.ems_stream_reset(self.h))
+
+    def stream_save(self) -> bytes:
+        """Checkpoint of the streaming state (ring, rolling columns, smoothing / AGC state)."""
+        n = C.c_size_t()
+        self._check(self.lib.ems_stream_state_size(self.h, C.byref(n)))
+        buf = C.create_string_buffer(n.value)
+        self._check(self.lib.ems_stream_save(self.h, buf, n.value))
+        return buf.raw
+
+    def stream_load(self, blob: bytes):
+        self._check(self.lib.ems_stream_load(self.h, blob, len(blob)))
 
     def stream_push(self, pcm_host, column_host):
         """pcm_host: CPU fp32 [hop*channels] interleaved; column_host: CPU u8 [channels][n_rows].

@@ -171,6 +171,15 @@ ems_status ems_stream_push(ems_handle* h, const float* pcm_host, uint8_t* column
 /* Clears the ring, the rolling grid and the smoothing state. */
 ems_status ems_stream_reset(ems_handle* h);
 
+/* Checkpoint / resume of a stream: the state is the push counter, the sample
+ * ring, the rolling accumulator columns, the smoothing and AGC state.  A blob saved from one
+ * handle can be loaded into another handle created with the same parameters; the columns
+ * that follow are bit-identical.  ems_stream_state_size is valid after the first push (or
+ * after a load); load returns EMS_ERR_INVALID_ARG when the blob does not match the handle. */
+ems_status ems_stream_state_size(ems_handle* h, size_t* bytes);
+ems_status ems_stream_save(ems_handle* h, void* blob_host, size_t bytes);
+ems_status ems_stream_load(ems_handle* h, const void* blob_host, size_t bytes);
+
 #ifdef __cplusplus
 }
 #endif

@@ -309,6 +309,33 @@ def test_streaming_on_callers_stream_and_live_controls(emspec):
     eng.close()
 
 
+def test_stream_checkpoint_resume(emspec):
+    """SURVEY.md §5 checkpoint/resume: a saved stream continues bit-identically in a new handle."""
+    hop, n_fft = 256, 2048
+    x = orc.synth_signal(SR // 2, SR, seed=22)
+    kw = dict(n_fft=n_fft, hop=hop, smoothing=0.3, agc_strength=0.5)
+    a = emspec.Engine(**kw)
+    col = torch.empty((1, n_fft // 2 + 1), dtype=torch.uint8).pin_memory()
+    hops = [torch.from_numpy(x[i * hop:(i + 1) * hop]).contiguous() for i in range(len(x) // hop)]
+    for hp in hops[:37]:
+        a.stream_push(hp, col)
+    blob = a.stream_save()
+    rest_a = []
+    for hp in hops[37:]:
+        ready, ci = a.stream_push(hp, col)
+        rest_a.append((ready, ci, col.numpy().copy()))
+    b = emspec.Engine(**kw)
+    b.stream_load(blob)
+    for hp, (ready_a, ci_a, col_a) in zip(hops[37:], rest_a):
+        ready, ci = b.stream_push(hp, col)
+        assert (ready, ci) == (ready_a, ci_a) and (not ready or (col.numpy() == col_a).all())
+    c = emspec.Engine(n_fft=n_fft, hop=hop // 2)
+    with pytest.raises(emspec.EmspecError):
+        c.stream_load(blob)                                # different geometry
+    for e in (a, b, c):
+        e.close()
+
+
 def test_colour_map_lut_is_bit_exact(emspec):
     """256-entry RGBA table lookup (README.md:15,45), integer work -> bit-exact,
     any alignment and length (head / 16-byte body / tail paths)."""
