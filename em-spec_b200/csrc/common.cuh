@@ -12,6 +12,12 @@ namespace ems {
 // Range per cell 2^20 (a full-scale sine is 1.0), resolution 5.7e-14 (-132 dB).
 constexpr float  kFixScale    = 17592186044416.0f;        // 2^44
 constexpr double kFixScaleInv = 1.0 / 17592186044416.0;
+// A single point contributes at most 2^12 (36 dB over a full-scale sine): 2^8 such points still
+// fit a cell, so PCM far outside [-1, 1] saturates instead of wrapping the 64-bit sum.
+constexpr float  kFixMaxEnergy = 4096.0f;
+__device__ __forceinline__ unsigned long long fix_energy(float e) {
+    return __float2ull_rn(fminf(e, kFixMaxEnergy) * kFixScale);
+}
 
 enum DepositMode : int {
     kStorePoints = 0,   // write (dt_cols, dk_bins, energy) triples

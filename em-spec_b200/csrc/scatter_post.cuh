@@ -29,7 +29,7 @@ scatter_points_kernel(const float* __restrict__ dt_cols, const float* __restrict
         const long long o = (ch * F + col) * rows + row;
         if (acc_is_u64)
             atomicAdd(reinterpret_cast<unsigned long long*>(acc) + o,
-                      __float2ull_rn(e * kFixScale));
+                      fix_energy(e));
         else
             atomicAdd(reinterpret_cast<float*>(acc) + o, e);
         flags[flag_index((int)ch, F, rows, col, row)] = 1;

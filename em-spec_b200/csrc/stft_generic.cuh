@@ -112,7 +112,7 @@ __device__ __forceinline__ void reassign_emit(const StftArgs& a, int ch,
         const long long o = acc_cell(a, ch, col, row);
         if (a.mode == kDepositU64)
             atomicAdd(reinterpret_cast<unsigned long long*>(a.acc) + o,
-                      __float2ull_rn(e * kFixScale));
+                      fix_energy(e));
         else
             atomicAdd(reinterpret_cast<float*>(a.acc) + o, e);
         if (a.flags) a.flags[flag_index(ch, a.F, a.rows, col, row)] = 1;

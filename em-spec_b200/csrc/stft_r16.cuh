@@ -210,7 +210,7 @@ __device__ __forceinline__ void bin_emit(const StftArgs& a, const FrameCtx& fc, 
         const long long col = fc.f + (long long)rc;
         const long long o = acc_cell(a, fc.ch, col, row);
         if (MODE == kDepositU64)
-            atomicAdd(reinterpret_cast<unsigned long long*>(a.acc) + o, __float2ull_rn(e * kFixScale));
+            atomicAdd(reinterpret_cast<unsigned long long*>(a.acc) + o, fix_energy(e));
         else
             atomicAdd(reinterpret_cast<float*>(a.acc) + o, e);
         if (a.flags) a.flags[flag_index(fc.ch, a.F, a.rows, col, row)] = 1;

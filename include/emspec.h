@@ -47,8 +47,10 @@ typedef enum ems_status {
 /* flags */
 #define EMS_FLAG_REASSIGN      1u /* 1: reassigned ("Enhanced"), 0: plain |X_h|^2 columns ("Natural");
                                      assets/settings.png buttons */
-#define EMS_FLAG_DETERMINISTIC 2u /* scatter accumulates in 64-bit fixed point: order-independent,
-                                     bit-exact across runs; 0: fp32 red.global.add fast mode */
+#define EMS_FLAG_DETERMINISTIC 2u /* scatter accumulates in 64-bit fixed point (2^-44 steps, a point
+                                     saturates at 2^12 = +36 dB re full scale): order-independent,
+                                     bit-exact across runs; 0: fp32 red.global.add fast mode.
+                                     PCM is expected in [-1, 1] (full scale 1.0). */
 #define EMS_FLAG_SYNC          4u /* offline calls synchronise the stream before returning */
 
 /* Parameter surface = the README settings glossary (/root/reference/README.md:41-51);

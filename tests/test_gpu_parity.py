@@ -240,6 +240,21 @@ def test_deterministic_and_fast_mode(emspec):
     assert rel_l2(gf.cpu().numpy(), runs[0][0].cpu().numpy()) < 1e-5
 
 
+def test_fixed_point_accumulator_saturates_instead_of_wrapping(emspec):
+    """PCM far outside [-1, 1]: a point contributes at most 2^12 in deterministic mode, the
+    64-bit sum never wraps (the fp32 fast mode shows what an unbounded sum would be)."""
+    t = np.arange(SR // 2) / SR
+    x = torch.from_numpy((300.0 * np.sin(2 * np.pi * 1000.0 * t)).astype(np.float32)).cuda()
+    det = emspec.Engine(n_fft=2048, hop=64, flags=emspec.FLAG_REASSIGN | emspec.FLAG_DETERMINISTIC | emspec.FLAG_SYNC)
+    fast = emspec.Engine(n_fft=2048, hop=64, flags=emspec.FLAG_REASSIGN | emspec.FLAG_SYNC)
+    gd, _ = det.process_grid(x)
+    gf, _ = fast.process_grid(x)
+    det.close(); fast.close()
+    assert gf.max() > 4096.0 * 4                                   # really beyond the range
+    assert torch.isfinite(gd).all() and (gd <= gf * (1 + 1e-5) + 1e-6).all()
+    assert gd.max() >= 4096.0                                      # saturated, not wrapped to small values
+
+
 def test_stereo_planar(emspec):
     xl = orc.synth_signal(SR // 2, SR, seed=7)
     xr = orc.synth_signal(SR // 2, SR, seed=8)
