@@ -190,7 +190,7 @@ static ems_status launch_big(ems_handle* h, const StftArgs& a) {
 
 // Tuned n_fft = 4096 kernel: persistent, one CTA per SM, 3 workers x 128 threads.
 static ems_status launch_r16(ems_handle* h, const StftArgs& a, int tile_T) {
-    const size_t smem = (size_t)r16::kFixedBytes + 2 * (size_t)r16::kTileFloats * sizeof(float);
+    const size_t smem = (size_t)r16::kFixedBytes + 2 * (size_t)r16::kTileFloats * sizeof(float) + r16::kSyncBytes;
     void (*kern)(const StftArgs, const int) =
         a.mode == kStorePoints ? r16::stft_reassign_r16<kStorePoints>
         : a.mode == kDepositU64 ? r16::stft_reassign_r16<kDepositU64>

@@ -13,7 +13,8 @@
 // Layout of the work (DESIGN.md "K1-K3"):
 //   * persistent CTAs, one per SM, 3 workers x 128 threads; a CTA walks tiles of T
 //     consecutive frames whose samples ((T-1)*hop + 4096 floats) sit once in shared memory,
-//     double-buffered with cp.async so the next tile lands while this one is analysed;
+//     double-buffered with cp.async; buffers are handed over through an mbarrier and a
+//     release counter, never a CTA-wide barrier, so the workers run out of phase;
 //   * a worker analyses one frame at a time, entirely on-chip: Z as 16 x 16 x 16, two radix-16
 //     butterflies per thread per pass in packed fp32x2 arithmetic, in-place
 //     decimation-in-frequency in the worker's private buffer, padding padZ(a) = a + (a >> 8)
@@ -47,7 +48,8 @@ constexpr int kScratch = 20;           // 2 X_th' of the 17 self-paired bins
 constexpr int kTabFloat2 = kZtab + kT2;
 constexpr int kFixedBytes = (kWorkers * (kZBuf + kXBuf + kScratch) + kTabFloat2) * 8;
 constexpr int kMaxSmem = 232448;       // 227 KB
-constexpr int kTileFloats = ((kMaxSmem - kFixedBytes) / 8) & ~3;   // per buffer, two buffers
+constexpr int kSyncBytes = 64;          // 2 mbarriers, 2 release counters, kWorkers refill flags
+constexpr int kTileFloats = ((kMaxSmem - kFixedBytes - kSyncBytes) / 8) & ~3;   // per buffer, two buffers
 
 // frames per tile: both tile buffers must hold (T-1)*hop + N samples
 __host__ __device__ constexpr int tile_frames(int hop) {
@@ -171,6 +173,29 @@ __device__ __forceinline__ float rcp_approx(float x) {
     return r;
 }
 
+// a4 for one kept point.  Deliberately not inlined: the row warp (log1pf), the 64-bit cell and
+// flag indices and the atomics would otherwise sit 17 times in the frame loop and push it out
+// of the instruction cache (measured: no_instruction stalls 1.0 per issue, -8 % throughput).
+struct DepositCtx {      // passed by value (registers): taking the address of StftArgs would
+    void* acc;           // push the whole argument block into local memory
+    unsigned char* flags;
+    long long F;
+    int ring, rows, warp_mode;
+    float warp_a, warp_c, inv_half;
+};
+template <int MODE>
+__device__ __noinline__ void deposit_point(const DepositCtx d, int ch, long long col, int k, float dk,
+                                           float wh, float e) {
+    const int row = out_row(d.warp_mode, d.warp_a, d.warp_c, d.inv_half, k, dk, wh);
+    const long long o = d.ring ? ((long long)ch * d.ring + (col % d.ring)) * d.rows + row
+                               : ((long long)ch * d.F + col) * d.rows + row;
+    if (MODE == kDepositU64)
+        atomicAdd(reinterpret_cast<unsigned long long*>(d.acc) + o, fix_energy(e));
+    else
+        atomicAdd(reinterpret_cast<float*>(d.acc) + o, e);
+    if (d.flags) d.flags[flag_index(ch, d.F, d.rows, col, row)] = 1;
+}
+
 // One bin of the epilogue: Hann / Hann-derivative stencils of the rectangular spectrum, the
 // Auger-Flandrin operators and the emit — same decisions as reassign_emit (stft_generic.cuh).
 //   xk, xm, xp = 2 X[k], 2 X[k-1], 2 X[k+1];  t2 = 2 X_th'[k]
@@ -206,14 +231,8 @@ __device__ __forceinline__ void bin_emit(const StftArgs& a, const FrameCtx& fc, 
     if (MODE == kStorePoints) {
         if (owner) { fc.pd[k] = dtc; fc.pk[k] = dk; fc.pe[k] = ok ? e : 0.f; }
     } else if (ok && owner) {
-        const int row = out_row(a.warp_mode, a.warp_a, a.warp_c, a.inv_half, k, dk, wh);
-        const long long col = fc.f + (long long)rc;
-        const long long o = acc_cell(a, fc.ch, col, row);
-        if (MODE == kDepositU64)
-            atomicAdd(reinterpret_cast<unsigned long long*>(a.acc) + o, fix_energy(e));
-        else
-            atomicAdd(reinterpret_cast<float*>(a.acc) + o, e);
-        if (a.flags) a.flags[flag_index(fc.ch, a.F, a.rows, col, row)] = 1;
+        const DepositCtx d{a.acc, a.flags, a.F, a.ring, a.rows, a.warp_mode, a.warp_a, a.warp_c, a.inv_half};
+        deposit_point<MODE>(d, fc.ch, fc.f + (long long)rc, k, dk, wh, e);
     }
 }
 
@@ -271,36 +290,90 @@ stft_reassign_r16(const StftArgs a_in, const int tile_T) {
     const long long n_tiles = tiles_per_ch * a.channels;
     constexpr int B = N / 2 + 1;
 
-    // Tiles are double-buffered: while the workers analyse tile i, cp.async brings the
-    // samples of this CTA's next tile into the other buffer (4-byte copies: no alignment
-    // demands on pcm, hop or the channel stride).
-    auto prefetch = [&](long long tl, float* dst) {
-        const int ch = (int)(tl / tiles_per_ch);
-        const long long f0 = a.f_begin + (tl - (long long)ch * tiles_per_ch) * tile_T;
-        const int nf = (int)min((long long)tile_T, a.f_end - f0);
+    // Tiles are double-buffered and handed over without any CTA-wide barrier, so the three
+    // workers drift apart and their FP-heavy and shared-memory-heavy phases interleave (in
+    // lockstep they collide: measured +13 %).  Protocol per buffer b:
+    //   * a worker that has read its last sample of the tile in b bumps done[b]; the third one
+    //     to do so refills b with the tile after next (cp.async from its 128 threads, 4-byte
+    //     copies: no alignment demands) and the copies arrive on the mbarrier full[b];
+    //   * a worker waits on full[b] before it reads a refilled buffer.
+    unsigned long long* full = reinterpret_cast<unsigned long long*>(tile0 + 2 * kTileFloats);   // [2]
+    unsigned* done = reinterpret_cast<unsigned*>(full + 2);                                     // [2]
+    int* refill = reinterpret_cast<int*>(done + 2);                                             // [kWorkers]
+    const unsigned full_sm = (unsigned)__cvta_generic_to_shared(full);
+    auto tile_geom = [&](long long tl, int& ch, long long& f0, int& nf) {
+        ch = (int)(tl / tiles_per_ch);
+        f0 = a.f_begin + (tl - (long long)ch * tiles_per_ch) * tile_T;
+        nf = (int)min((long long)tile_T, a.f_end - f0);
+    };
+    auto copy_tile = [&](long long tl, float* dst, int t0, int nth) {
+        int ch, nf; long long f0;
+        tile_geom(tl, ch, f0, nf);
         const int n_samp = (nf - 1) * a.hop + N;
         const float* src = a.pcm + (long long)ch * a.S + f0 * a.hop + a.samp_off;
         const unsigned d0 = (unsigned)__cvta_generic_to_shared(dst);
-        for (int s = tid; s < n_samp; s += kThreads)
+        for (int s = t0; s < n_samp; s += nth)
             asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d0 + 4u * s), "l"(src + s) : "memory");
-        asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    int buf = 0;
-    if ((long long)blockIdx.x < n_tiles) prefetch(blockIdx.x, tile0);
+    // prologue: the first two tiles by all threads
+    const long long tile_step = gridDim.x;
+    if ((long long)blockIdx.x < n_tiles) copy_tile(blockIdx.x, tile0, tid, kThreads);
+    if ((long long)blockIdx.x + tile_step < n_tiles) copy_tile(blockIdx.x + tile_step, tile0 + kTileFloats, tid, kThreads);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(full_sm), "r"(kWorkerThreads));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(full_sm + 8), "r"(kWorkerThreads));
+        done[0] = 0; done[1] = 0;
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    // (no initial stagger: measured, it makes no difference)
 
-    for (long long tl = blockIdx.x; tl < n_tiles; tl += gridDim.x, buf ^= 1) {
-        const int ch = (int)(tl / tiles_per_ch);
-        const long long f0 = a.f_begin + (tl - (long long)ch * tiles_per_ch) * tile_T;
-        const int nf = (int)min((long long)tile_T, a.f_end - f0);
+    // this worker is done reading buffer b (tile number ti of this CTA): called by its thread
+    // p == 0 after a worker barrier; tells the worker whether it has to refill the buffer
+    auto release_tile = [&](int b) {
+        __threadfence_block();
+        const unsigned old = atomicAdd(&done[b], 1u);
+        const bool last = old == kWorkers - 1;
+        if (last) done[b] = 0;
+        __threadfence_block();
+        refill[w] = last ? 1 : 0;
+    };
+    // all 128 threads of the refilling worker
+    auto refill_tile = [&](int b, long long ti_next) {
+        const long long tl2 = blockIdx.x + ti_next * tile_step;
+        if (tl2 >= n_tiles) return;
+        copy_tile(tl2, tile0 + b * kTileFloats, p, kWorkerThreads);
+        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(full_sm + 8u * b) : "memory");
+    };
+
+    for (long long ti = 0;; ++ti) {
+        const long long tl = blockIdx.x + ti * tile_step;
+        if (tl >= n_tiles) break;
+        const int buf = (int)(ti & 1);
+        if (ti >= 2) {                      // refilled buffer: wait until the copies have landed
+            const unsigned parity = (unsigned)(((ti >> 1) - 1) & 1);
+            unsigned ok = 0;
+            while (!ok)
+                asm volatile("{ .reg .pred q; mbarrier.try_wait.parity.shared::cta.b64 q, [%1], %2; selp.u32 %0, 1, 0, q; }"
+                             : "=r"(ok) : "r"(full_sm + 8u * buf), "r"(parity) : "memory");
+        }
+        int ch, nf; long long f0;
+        tile_geom(tl, ch, f0, nf);
         const float* tile = tile0 + buf * kTileFloats;
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-        __syncthreads();            // this tile has landed; the other buffer is fully consumed
-        if (tl + gridDim.x < n_tiles) prefetch(tl + gridDim.x, tile0 + (buf ^ 1) * kTileFloats);
         const long long chan_off = a.ring ? 0 : (long long)ch * a.F;
+        if (w >= nf) {                      // no frame for this worker in a short tile: just release it
+            if (p == 0) release_tile(buf);
+            worker_bar(w);
+            if (refill[w]) refill_tile(buf, ti + 2);
+            worker_bar(w);
+            continue;
+        }
 
         for (int fi = w; fi < nf; fi += kWorkers) {
             const float* xs = tile + fi * a.hop;
             const long long f = f0 + fi;
+            const bool last_frame = fi + kWorkers >= nf;
 
             // ================= pass 1: butterflies b = p, p + 128 on z[n] = x[n] (1 + j th'[n])
             static_for<2>([&](auto uc) {
@@ -318,6 +391,7 @@ stft_reassign_r16(const StftArgs a_in, const int tile_T) {
                 for (int i = 1; i < 16; ++i) Zb[b + 257 * i] = cmul2(v[o16(i)], Ztab[(i - 1) * 256 + b]);
             });
             worker_bar(w);
+            if (last_frame && p == 0) release_tile(buf);   // every sample of the tile has been read
 
             // ================= pass 2: sub-FFTs of length 256, butterflies (i1, q2), (i1, q2 + 8),
             // software-pipelined by hand: the second butterfly's loads fly while the first computes
@@ -339,6 +413,7 @@ stft_reassign_r16(const StftArgs a_in, const int tile_T) {
                 for (int i = 1; i < 16; ++i) bz1[16 * i] = cmul2(v1[o16(i)], T2[(i - 1) * 16 + q2 + 8]);
             }
             worker_bar(w);
+            if (last_frame && refill[w]) refill_tile(buf, ti + 2);
 
             // ================= pass 3: residues tA, tB; untangle; X to shared memory
             float2 za[16], zb[16];
