@@ -89,7 +89,7 @@ __device__ __forceinline__ long long acc_cell(const StftArgs& a, int ch, long lo
 __device__ __forceinline__ int out_row(int warp_mode, float warp_a, float warp_c, float inv_half,
                                        int k, float dk, float wh) {
     if (warp_mode == 0) return k + (int)rintf(dk);
-    const float x = wh * inv_half;
+    const float x = fminf(fmaxf(wh * inv_half, 0.f), 1.f);
     return (int)rintf((warp_mode == 2 ? log1pf(warp_a * x) : x) * warp_c);
 }
 

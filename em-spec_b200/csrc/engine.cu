@@ -99,7 +99,7 @@ static ems_status ensure(ems_handle* h, DevBuf& b, size_t bytes) {
 static bool valid_params(const ems_params& p) {
     if (p.n_fft < 256 || p.n_fft > 32768 || (p.n_fft & (p.n_fft - 1))) return false;
     if (p.hop < 1 || p.hop > p.n_fft) return false;
-    if (!(p.sample_rate > 0.f) || p.channels < 1 || p.channels > 64) return false;
+    if (!(p.sample_rate > 0.f) || p.channels < 1 || p.channels > 65535) return false;
     if (!(p.db_range > 0.f) || !(p.gain >= 0.f) || !(p.low_end_boost > 0.f)) return false;
     if (!(p.smoothing >= 0.f) || !(p.smoothing < 1.f)) return false;
     if (!std::isfinite(p.noise_gate_db)) return false;

@@ -98,7 +98,7 @@ __device__ __forceinline__ void reassign_emit(const StftArgs& a, int ch,
         wh = (float)k + dk;
         const float rc = rintf(dtc);
         col = f + (long long)rc;
-        ok = (fabsf(dts) <= (float)(N / 2)) && (wh >= 0.f) && (wh <= (float)(N / 2)) &&
+        ok = (fabsf(dts) <= (float)(N / 2)) && (wh >= -0.5f) && (wh <= (float)(N / 2) + 0.5f) &&
              (col >= 0) && (col < a.F);
         if (!ok) { dtc = 0.f; dk = 0.f; }
     }

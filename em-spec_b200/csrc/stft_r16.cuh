@@ -223,7 +223,7 @@ __device__ __forceinline__ void bin_emit(const StftArgs& a, const FrameCtx& fc, 
         dtc = dts * a.inv_hop;
         rc = rintf(dtc);
         wh = kf + dk;
-        ok = live && (fabsf(dts) <= (float)(N / 2)) && (wh >= 0.f) && (wh <= (float)(N / 2)) &&
+        ok = live && (fabsf(dts) <= (float)(N / 2)) && (wh >= -0.5f) && (wh <= (float)(N / 2) + 0.5f) &&
              (rc >= fc.lo) && (rc <= fc.hi);
         dtc = ok ? dtc : 0.f;
         dk = ok ? dk : 0.f;

@@ -59,7 +59,8 @@ typedef struct ems_params {
     int32_t  n_fft;         /* "FFT Size" README.md:43; power of two, 256..32768      (4096) */
     int32_t  hop;           /* "Scroll Speed" README.md:44 maps to hop, 1..n_fft      (128)  */
     float    sample_rate;   /* Hz                                                     (48000)*/
-    int32_t  channels;      /* planar channels per call, >= 1                         (1)    */
+    int32_t  channels;      /* planar channels (or equal-length clips of a batch) per call,
+                               1..65535                                              (1)    */
     float    db_range;      /* "dB Range" README.md:46; floor = 0 dB - range          (58)   */
     float    gain;          /* "Gain" README.md:47; linear amplitude                  (3.5)  */
     float    low_end_boost; /* "Low-End Boost" README.md:49; weight at DC             (3.9)  */

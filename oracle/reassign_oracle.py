@@ -28,7 +28,9 @@ Conventions (SURVEY.md §7 "Sign conventions", §8c):
   points are reported as displacements (dt/H columns, dk bins) from (m, k) so that
   fp32 keeps full precision on hour-long streams;
   a point is dropped (energy 0, zero displacement) when e <= gate, |dt| > N/2,
-  w^ outside [0, N/2], or m + rint(dt/H) outside [0, F-1];
+  w^ outside [-0.5, N/2 + 0.5] (its nearest bin would leave the spectrum; the half-bin margin
+  keeps DC and Nyquist energy, whose w^ sits exactly on 0 and N/2, off a knife edge),
+  or m + rint(dt/H) outside [0, F-1];
   nearest-cell deposit at (m + rint(dt/H), k + rint(dk)), round-half-even (np.rint / rintf).
 Display shaping (/root/reference/README.md:46-51): gain, low-end boost, smoothing,
 noise gate, dB range -> u8 colour index.  Semantics are stand-ins.
@@ -152,7 +154,7 @@ def reassign_points(x: np.ndarray, prm: Params, chunk: int = 256, workers: int =
             dc = dt / H
             col = m + np.rint(dc)
             wh = k + dk
-            ok = (e > gate) & (np.abs(dt) <= N / 2) & (wh >= 0.0) & (wh <= N / 2) \
+            ok = (e > gate) & (np.abs(dt) <= N / 2) & (wh >= -0.5) & (wh <= N / 2 + 0.5) \
                  & (col >= 0) & (col <= F - 1)
             dcol[m0:m1] = np.where(ok, dc, 0.0)
             dbin[m0:m1] = np.where(ok, dk, 0.0)
@@ -171,7 +173,7 @@ def output_row(k, dk, prm: Params):
     a = 10^(2 freq_scale) - 1 (a -> 0: linear)."""
     if prm.display_rows <= 0:
         return k + np.rint(dk).astype(np.int64)
-    x = (k + dk) / (prm.n_fft / 2)
+    x = np.clip((k + dk) / (prm.n_fft / 2), 0.0, 1.0)
     a = prm.warp_a
     u = np.log1p(a * x) / np.log1p(a) if a > 1e-6 else x
     return np.rint(u * (prm.display_rows - 1)).astype(np.int64)

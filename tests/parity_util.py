@@ -51,8 +51,8 @@ def check_points(gpu_pts, x: np.ndarray, prm: orc.Params, hop_for_msg=None):
             # operators of a bin 100 dB under the peak carry ~1e-2 relative error
             slack = 2e-6 * np.sqrt(peak / max(raw[f, k], 1e-300))
             t_tol = 1e-2 + slack * N / 2
-            edge = (abs(abs(dts) - N / 2) < t_tol or abs(wh) < 1e-3 + slack
-                    or abs(wh - N / 2) < 1e-3 + slack
+            edge = (abs(abs(dts) - N / 2) < t_tol or abs(wh + 0.5) < 1e-3 + slack
+                    or abs(wh - N / 2 - 0.5) < 1e-3 + slack
                     or abs(dc - np.rint(dc)) > 0.5 - 2e-3 - t_tol / H)   # column rounding decides in/out of stream
             bad += 0 if edge else 1
         assert bad == 0, f"{bad} kept/dropped mismatches away from any threshold"

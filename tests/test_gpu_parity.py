@@ -269,6 +269,25 @@ def test_stereo_planar(emspec):
         check_grid(g[c].cpu().numpy(), x, prm)
 
 
+def test_batch_of_clips_as_channels(emspec):
+    """configs[3] shape in miniature: equal-length clips passed as planar channels of one call
+    give, clip by clip, what single-clip calls give (clips are independent)."""
+    n_clips, S = 7, SR // 2
+    clips = np.stack([orc.synth_signal(S, SR, clip_index=c) for c in range(n_clips)])
+    fl = emspec.FLAG_REASSIGN | emspec.FLAG_DETERMINISTIC | emspec.FLAG_SYNC
+    batch = emspec.Engine(n_fft=4096, hop=256, channels=n_clips, flags=fl)
+    gb, ib = batch.process_grid(torch.from_numpy(clips).cuda())
+    pb = batch.process_points(torch.from_numpy(clips).cuda())
+    batch.close()
+    one = emspec.Engine(n_fft=4096, hop=256, flags=fl)
+    for c in range(n_clips):
+        g1, i1 = one.process_grid(torch.from_numpy(clips[c]).cuda())
+        p1 = one.process_points(torch.from_numpy(clips[c]).cuda())
+        assert torch.equal(g1[0], gb[c]) and torch.equal(i1[0], ib[c])
+        assert all(torch.equal(a[0], b[c]) for a, b in zip(p1, pb))
+    one.close()
+
+
 def test_process_host_matches_device(emspec):
     """The HOST-buffer call (chunked, overlapped copies) equals the device-buffer call."""
     x = orc.synth_signal(3 * SR, SR, seed=9)
