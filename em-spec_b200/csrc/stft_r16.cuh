@@ -386,9 +386,18 @@ stft_reassign_r16(const StftArgs a_in, const int tile_T) {
                     v[j] = make_float2(x, x * thw[u][j]);
                 }
                 dft16(v);
+                // twiddles W^{b i}: four exact values from the table, the other eleven as products
+                // (<= 3 multiplies deep): 11 x 2 fewer shared-memory wavefronts per butterfly
+                float2 tw[16];
+                tw[1] = Ztab[0 * 256 + b]; tw[2] = Ztab[1 * 256 + b];
+                tw[4] = Ztab[3 * 256 + b]; tw[8] = Ztab[7 * 256 + b];
+                tw[3] = cmul2(tw[1], tw[2]);   tw[5] = cmul2(tw[1], tw[4]);   tw[6] = cmul2(tw[2], tw[4]);
+                tw[7] = cmul2(tw[3], tw[4]);   tw[9] = cmul2(tw[1], tw[8]);   tw[10] = cmul2(tw[2], tw[8]);
+                tw[11] = cmul2(tw[3], tw[8]);  tw[12] = cmul2(tw[4], tw[8]);  tw[13] = cmul2(tw[5], tw[8]);
+                tw[14] = cmul2(tw[6], tw[8]);  tw[15] = cmul2(tw[7], tw[8]);
                 Zb[b] = v[o16(0)];
 #pragma unroll
-                for (int i = 1; i < 16; ++i) Zb[b + 257 * i] = cmul2(v[o16(i)], Ztab[(i - 1) * 256 + b]);
+                for (int i = 1; i < 16; ++i) Zb[b + 257 * i] = cmul2(v[o16(i)], tw[i]);
             });
             worker_bar(w);
             if (last_frame && p == 0) release_tile(buf);   // every sample of the tile has been read
