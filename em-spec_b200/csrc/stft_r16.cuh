@@ -42,7 +42,7 @@ constexpr int kWorkerThreads = 128;
 constexpr int kThreads = kWorkers * kWorkerThreads;
 constexpr int kZBuf = 4112;            // float2, padZ(4095) = 4110
 constexpr int kXBuf = 2052;            // float2: 2 X[k] at index k + 1, mirrors at 0 and 2050
-constexpr int kZtab = 15 * 256;        // W_4096^{b i}, i = 1..15, b < 256
+constexpr int kZtab = 4 * 256;         // W_4096^{b i}, i = 1, 2, 4, 8, b < 256 (the other powers are products)
 constexpr int kT2 = 15 * 16;           // W_256^{p2 i}
 constexpr int kScratch = 20;           // 2 X_th' of the 17 self-paired bins
 constexpr int kTabFloat2 = kZtab + kT2;
@@ -246,7 +246,7 @@ stft_reassign_r16(const StftArgs a_in, const int tile_T) {
     if (!stream_decode(a)) return;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* sm = reinterpret_cast<float2*>(smem_raw);
-    float2* Ztab = sm;                         // [15][256]
+    float2* Ztab = sm;                         // [4][256]: rows i = 1, 2, 4, 8
     float2* T2 = Ztab + kZtab;                 // [15][16]
     float2* wbuf = T2 + kT2;                   // per worker: Z, X, scratch
     float* tile0 = reinterpret_cast<float*>(wbuf + kWorkers * (kZBuf + kXBuf + kScratch));   // 2 x kTileFloats
@@ -261,7 +261,7 @@ stft_reassign_r16(const StftArgs a_in, const int tile_T) {
     float2* Sc = Xs + kXBuf;
 
     // ---- twiddle tables (once per CTA)
-    for (int e = tid; e < kZtab; e += kThreads) { const int i = e / 256 + 1, b = e % 256; Ztab[e] = __ldg(&a.tw[b * i]); }
+    for (int e = tid; e < kZtab; e += kThreads) { const int i = 1 << (e / 256), b = e % 256; Ztab[e] = __ldg(&a.tw[b * i]); }
     for (int e = tid; e < kT2; e += kThreads) { const int i = e / 16 + 1, q = e % 16; T2[e] = __ldg(&a.tw[16 * q * i]); }
 
     // ---- per-thread constants
@@ -390,7 +390,7 @@ stft_reassign_r16(const StftArgs a_in, const int tile_T) {
                 // (<= 3 multiplies deep): 11 x 2 fewer shared-memory wavefronts per butterfly
                 float2 tw[16];
                 tw[1] = Ztab[0 * 256 + b]; tw[2] = Ztab[1 * 256 + b];
-                tw[4] = Ztab[3 * 256 + b]; tw[8] = Ztab[7 * 256 + b];
+                tw[4] = Ztab[2 * 256 + b]; tw[8] = Ztab[3 * 256 + b];
                 tw[3] = cmul2(tw[1], tw[2]);   tw[5] = cmul2(tw[1], tw[4]);   tw[6] = cmul2(tw[2], tw[4]);
                 tw[7] = cmul2(tw[3], tw[4]);   tw[9] = cmul2(tw[1], tw[8]);   tw[10] = cmul2(tw[2], tw[8]);
                 tw[11] = cmul2(tw[3], tw[8]);  tw[12] = cmul2(tw[4], tw[8]);  tw[13] = cmul2(tw[5], tw[8]);
