@@ -163,8 +163,8 @@ def synth_device(S: int, seed: int, device):
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of stft_reassign_r16<store>, one `ncu --set full`
-# capture of a 224,969-frame launch (profiles/r01_ncu_stft_reassign_r16.txt): 5.6015 GB
-NCU_DRAM_BYTES_PER_FRAME = (123.196672e6 + 5.478282e9) / 224969
+# capture of a 224,969-frame launch (profiles/r01_ncu_stft_reassign_r16.txt): 5.6072 GB
+NCU_DRAM_BYTES_PER_FRAME = (126.921216e6 + 5.480240e9) / 224969
 
 
 def peaks():
