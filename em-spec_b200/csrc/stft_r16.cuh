@@ -43,7 +43,7 @@ constexpr int kThreads = kWorkers * kWorkerThreads;
 constexpr int kZBuf = 4112;            // float2, padZ(4095) = 4110
 constexpr int kXBuf = 2052;            // float2: 2 X[k] at index k + 1, mirrors at 0 and 2050
 constexpr int kZtab = 4 * 256;         // W_4096^{b i}, i = 1, 2, 4, 8, b < 256 (the other powers are products)
-constexpr int kT2 = 15 * 16;           // W_256^{p2 i}
+constexpr int kT2 = 16 * 16;           // W_256^{p2 i} as [p2][i]: a butterfly's 16 twiddles are contiguous
 constexpr int kScratch = 20;           // 2 X_th' of the 17 self-paired bins
 constexpr int kTabFloat2 = kZtab + kT2;
 constexpr int kFixedBytes = (kWorkers * (kZBuf + kXBuf + kScratch) + kTabFloat2) * 8;
@@ -247,7 +247,7 @@ stft_reassign_r16(const StftArgs a_in, const int tile_T) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* sm = reinterpret_cast<float2*>(smem_raw);
     float2* Ztab = sm;                         // [4][256]: rows i = 1, 2, 4, 8
-    float2* T2 = Ztab + kZtab;                 // [15][16]
+    float2* T2 = Ztab + kZtab;                 // [16][16]
     float2* wbuf = T2 + kT2;                   // per worker: Z, X, scratch
     float* tile0 = reinterpret_cast<float*>(wbuf + kWorkers * (kZBuf + kXBuf + kScratch));   // 2 x kTileFloats
 
@@ -262,7 +262,7 @@ stft_reassign_r16(const StftArgs a_in, const int tile_T) {
 
     // ---- twiddle tables (once per CTA)
     for (int e = tid; e < kZtab; e += kThreads) { const int i = 1 << (e / 256), b = e % 256; Ztab[e] = __ldg(&a.tw[b * i]); }
-    for (int e = tid; e < kT2; e += kThreads) { const int i = e / 16 + 1, q = e % 16; T2[e] = __ldg(&a.tw[16 * q * i]); }
+    for (int e = tid; e < kT2; e += kThreads) { const int q = e / 16, i = e % 16; T2[e] = __ldg(&a.tw[16 * q * i]); }
 
     // ---- per-thread constants
     // th'[n] = ((n - N/2) / (N/2)) * (0.5 - 0.5 cos(2 pi n / N)) at this thread's 32 pass-1
@@ -412,14 +412,22 @@ stft_reassign_r16(const StftArgs a_in, const int tile_T) {
                 for (int j = 0; j < 16; ++j) v0[j] = bz0[16 * j];
 #pragma unroll
                 for (int j = 0; j < 16; ++j) v1[j] = bz1[16 * j];
+                // twiddles W_256^{p2 i}: the 16 of a butterfly are contiguous, two per 128-bit load
+                // (the whole warp reads two addresses: one wavefront per load)
+                auto twiddle_store = [&](float2 (&v)[16], float2* base, int p2) {
+                    const float4* t4 = reinterpret_cast<const float4*>(T2 + 16 * p2);
+#pragma unroll
+                    for (int h = 0; h < 8; ++h) {
+                        const float4 t = t4[h];
+                        if (h == 0) base[0] = v[o16(0)];
+                        else base[16 * (2 * h)] = cmul2(v[o16(2 * h)], make_float2(t.x, t.y));
+                        base[16 * (2 * h + 1)] = cmul2(v[o16(2 * h + 1)], make_float2(t.z, t.w));
+                    }
+                };
                 dft16(v0);
-                bz0[0] = v0[o16(0)];
-#pragma unroll
-                for (int i = 1; i < 16; ++i) bz0[16 * i] = cmul2(v0[o16(i)], T2[(i - 1) * 16 + q2]);
+                twiddle_store(v0, bz0, q2);
                 dft16(v1);
-                bz1[0] = v1[o16(0)];
-#pragma unroll
-                for (int i = 1; i < 16; ++i) bz1[16 * i] = cmul2(v1[o16(i)], T2[(i - 1) * 16 + q2 + 8]);
+                twiddle_store(v1, bz1, q2 + 8);
             }
             worker_bar(w);
             if (last_frame && refill[w]) refill_tile(buf, ti + 2);
