@@ -34,7 +34,7 @@ struct StftArgs {
     long long     f_end;
     int           channels;
     int           hop;
-    const float4* win;        // [N] {h, th*(2/N), dh*(N/pi), 0}
+    const float*  thw;        // [N] th'[n] = (n - N/2) (2/N) (0.5 - 0.5 cos(2 pi n/N))
     const float2* tw;         // [N] W_N^j = (cos, -sin)(2 pi j / N)
     float*        dt_cols;    // [channels][F][B] or null
     float*        dk_bins;

@@ -37,7 +37,7 @@ struct ems_handle {
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;      // the stream calls run on
     cudaStream_t copy_in = nullptr, copy_out = nullptr;
-    float4* win = nullptr;              // [N]
+    float*  thw = nullptr;              // [N] th' window
     float2* tw = nullptr;               // [N]
     float*  weight = nullptr;           // [B]
     ems::DevBuf acc, flags, carry, ema_local, ema_carry, host_pcm, host_i16, host_idx, host_grid, big_scratch, lut, colscale, agc_level;
@@ -237,7 +237,7 @@ static StftArgs make_args(ems_handle* h, const float* pcm, size_t S, long long F
     StftArgs a{};
     a.pcm = pcm; a.S = (long long)S; a.F = F; a.f_begin = 0; a.f_end = F;
     a.channels = h->prm.channels; a.hop = h->prm.hop;
-    a.win = h->win; a.tw = h->tw;
+    a.thw = h->thw; a.tw = h->tw;
     a.gate_lin = (float)std::pow(10.0, (double)h->prm.noise_gate_db / 10.0);
     a.inv_hop = 1.0f / (float)h->prm.hop;
     a.reassign = (h->prm.flags & EMS_FLAG_REASSIGN) ? 1 : 0;
@@ -560,20 +560,20 @@ ems_status ems_create(const ems_params* params, ems_handle** out) {
             if (cudaEventCreate(&x) != cudaSuccess) return bail(EMS_ERR_CUDA);
 
     const int N = params->n_fft;
-    if (cudaMalloc(&h->win, sizeof(float4) * N) != cudaSuccess ||
+    if (cudaMalloc(&h->thw, sizeof(float) * N) != cudaSuccess ||
         cudaMalloc(&h->tw, sizeof(float2) * N) != cudaSuccess ||
         cudaMalloc(&h->weight, sizeof(float) * rows_of(*params)) != cudaSuccess)
         return bail(EMS_ERR_NOMEM);
-    std::vector<float4> win(N);
+    std::vector<float> thw(N);
     std::vector<float2> tw(N);
     for (int n = 0; n < N; ++n) {
         const double ang = 2.0 * kPi * (double)n / (double)N;
         const double c = std::cos(ang), s = std::sin(ang);
         const double hn = 0.5 - 0.5 * c;
-        win[n] = make_float4((float)hn, (float)(((double)n - N / 2) * hn * (2.0 / N)), (float)s, 0.f);
+        thw[n] = (float)(((double)n - N / 2) * hn * (2.0 / N));
         tw[n] = make_float2((float)c, (float)(-s));
     }
-    if (cudaMemcpy(h->win, win.data(), sizeof(float4) * N, cudaMemcpyHostToDevice) != cudaSuccess ||
+    if (cudaMemcpy(h->thw, thw.data(), sizeof(float) * N, cudaMemcpyHostToDevice) != cudaSuccess ||
         cudaMemcpy(h->tw, tw.data(), sizeof(float2) * N, cudaMemcpyHostToDevice) != cudaSuccess)
         return bail(EMS_ERR_CUDA);
     ems_status s = upload_display(h);
@@ -589,7 +589,7 @@ ems_status ems_destroy(ems_handle* h) {
                       &h->host_idx, &h->host_grid, &h->big_scratch})
         if (b->p) cudaFree(b->p);
     stream_free(h);
-    if (h->win) cudaFree(h->win);
+    if (h->thw) cudaFree(h->thw);
     if (h->tw) cudaFree(h->tw);
     if (h->weight) cudaFree(h->weight);
     for (auto& e : h->ev)

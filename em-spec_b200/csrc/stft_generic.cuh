@@ -148,7 +148,7 @@ stft_reassign_generic(const StftArgs a_in) {
         const float* x = a.pcm + (long long)ch * a.S + f * a.hop + a.samp_off;
         for (int n = tid; n < N; n += THREADS) {
             const float v = __ldg(x + n);
-            Z[n] = make_float2(v, v * __ldg(&a.win[n]).y);
+            Z[n] = make_float2(v, v * __ldg(&a.thw[n]));
         }
         __syncthreads();
         fft_inplace_dif<LOG2N>(Z, a.tw, 0, tid, THREADS);
@@ -193,7 +193,7 @@ stft_reassign_big(const StftArgs a_in, float2* __restrict__ scratch_all) {
 #pragma unroll 1
         for (int wi = 0; wi < 2; ++wi) {
             for (int n = tid; n < N; n += THREADS)
-                Yf[n] = wi == 0 ? __ldg(x + n) : __ldg(x + n) * __ldg(&a.win[n]).y;
+                Yf[n] = wi == 0 ? __ldg(x + n) : __ldg(x + n) * __ldg(&a.thw[n]);
             __syncthreads();
             fft_inplace_dif<LOG2N - 1>(Y, a.tw, 1, tid, THREADS);
             // real FFT of length N from the N/2-point FFT of its even/odd samples

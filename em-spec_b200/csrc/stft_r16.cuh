@@ -265,17 +265,13 @@ stft_reassign_r16(const StftArgs a_in, const int tile_T) {
     for (int e = tid; e < kT2; e += kThreads) { const int q = e / 16, i = e % 16; T2[e] = __ldg(&a.tw[16 * q * i]); }
 
     // ---- per-thread constants
-    // th'[n] = ((n - N/2) / (N/2)) * (0.5 - 0.5 cos(2 pi n / N)) at this thread's 32 pass-1
-    // samples n = p + 128 u + 256 j: frame-independent, so they live in registers for the whole
-    // persistent loop (cos from the table entry of n, exact to fp32 rounding)
+    // th'[n] at this thread's 32 pass-1 samples n = p + 128 u + 256 j: frame-independent, so they
+    // live in registers for the whole persistent loop
     float thw[2][16];
 #pragma unroll
     for (int u = 0; u < 2; ++u)
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            const int n = p + 128 * u + 256 * j;
-            thw[u][j] = (float)(n - N / 2) * (1.0f / (N / 2)) * (0.5f - 0.5f * __ldg(&a.tw[n]).x);
-        }
+        for (int j = 0; j < 16; ++j) thw[u][j] = __ldg(&a.thw[p + 128 * u + 256 * j]);
     const int tA = p, tB = p ? 256 - p : 128;              // output residues of this thread
     const int zA = 257 * (tA & 15) + 16 * (tA >> 4), zB = 257 * (tB & 15) + 16 * (tB >> 4);
     const int i1 = p & 15, q2 = p >> 4;                    // pass-2 butterfly coordinates
