@@ -751,11 +751,14 @@ static ems_status process_host_impl(ems_handle* h, const void* pcm_host_v, bool 
     // Frame chunks: H2D of chunk c+1 overlaps the kernels of chunk c, whose finished
     // columns (those no later frame can reach: col < f_end - R) go back while c+1 runs.
     const long long R = (N / 2 + H - 1) / H;
-    long long chunk = (long long)(((size_t)64 << 20) / ((size_t)H * sizeof(float)));  // ~64 MiB of new samples
+    // Chunk = about 64 MiB of output image: the pipeline's tail is the D2H of the last chunk
+    // (~1.2 ms at PCIe Gen5 rates) whatever the row count, and launches stay large.
+    long long chunk = (long long)(((size_t)64 << 20) / ((size_t)B * C));
     if (const char* ev = getenv("EMS_HOST_CHUNK_FRAMES")) {   // test hook: force small chunks
         const long long v = atoll(ev);
         if (v > 0) chunk = v;
     }
+    if (chunk > 262144) chunk = 262144;
     if (chunk < 4 * R + 1024) chunk = 4 * R + 1024;
     const int n_chunks = (int)((F + chunk - 1) / chunk);
     std::vector<cudaEvent_t> ev_in(n_chunks), ev_done(n_chunks);
