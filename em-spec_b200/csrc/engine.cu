@@ -50,11 +50,11 @@ struct ems_handle {
         bool ready = false;
         cudaGraphExec_t graph = nullptr;
         long long* sstate = nullptr;     // device push counter
-        float* in_dev = nullptr;         // [hop][channels]
+        float* in_dev = nullptr;         // device alias of in_pin
         float* ring = nullptr;           // [channels][2*Lr]
         void* acc = nullptr;             // [channels][ring_cols][B]
         float* carry = nullptr;          // [channels][B]
-        uint8_t* out_dev = nullptr;      // [channels][B]
+        uint8_t* out_dev = nullptr;      // device alias of out_pin
         float* etmp = nullptr;           // [channels][B]
         float* agc = nullptr;            // [2][channels]
         float* in_pin = nullptr;         // pinned staging
@@ -403,8 +403,7 @@ static ems_status finish(ems_handle* h) {
 static void stream_free(ems_handle* h) {
     auto& st = h->st;
     if (st.graph) cudaGraphExecDestroy(st.graph);
-    for (void* p : {(void*)st.sstate, (void*)st.in_dev, (void*)st.ring, st.acc, (void*)st.carry,
-                    (void*)st.out_dev, (void*)st.etmp, (void*)st.agc})
+    for (void* p : {(void*)st.sstate, (void*)st.ring, st.acc, (void*)st.carry, (void*)st.etmp, (void*)st.agc})
         if (p) cudaFree(p);
     if (st.in_pin) cudaFreeHost(st.in_pin);
     if (st.out_pin) cudaFreeHost(st.out_pin);
@@ -414,7 +413,7 @@ static void stream_free(ems_handle* h) {
 static ems_status stream_zero(ems_handle* h) {
     auto& st = h->st;
     const int C = h->prm.channels, B = rows_of(h->prm);
-    EMS_CUDA(h, cudaMemsetAsync(st.sstate, 0, sizeof(long long), h->stream));
+    EMS_CUDA(h, cudaMemsetAsync(st.sstate, 0, 2 * sizeof(long long), h->stream));
     EMS_CUDA(h, cudaMemsetAsync(st.ring, 0, sizeof(float) * C * 2 * st.Lr, h->stream));
     EMS_CUDA(h, cudaMemsetAsync(st.acc, 0, st.acc_bytes, h->stream));
     EMS_CUDA(h, cudaMemsetAsync(st.carry, 0, sizeof(float) * C * B, h->stream));
@@ -433,16 +432,17 @@ static ems_status stream_init(ems_handle* h) {
     st.R = (N / 2 + H - 1) / H;
     st.ring_cols = 2 * st.R + 1;
     st.acc_bytes = (size_t)C * st.ring_cols * B * (det ? 8 : 4);
-    EMS_CUDA(h, cudaMalloc(&st.sstate, sizeof(long long)));
-    EMS_CUDA(h, cudaMalloc(&st.in_dev, sizeof(float) * H * C));
+    EMS_CUDA(h, cudaMalloc(&st.sstate, 2 * sizeof(long long)));
     EMS_CUDA(h, cudaMalloc(&st.ring, sizeof(float) * C * 2 * st.Lr));
     EMS_CUDA(h, cudaMalloc(&st.acc, st.acc_bytes));
     EMS_CUDA(h, cudaMalloc(&st.carry, sizeof(float) * C * B));
-    EMS_CUDA(h, cudaMalloc(&st.out_dev, (size_t)C * B));
     EMS_CUDA(h, cudaMalloc(&st.etmp, sizeof(float) * C * B));
     EMS_CUDA(h, cudaMalloc(&st.agc, sizeof(float) * 2 * C));
-    EMS_CUDA(h, cudaMallocHost(&st.in_pin, sizeof(float) * H * C));
-    EMS_CUDA(h, cudaMallocHost(&st.out_pin, (size_t)C * B));
+    // staging the device reads / writes in place (mapped pinned memory): no copy nodes in the graph
+    EMS_CUDA(h, cudaHostAlloc(&st.in_pin, sizeof(float) * H * C, cudaHostAllocMapped));
+    EMS_CUDA(h, cudaHostAlloc(&st.out_pin, (size_t)C * B, cudaHostAllocMapped));
+    EMS_CUDA(h, cudaHostGetDevicePointer((void**)&st.in_dev, st.in_pin, 0));
+    EMS_CUDA(h, cudaHostGetDevicePointer((void**)&st.out_dev, st.out_pin, 0));
     ems_status s = stream_zero(h);
     if (s != EMS_OK) return s;
     if (N == 32768 && (s = ensure(h, h->big_scratch, (size_t)h->sm_count * (N / 2 + 3) * sizeof(float2))) != EMS_OK) return s;
@@ -450,9 +450,10 @@ static ems_status stream_init(ems_handle* h) {
     return EMS_OK;
 }
 
-// Records one push as a graph: H2D of the hop, ring ingest, fused STFT + reassignment +
-// deposit of the frame the hop completes, post-pass of the column that became final,
-// counter advance, D2H of that column.
+// Records one push as a graph of three kernels: ring ingest (reads the hop from mapped pinned
+// memory), fused STFT + reassignment + deposit of the frame the hop completes, and the finish
+// kernel (post-pass of the column that became final, written to mapped pinned memory, AGC level
+// and push counter advanced).
 static ems_status stream_capture(ems_handle* h) {
     auto& st = h->st;
     const int H = h->prm.hop, C = h->prm.channels, B = rows_of(h->prm);
@@ -484,13 +485,9 @@ static ems_status stream_capture(ems_handle* h) {
         h->stream = user;
         return fail(h, EMS_ERR_CUDA, "stream capture: %s", cudaGetErrorString(be));
     }
-    cudaMemcpyAsync(st.in_dev, st.in_pin, sizeof(float) * H * C, cudaMemcpyHostToDevice, h->stream);
     stream_ingest_kernel<<<(H * C + 255) / 256, 256, 0, h->stream>>>(sa);
     ems_status ls = launch_stft(h, a);
-    stream_shape_kernel<<<(B * C + 255) / 256, 256, 0, h->stream>>>(sa);
-    stream_emit_kernel<<<(B * C + 255) / 256, 256, 0, h->stream>>>(sa);
-    stream_advance_kernel<<<1, 1, 0, h->stream>>>(sa);
-    cudaMemcpyAsync(st.out_pin, st.out_dev, (size_t)C * B, cudaMemcpyDeviceToHost, h->stream);
+    stream_finish_kernel<<<C, 1024, 0, h->stream>>>(sa);
     cudaError_t ce = cudaStreamEndCapture(h->stream, &g);
     h->stream = user;
     h->launches -= 1;                                  // counted per push below, not at capture
@@ -887,7 +884,7 @@ ems_status ems_stream_push(ems_handle* h, const float* pcm_host, uint8_t* column
     const int H = h->prm.hop, C = h->prm.channels, B = rows_of(h->prm);
     memcpy(st.in_pin, pcm_host, sizeof(float) * H * C);
     EMS_CUDA(h, cudaGraphLaunch(st.graph, h->stream));
-    h->launches += 5;
+    h->launches += 3;
     EMS_CUDA(h, cudaStreamSynchronize(h->stream));
     const long long cf = st.pushes + 1 - st.M - st.R;   // column finalised by this push
     ++st.pushes;

@@ -1,6 +1,7 @@
-// stream.cuh — device side of streaming mode (ems_stream_push): sample ring ingest, the
-// post-pass of the column that just became final, and the push counter.  All three read the
-// push counter from device memory so the whole push is one static CUDA graph.
+// stream.cuh — device side of streaming mode (ems_stream_push): sample ring ingest and the
+// post-pass of the column that just became final.  Both read the push counter from device
+// memory, so the whole push is one static CUDA graph of three kernels (ingest, STFT, finish);
+// the hop is read from, and the column written to, mapped pinned host memory directly.
 // Stands in for "start visualizing your system audio" (/root/reference/README.md:36).
 #pragma once
 #include "common.cuh"
@@ -9,15 +10,15 @@
 namespace ems {
 
 struct StreamArgs {
-    long long*   sstate;     // [0] pushes completed
-    const float* in;         // [hop][channels] interleaved, this push
+    long long*   sstate;     // [0] pushes completed, [1] blocks of the finish kernel that are done
+    const float* in;         // [hop][channels] interleaved, this push (mapped pinned host memory)
     float*       ring;       // [channels][2*Lr] doubled sample ring
     void*        acc;        // [channels][ring_cols][B] accumulator ring
     float*       carry;      // [channels][B] EMA state
     const float* weight;     // [B]
-    uint8_t*     out;        // [channels][B] colour index of the final column
+    uint8_t*     out;        // [channels][B] colour index of the final column (mapped pinned host memory)
     float*       etmp;       // [channels][B] shaped energy of the final column
-    float*       agc;        // [2][channels]: column peak, running level
+    float*       agc;        // [2][channels]: (unused), running level
     int hop, channels, M, Lr, R, ring_cols, B, acc_is_u64;
     float smoothing, db_floor, inv_range, gate_db, agc_strength, agc_lambda;
 };
@@ -37,53 +38,67 @@ __global__ void stream_ingest_kernel(const StreamArgs s) {
     }
 }
 
-// Column cf = f - R can no longer receive energy once frame f is in: shape it (weights, EMA),
-// keep its peak for the AGC, and clear its slot for column cf + ring_cols.
-__global__ void stream_shape_kernel(const StreamArgs s) {
-    const long long f = s.sstate[0] + 1 - s.M;
-    const long long cf = f - s.R;
-    if (cf < 0) return;
-    const int slot = (int)(cf % s.ring_cols);
-    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < s.B * s.channels;
-         e += gridDim.x * blockDim.x) {
-        const int ch = e / s.B, k = e - ch * s.B;
-        const long long o = ((long long)ch * s.ring_cols + slot) * s.B + k;
-        float E = acc_load(s.acc, s.acc_is_u64, o) * s.weight[k];
-        if (s.smoothing > 0.f) {
-            E = s.smoothing * s.carry[e] + (1.0f - s.smoothing) * E;
-            s.carry[e] = E;
+// One block per channel finishes the push.  Column cf = f - R can no longer receive energy once
+// frame f is in: shape it (weights, EMA), take its peak for the AGC, emit the colour index
+// straight into the caller-visible pinned column (mapped host memory: no copy node), clear
+// the slot for column cf + ring_cols.  The last block to finish advances the AGC level and the
+// push counter (every block has read the counter before it arrives there).
+__global__ void __launch_bounds__(1024)
+stream_finish_kernel(const StreamArgs s) {
+    __shared__ float s_red[32];
+    __shared__ float s_scale;
+    const long long i = s.sstate[0];
+    const long long cf = i + 1 - s.M - s.R;
+    const int ch = blockIdx.x, t = threadIdx.x;
+    if (cf >= 0) {
+        const int slot = (int)(cf % s.ring_cols);
+        float peak = 0.f;
+        for (int k = t; k < s.B; k += blockDim.x) {
+            const int e = ch * s.B + k;
+            const long long o = ((long long)ch * s.ring_cols + slot) * s.B + k;
+            float E = acc_load(s.acc, s.acc_is_u64, o) * s.weight[k];
+            if (s.smoothing > 0.f) {
+                E = s.smoothing * s.carry[e] + (1.0f - s.smoothing) * E;
+                s.carry[e] = E;
+            }
+            s.etmp[e] = E;
+            peak = fmaxf(peak, E);
+            acc_zero(s.acc, s.acc_is_u64, o);
         }
-        s.etmp[e] = E;
-        if (s.agc_strength > 0.f && E > 0.f) peak_max(s.agc, ch, E);
-        acc_zero(s.acc, s.acc_is_u64, o);
-    }
-}
-
-// Colour index of the final column, drawn at E / level^strength when the AGC is on.
-__global__ void stream_emit_kernel(const StreamArgs s) {
-    if (s.sstate[0] + 1 - s.M - s.R < 0) return;
-    PostArgs pa{};
-    pa.db_floor = s.db_floor; pa.inv_range = s.inv_range; pa.gate_db = s.gate_db;
-    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < s.B * s.channels;
-         e += gridDim.x * blockDim.x) {
-        const int ch = e / s.B;
+        float scale = 1.0f;
         if (s.agc_strength > 0.f) {
-            const float lv = fmaxf(s.agc[ch], s.agc_lambda * s.agc[s.channels + ch]);
-            s.out[e] = colour_index(s.etmp[e], lv > 0.f ? powf(lv, -s.agc_strength) : 1.0f, pa);
+            peak = warp_max(peak);
+            if ((t & 31) == 0) s_red[t >> 5] = peak;
+            __syncthreads();
+            if (t < 32) {
+                float v = t < (int)(blockDim.x >> 5) ? s_red[t] : 0.f;
+                v = warp_max(v);
+                if (t == 0) {
+                    const float lv = fmaxf(v, s.agc_lambda * s.agc[s.channels + ch]);
+                    s.agc[s.channels + ch] = lv;                       // level recurrence
+                    s_scale = lv > 0.f ? powf(lv, -s.agc_strength) : 1.0f;
+                }
+            }
+            __syncthreads();
+            scale = s_scale;
         } else {
-            s.out[e] = colour_index(s.etmp[e], pa);
+            __syncthreads();          // etmp written by this block is re-read below
+        }
+        PostArgs pa{};
+        pa.db_floor = s.db_floor; pa.inv_range = s.inv_range; pa.gate_db = s.gate_db;
+        for (int k = t; k < s.B; k += blockDim.x) {
+            const int e = ch * s.B + k;
+            s.out[e] = s.agc_strength > 0.f ? colour_index(s.etmp[e], scale, pa) : colour_index(s.etmp[e], pa);
         }
     }
-}
-
-// End of a push: AGC level recurrence, then the counter.
-__global__ void stream_advance_kernel(const StreamArgs s) {
-    if (s.sstate[0] + 1 - s.M - s.R >= 0)
-        for (int ch = 0; ch < s.channels; ++ch) {
-            s.agc[s.channels + ch] = fmaxf(s.agc[ch], s.agc_lambda * s.agc[s.channels + ch]);
-            s.agc[ch] = 0.f;
+    __syncthreads();
+    if (t == 0) {
+        __threadfence();
+        if (atomicAdd(reinterpret_cast<unsigned long long*>(s.sstate + 1), 1ull) == (unsigned long long)gridDim.x - 1) {
+            s.sstate[1] = 0;
+            s.sstate[0] = i + 1;
         }
-    s.sstate[0] += 1;
+    }
 }
 
 }  // namespace ems
