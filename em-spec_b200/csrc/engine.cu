@@ -188,15 +188,23 @@ static ems_status launch_big(ems_handle* h, const StftArgs& a) {
     return EMS_OK;
 }
 
-// Tuned n_fft = 4096 kernel: persistent, one CTA per SM, 3 workers x 128 threads.
-static ems_status launch_r16(ems_handle* h, const StftArgs& a, int tile_T) {
-    const size_t smem = (size_t)r16::kFixedBytes + 2 * (size_t)r16::kTileFloats * sizeof(float) + r16::kSyncBytes;
-    void (*kern)(const StftArgs, const int) =
-        a.mode == kStorePoints ? r16::stft_reassign_r16<kStorePoints>
-        : a.mode == kDepositU64 ? r16::stft_reassign_r16<kDepositU64>
-                                : r16::stft_reassign_r16<kDepositF32>;
-    EMS_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, r16::kMaxSmem));
+// Tuned kernels for n_fft = 256 R (R = 4, 8, 16): persistent, one CTA per SM, 48/R workers x 8R threads.
+template <int R>
+static ems_status launch_r16(ems_handle* h, const StftArgs& a) {
+    using C = r16::Cfg<R>;
+    int tile_T = C::tile_frames(a.hop);
+    if (tile_T < 1) return EMS_ERR_UNSUPPORTED;       // not a failure: the caller falls back to the generic kernel
+    // short inputs: smaller tiles so that every SM gets one
     const long long per_ch = a.f_end - a.f_begin;
+    const long long want = (per_ch * a.channels + h->sm_count - 1) / h->sm_count;
+    const long long t = ((want + C::kWorkers - 1) / C::kWorkers) * C::kWorkers;
+    if (t < tile_T) tile_T = (int)std::max<long long>(t, 1);
+    const size_t smem = (size_t)C::kFixedBytes + 2 * (size_t)C::kTileFloats * sizeof(float) + r16::kSyncBytes;
+    void (*kern)(const StftArgs, const int) =
+        a.mode == kStorePoints ? r16::stft_reassign_r16<R, kStorePoints>
+        : a.mode == kDepositU64 ? r16::stft_reassign_r16<R, kDepositU64>
+                                : r16::stft_reassign_r16<R, kDepositF32>;
+    EMS_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, r16::kMaxSmem));
     const long long n_tiles = ((per_ch + tile_T - 1) / tile_T) * a.channels;
     long long grid = h->sm_count;
     if (grid > n_tiles) grid = n_tiles;
@@ -208,16 +216,15 @@ static ems_status launch_r16(ems_handle* h, const StftArgs& a, int tile_T) {
 }
 
 static ems_status launch_stft(ems_handle* h, const StftArgs& a) {
-    if (h->prm.n_fft == 4096 && !h->force_generic) {
-        int tile_T = r16::tile_frames(a.hop);
-        if (tile_T >= r16::kWorkers) {
-            // short inputs: smaller tiles so that every SM gets one
-            const long long per_ch = a.f_end - a.f_begin;
-            const long long want = (per_ch * a.channels + h->sm_count - 1) / h->sm_count;
-            const long long t = ((want + r16::kWorkers - 1) / r16::kWorkers) * r16::kWorkers;
-            if (t < tile_T) tile_T = (int)std::max<long long>(t, r16::kWorkers);
-            return launch_r16(h, a, tile_T);
+    if (!h->force_generic) {
+        ems_status s = EMS_ERR_UNSUPPORTED;
+        switch (h->prm.n_fft) {
+            case 1024: s = launch_r16<4>(h, a); break;
+            case 2048: s = launch_r16<8>(h, a); break;
+            case 4096: s = launch_r16<16>(h, a); break;
+            default: break;
         }
+        if (s != EMS_ERR_UNSUPPORTED) return s;
     }
     switch (ilog2(h->prm.n_fft)) {
         case 8:  return launch_generic<8>(h, a);

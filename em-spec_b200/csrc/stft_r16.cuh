@@ -1,6 +1,7 @@
-// stft_r16.cuh — tuned fused frame gather + 3-window STFT + reassignment for n_fft = 4096.
+// stft_r16.cuh — tuned fused frame gather + 3-window STFT + reassignment for
+// n_fft = 256 R, R = 4, 8, 16 (1024, 2048, 4096).
 //
-// ONE complex FFT per frame.  Z = FFT_4096(x + j*x*th'), th' = th*(2/N): the real part is the
+// ONE complex FFT per frame.  Z = FFT_N(x + j*x*th'), th' = th*(2/N): the real part is the
 // *unwindowed* frame, so the untangle gives the rectangular-window spectrum X and X_th'.
 // Hann and its derivative are three-tap stencils of X in frequency
 //     X_h[k]   = X[k]/2 - (X[k-1] + X[k+1])/4          (h  = 0.5 - 0.5 cos(2 pi n/N))
@@ -11,20 +12,22 @@
 // probed against the float64 oracle: <= 4.3e-5 col / 5.2e-6 bin within 40 dB of the peak.
 //
 // Layout of the work (DESIGN.md "K1-K3"):
-//   * persistent CTAs, one per SM, 3 workers x 128 threads; a CTA walks tiles of T
-//     consecutive frames whose samples ((T-1)*hop + 4096 floats) sit once in shared memory,
-//     double-buffered with cp.async; buffers are handed over through an mbarrier and a
-//     release counter, never a CTA-wide barrier, so the workers run out of phase;
-//   * a worker analyses one frame at a time, entirely on-chip: Z as 16 x 16 x 16, two radix-16
-//     butterflies per thread per pass in packed fp32x2 arithmetic, in-place
-//     decimation-in-frequency in the worker's private buffer, padding padZ(a) = a + (a >> 8)
-//     makes every exchange bank-conflict-free (tools/bank_sim.py);
-//   * th' is not stored: cos(2 pi n/N) comes from the thread's base angle rotated by immediates;
-//   * the last pass gives thread p the output residues t = p and 256 - p, so Z[k] and Z[N-k] of
-//     its 16 bins are in its own registers: untangle in registers, X (16 KB) goes to shared
-//     memory once so that each bin can read its two neighbours, then the Auger-Flandrin
-//     epilogue runs on the thread's own bins.  3 named barriers per frame.  Residues 0 and 128
-//     pair with themselves (17 bins): one thread untangles them, 17 lanes of its warp finish them.
+//   * persistent CTAs, one per SM, 48/R workers x 8R threads (3 x 128 at n_fft = 4096); a CTA
+//     walks tiles of T consecutive frames whose samples ((T-1)*hop + N floats) sit once in
+//     shared memory, double-buffered with cp.async; buffers are handed over through an
+//     mbarrier and a release counter, never a CTA-wide barrier, so the workers run out of phase;
+//   * a worker analyses one frame at a time, entirely on-chip: Z as R x 16 x 16 — pass 1 is
+//     32/R radix-R butterflies per thread straight from the tile, passes 2 and 3 two radix-16
+//     butterflies per thread — in packed fp32x2 arithmetic, in-place decimation-in-frequency
+//     in the worker's private buffer; the padding (Cfg::kSI, Cfg::kS16) makes every exchange
+//     bank-conflict-free (tools/bank_sim.py);
+//   * th' of a thread's 32 pass-1 samples is frame-independent and lives in registers;
+//   * the last pass gives thread p the output residues t = p and 16R - p (mod 16R), so Z[k] and
+//     Z[N-k] of its 16 bins are in its own registers: untangle in registers, X (N/2+1 values)
+//     goes to shared memory once so that each bin can read its two neighbours, then the
+//     Auger-Flandrin epilogue runs on the thread's own bins.  3 worker barriers per frame.
+//     Residues 0 and 8R pair with themselves (17 bins): one thread untangles them, 17 lanes of
+//     its warp finish them.
 // Decisions (gate, drop rule, deposit) are those of stft_generic.cuh::reassign_emit.
 #pragma once
 #include "common.cuh"
@@ -36,27 +39,42 @@
 namespace ems {
 namespace r16 {
 
-constexpr int N = 4096;
-constexpr int kWorkers = 3;
-constexpr int kWorkerThreads = 128;
-constexpr int kThreads = kWorkers * kWorkerThreads;
-constexpr int kZBuf = 4112;            // float2, padZ(4095) = 4110
-constexpr int kXBuf = 2052;            // float2: 2 X[k] at index k + 1, mirrors at 0 and 2050
-constexpr int kZtab = 4 * 256;         // W_4096^{b i}, i = 1, 2, 4, 8, b < 256 (the other powers are products)
+constexpr int kMaxSmem = 232448;       // 227 KB
+constexpr int kSyncBytes = 128;        // 2 mbarriers, 2 release counters, kWorkers refill flags
 constexpr int kT2 = 16 * 16;           // W_256^{p2 i} as [p2][i]: a butterfly's 16 twiddles are contiguous
 constexpr int kScratch = 20;           // 2 X_th' of the 17 self-paired bins
-constexpr int kTabFloat2 = kZtab + kT2;
-constexpr int kFixedBytes = (kWorkers * (kZBuf + kXBuf + kScratch) + kTabFloat2) * 8;
-constexpr int kMaxSmem = 232448;       // 227 KB
-constexpr int kSyncBytes = 64;          // 2 mbarriers, 2 release counters, kWorkers refill flags
-constexpr int kTileFloats = ((kMaxSmem - kFixedBytes - kSyncBytes) / 8) & ~3;   // per buffer, two buffers
+constexpr int kThreads = 384;
 
-// frames per tile: both tile buffers must hold (T-1)*hop + N samples
-__host__ __device__ constexpr int tile_frames(int hop) {
-    int t = (kTileFloats - N) / hop + 1;
-    t -= t % kWorkers;
-    return t > 36 ? 36 : t;
-}
+template <int R_>
+struct Cfg {
+    static_assert(R_ == 4 || R_ == 8 || R_ == 16, "pass-1 radix");
+    static constexpr int R = R_;                    // radix of pass 1; passes 2 and 3 are radix 16
+    static constexpr int kLogR = R == 4 ? 2 : R == 8 ? 3 : 4;
+    static constexpr int N = 256 * R;
+    static constexpr int kWT = 8 * R;               // threads per worker
+    static constexpr int kWorkers = kThreads / kWT;
+    static constexpr int kU = 32 / R;               // pass-1 butterflies per thread
+    static constexpr int kRes = 16 * R;             // output residues of the last pass: k = t + kRes c
+    // Z buffer: element b of sub-FFT i sits at kSI i + b + (b >> 4) (kS16 - 16).  With R = 16 the
+    // classic 257 stride does it; narrower pass-1 radices put several sub-FFT rows of the same i
+    // into one half-warp, so every 16 elements get one slot of padding and kSI = 16/R (mod 16).
+    static constexpr int kS16 = R >= 16 ? 16 : 17;
+    static constexpr int kSI = R >= 16 ? 257 : 272 + 16 / R;
+    static constexpr int kZBuf = R >= 16 ? 4112 : R * kSI;
+    static constexpr int kXBuf = N / 2 + 4;         // float2: 2 X[k] at index k + 1, mirrors at 0 and N/2 + 2
+    static constexpr int kZtab = kLogR * 256;       // W_N^{b i}, i = 1, 2, 4, .., b < 256 (the other powers are products)
+    static constexpr int kTabFloat2 = kZtab + kT2;
+    static constexpr int kFixedBytes = (kWorkers * (kZBuf + kXBuf + kScratch) + kTabFloat2) * 8;
+    static constexpr int kTileFloats = ((kMaxSmem - kFixedBytes - kSyncBytes) / 8) & ~3;   // per buffer, two buffers
+    static constexpr int kMaxTile = 12 * kWorkers;
+    // frames per tile: both tile buffers must hold (T-1)*hop + N samples
+    __host__ __device__ static constexpr int tile_frames(int hop) {
+        int t = (kTileFloats - N) / hop + 1;
+        if (t > kWorkers) t -= t % kWorkers;
+        return t > kMaxTile ? kMaxTile : t;
+    }
+    __host__ __device__ static constexpr int zpos(int i, int b) { return kSI * i + b + (b >> 4) * (kS16 - 16); }
+};
 
 template <int... Is, class Fn>
 __device__ __forceinline__ void static_for_impl(std::integer_sequence<int, Is...>, Fn&& fn) {
@@ -138,8 +156,32 @@ __device__ __forceinline__ void dft16(float2 (&a)[16]) {
     for (int i0 = 0; i0 < 4; ++i0) dft4(a[4 * i0], a[4 * i0 + 1], a[4 * i0 + 2], a[4 * i0 + 3]);
 }
 
+// forward DFT-8 in registers.  Output i sits in a[o8(i)].
+__host__ __device__ constexpr int o8(int i) { return 2 * (i & 3) + (i >> 2); }
+
+__device__ __forceinline__ void dft8(float2 (&a)[8]) {
+    dft4(a[0], a[2], a[4], a[6]);
+    dft4(a[1], a[3], a[5], a[7]);
+    // a[1 + 2 i0] *= W8^{i0}
+    a[3] = mul_w16<2>(a[3]);   a[5] = mul_w16<4>(a[5]);   a[7] = mul_w16<6>(a[7]);
+#pragma unroll
+    for (int i0 = 0; i0 < 4; ++i0) {
+        const float2 s = a[2 * i0] + a[2 * i0 + 1], d = a[2 * i0] - a[2 * i0 + 1];
+        a[2 * i0] = s; a[2 * i0 + 1] = d;
+    }
+}
+
+// radix-R butterfly of pass 1; output i sits in a[oR<R>(i)]
+template <int R> __host__ __device__ constexpr int oR(int i) { return R == 16 ? o16(i) : R == 8 ? o8(i) : i; }
+__device__ __forceinline__ void dftR(float2 (&a)[16]) { dft16(a); }
+__device__ __forceinline__ void dftR(float2 (&a)[8]) { dft8(a); }
+__device__ __forceinline__ void dftR(float2 (&a)[4]) { dft4(a[0], a[1], a[2], a[3]); }
+
+// barrier of one worker (a single warp when n_fft = 1024)
+template <int WT>
 __device__ __forceinline__ void worker_bar(int w) {
-    asm volatile("bar.sync %0, %1;" ::"r"(w + 1), "r"(kWorkerThreads) : "memory");
+    if constexpr (WT == 32) __syncwarp();
+    else asm volatile("bar.sync %0, %1;" ::"r"(w + 1), "r"(WT) : "memory");
 }
 
 // cos(q pi/16), sin(q pi/16) for compile-time q
@@ -201,7 +243,7 @@ __device__ __noinline__ void deposit_point(const DepositCtx d, int ch, long long
 //   xk, xm, xp = 2 X[k], 2 X[k-1], 2 X[k+1];  t2 = 2 X_th'[k]
 // A whole warp under the gate leaves after the stencil; everything else is predicated.
 // Must be reached by all 32 lanes of the warp (`owner` masks lanes that only tag along).
-template <int MODE>
+template <int N, int MODE>
 __device__ __forceinline__ void bin_emit(const StftArgs& a, const FrameCtx& fc, bool owner, int k,
                                          float kf, float2 xk, float2 xm, float2 xp, float2 t2) {
     const float2 A2 = fma2(xm + xp, make_float2(-0.25f, -0.25f), mul2(xk, make_float2(0.5f, 0.5f)));   // 2 X_h
@@ -239,47 +281,52 @@ __device__ __forceinline__ void bin_emit(const StftArgs& a, const FrameCtx& fc, 
 // conj(a)
 __device__ __forceinline__ float2 cj(float2 a) { return make_float2(a.x, -a.y); }
 
-template <int MODE>
+template <int R, int MODE>
 __global__ void __launch_bounds__(kThreads, 1)
 stft_reassign_r16(const StftArgs a_in, const int tile_T) {
+    using C = Cfg<R>;
+    constexpr int N = C::N, kWT = C::kWT, kWorkers = C::kWorkers, kRes = C::kRes, kZBuf = C::kZBuf,
+                  kXBuf = C::kXBuf, kZtab = C::kZtab, kTileFloats = C::kTileFloats, kSI = C::kSI,
+                  kS16 = C::kS16, kU = C::kU, kLogR = C::kLogR;
     StftArgs a = a_in;
     if (!stream_decode(a)) return;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* sm = reinterpret_cast<float2*>(smem_raw);
-    float2* Ztab = sm;                         // [4][256]: rows i = 1, 2, 4, 8
+    float2* Ztab = sm;                         // [log2 R][256]: rows i = 1, 2, 4, ..
     float2* T2 = Ztab + kZtab;                 // [16][16]
     float2* wbuf = T2 + kT2;                   // per worker: Z, X, scratch
     float* tile0 = reinterpret_cast<float*>(wbuf + kWorkers * (kZBuf + kXBuf + kScratch));   // 2 x kTileFloats
 
     const int tid = threadIdx.x;
-    const int w = tid >> 7;                    // worker
+    const int w = tid / kWT;                   // worker
     // role of this thread inside its worker; rotated by one warp per worker so that the warp
     // carrying the self-paired bins lands on a different scheduler in each worker
-    const int p = (tid + 32 * w) & 127;
+    const int p = (tid + 32 * w) & (kWT - 1);
     float2* Zb = wbuf + w * (kZBuf + kXBuf + kScratch);
     float2* Xs = Zb + kZBuf;                   // 2 X[k] at Xs[k + 1]
     float2* Sc = Xs + kXBuf;
 
     // ---- twiddle tables (once per CTA)
     for (int e = tid; e < kZtab; e += kThreads) { const int i = 1 << (e / 256), b = e % 256; Ztab[e] = __ldg(&a.tw[b * i]); }
-    for (int e = tid; e < kT2; e += kThreads) { const int q = e / 16, i = e % 16; T2[e] = __ldg(&a.tw[16 * q * i]); }
+    for (int e = tid; e < kT2; e += kThreads) { const int q = e / 16, i = e % 16; T2[e] = __ldg(&a.tw[R * q * i]); }
 
     // ---- per-thread constants
-    // th'[n] at this thread's 32 pass-1 samples n = p + 128 u + 256 j: frame-independent, so they
+    // th'[n] at this thread's 32 pass-1 samples n = p + kWT u + 256 j: frame-independent, so they
     // live in registers for the whole persistent loop
-    float thw[2][16];
+    float thw[kU][R];
 #pragma unroll
-    for (int u = 0; u < 2; ++u)
+    for (int u = 0; u < kU; ++u)
 #pragma unroll
-        for (int j = 0; j < 16; ++j) thw[u][j] = __ldg(&a.thw[p + 128 * u + 256 * j]);
-    const int tA = p, tB = p ? 256 - p : 128;              // output residues of this thread
-    const int zA = 257 * (tA & 15) + 16 * (tA >> 4), zB = 257 * (tB & 15) + 16 * (tB >> 4);
-    const int i1 = p & 15, q2 = p >> 4;                    // pass-2 butterfly coordinates
+        for (int j = 0; j < R; ++j) thw[u][j] = __ldg(&a.thw[p + kWT * u + 256 * j]);
+    const int tA = p, tB = p ? kRes - p : kRes / 2;        // output residues of this thread
+    // residue t = i + R i' holds the outputs of row i' of sub-FFT i
+    const int zA = kSI * (tA & (R - 1)) + kS16 * (tA / R), zB = kSI * (tB & (R - 1)) + kS16 * (tB / R);
+    const int i1 = p & (R - 1), q2 = p / R;                // pass-2 butterfly coordinates
     const bool owner = p != 0;                              // thread 0's residues pair with themselves
     const float tAf = (float)tA, tBf = (float)tB;
-    // self-paired bins (residues 0 and 128): lane l <= 8 takes bin 256 l, lanes 9..16 bins 128 + 256 (l - 9)
+    // self-paired bins (residues 0 and 8R): lane l <= 8 takes bin kRes l, lanes 9..16 bins kRes/2 + kRes (l - 9)
     const int ls = min(p, 16);
-    const int ks = ls <= 8 ? 256 * ls : 128 + 256 * (ls - 9);
+    const int ks = ls <= 8 ? kRes * ls : kRes / 2 + kRes * (ls - 9);
 
     const long long per_ch = a.f_end - a.f_begin;
     const long long tiles_per_ch = (per_ch + tile_T - 1) / tile_T;
@@ -289,9 +336,10 @@ stft_reassign_r16(const StftArgs a_in, const int tile_T) {
     // Tiles are double-buffered and handed over without any CTA-wide barrier, so the three
     // workers drift apart and their FP-heavy and shared-memory-heavy phases interleave (in
     // lockstep they collide: measured +13 %).  Protocol per buffer b:
-    //   * a worker that has read its last sample of the tile in b bumps done[b]; the third one
-    //     to do so refills b with the tile after next (cp.async from its 128 threads, 4-byte
-    //     copies: no alignment demands) and the copies arrive on the mbarrier full[b];
+    //   * a worker that has read its last sample of the tile in b bumps done[b]; the last one
+    //     to do so refills b with the tile after next (cp.async from its own threads, 16-byte
+    //     copies when the tile starts on a 16-byte boundary and hop is a multiple of 4, else
+    //     4-byte ones) and the copies arrive on the mbarrier full[b];
     //   * a worker waits on full[b] before it reads a refilled buffer.
     unsigned long long* full = reinterpret_cast<unsigned long long*>(tile0 + 2 * kTileFloats);   // [2]
     unsigned* done = reinterpret_cast<unsigned*>(full + 2);                                     // [2]
@@ -308,8 +356,13 @@ stft_reassign_r16(const StftArgs a_in, const int tile_T) {
         const int n_samp = (nf - 1) * a.hop + N;
         const float* src = a.pcm + (long long)ch * a.S + f0 * a.hop + a.samp_off;
         const unsigned d0 = (unsigned)__cvta_generic_to_shared(dst);
-        for (int s = t0; s < n_samp; s += nth)
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d0 + 4u * s), "l"(src + s) : "memory");
+        if ((((unsigned long long)src | (unsigned long long)(unsigned)a.hop * 4ull) & 15ull) == 0) {
+            for (int s = 4 * t0; s < n_samp; s += 4 * nth)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d0 + 4u * s), "l"(src + s) : "memory");
+        } else {
+            for (int s = t0; s < n_samp; s += nth)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d0 + 4u * s), "l"(src + s) : "memory");
+        }
     };
     // prologue: the first two tiles by all threads
     const long long tile_step = gridDim.x;
@@ -317,8 +370,8 @@ stft_reassign_r16(const StftArgs a_in, const int tile_T) {
     if ((long long)blockIdx.x + tile_step < n_tiles) copy_tile(blockIdx.x + tile_step, tile0 + kTileFloats, tid, kThreads);
     asm volatile("cp.async.commit_group;" ::: "memory");
     if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(full_sm), "r"(kWorkerThreads));
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(full_sm + 8), "r"(kWorkerThreads));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(full_sm), "r"(kWT));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(full_sm + 8), "r"(kWT));
         done[0] = 0; done[1] = 0;
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -335,11 +388,11 @@ stft_reassign_r16(const StftArgs a_in, const int tile_T) {
         __threadfence_block();
         refill[w] = last ? 1 : 0;
     };
-    // all 128 threads of the refilling worker
+    // all threads of the refilling worker
     auto refill_tile = [&](int b, long long ti_next) {
         const long long tl2 = blockIdx.x + ti_next * tile_step;
         if (tl2 >= n_tiles) return;
-        copy_tile(tl2, tile0 + b * kTileFloats, p, kWorkerThreads);
+        copy_tile(tl2, tile0 + b * kTileFloats, p, kWT);
         asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(full_sm + 8u * b) : "memory");
     };
 
@@ -360,9 +413,9 @@ stft_reassign_r16(const StftArgs a_in, const int tile_T) {
         const long long chan_off = a.ring ? 0 : (long long)ch * a.F;
         if (w >= nf) {                      // no frame for this worker in a short tile: just release it
             if (p == 0) release_tile(buf);
-            worker_bar(w);
+            worker_bar<kWT>(w);
             if (refill[w]) refill_tile(buf, ti + 2);
-            worker_bar(w);
+            worker_bar<kWT>(w);
             continue;
         }
 
@@ -371,43 +424,47 @@ stft_reassign_r16(const StftArgs a_in, const int tile_T) {
             const long long f = f0 + fi;
             const bool last_frame = fi + kWorkers >= nf;
 
-            // ================= pass 1: butterflies b = p, p + 128 on z[n] = x[n] (1 + j th'[n])
-            static_for<2>([&](auto uc) {
+            // ================= pass 1: radix-R butterflies b = p + kWT u on z[n] = x[n] (1 + j th'[n])
+            static_for<kU>([&](auto uc) {
                 constexpr int u = decltype(uc)::value;
-                const int b = p + 128 * u;
-                float2 v[16];
+                const int b = p + kWT * u;
+                float2 v[R];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
+                for (int j = 0; j < R; ++j) {
                     const float x = xs[b + 256 * j];                   // n = b + 256 j
                     v[j] = make_float2(x, x * thw[u][j]);
                 }
-                dft16(v);
-                // twiddles W^{b i}: four exact values from the table, the other eleven as products
-                // (<= 3 multiplies deep): 11 x 2 fewer shared-memory wavefronts per butterfly
-                float2 tw[16];
-                tw[1] = Ztab[0 * 256 + b]; tw[2] = Ztab[1 * 256 + b];
-                tw[4] = Ztab[2 * 256 + b]; tw[8] = Ztab[3 * 256 + b];
-                tw[3] = cmul2(tw[1], tw[2]);   tw[5] = cmul2(tw[1], tw[4]);   tw[6] = cmul2(tw[2], tw[4]);
-                tw[7] = cmul2(tw[3], tw[4]);   tw[9] = cmul2(tw[1], tw[8]);   tw[10] = cmul2(tw[2], tw[8]);
-                tw[11] = cmul2(tw[3], tw[8]);  tw[12] = cmul2(tw[4], tw[8]);  tw[13] = cmul2(tw[5], tw[8]);
-                tw[14] = cmul2(tw[6], tw[8]);  tw[15] = cmul2(tw[7], tw[8]);
-                Zb[b] = v[o16(0)];
+                dftR(v);
+                // twiddles W^{b i}: log2 R exact values from the table, the others as products
+                // (<= 3 multiplies deep): two fewer shared-memory wavefronts per product
+                float2 tw[R];
+                static_for<kLogR>([&](auto lc) {
+                    constexpr int l = decltype(lc)::value;
+                    tw[1 << l] = Ztab[l * 256 + b];
+                });
+                static_for<R>([&](auto ic) {
+                    constexpr int i = decltype(ic)::value;
+                    constexpr int hb = i >= 8 ? 8 : i >= 4 ? 4 : i >= 2 ? 2 : 1;     // highest set bit
+                    if constexpr (i > hb && hb > 0 && i >= 3) tw[i] = cmul2(tw[i - hb], tw[hb]);
+                });
+                float2* zo = Zb + b + (b >> 4) * (kS16 - 16);
+                zo[0] = v[oR<R>(0)];
 #pragma unroll
-                for (int i = 1; i < 16; ++i) Zb[b + 257 * i] = cmul2(v[o16(i)], tw[i]);
+                for (int i = 1; i < R; ++i) zo[kSI * i] = cmul2(v[oR<R>(i)], tw[i]);
             });
-            worker_bar(w);
+            worker_bar<kWT>(w);
             if (last_frame && p == 0) release_tile(buf);   // every sample of the tile has been read
 
             // ================= pass 2: sub-FFTs of length 256, butterflies (i1, q2), (i1, q2 + 8),
             // software-pipelined by hand: the second butterfly's loads fly while the first computes
             {
-                float2* bz0 = Zb + 257 * i1 + q2;
+                float2* bz0 = Zb + kSI * i1 + q2;
                 float2* bz1 = bz0 + 8;
                 float2 v0[16], v1[16];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) v0[j] = bz0[16 * j];
+                for (int j = 0; j < 16; ++j) v0[j] = bz0[kS16 * j];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) v1[j] = bz1[16 * j];
+                for (int j = 0; j < 16; ++j) v1[j] = bz1[kS16 * j];
                 // twiddles W_256^{p2 i}: the 16 of a butterfly are contiguous, two per 128-bit load
                 // (the whole warp reads two addresses: one wavefront per load)
                 auto twiddle_store = [&](float2 (&v)[16], float2* base, int p2) {
@@ -416,8 +473,8 @@ stft_reassign_r16(const StftArgs a_in, const int tile_T) {
                     for (int h = 0; h < 8; ++h) {
                         const float4 t = t4[h];
                         if (h == 0) base[0] = v[o16(0)];
-                        else base[16 * (2 * h)] = cmul2(v[o16(2 * h)], make_float2(t.x, t.y));
-                        base[16 * (2 * h + 1)] = cmul2(v[o16(2 * h + 1)], make_float2(t.z, t.w));
+                        else base[kS16 * (2 * h)] = cmul2(v[o16(2 * h)], make_float2(t.x, t.y));
+                        base[kS16 * (2 * h + 1)] = cmul2(v[o16(2 * h + 1)], make_float2(t.z, t.w));
                     }
                 };
                 dft16(v0);
@@ -425,7 +482,7 @@ stft_reassign_r16(const StftArgs a_in, const int tile_T) {
                 dft16(v1);
                 twiddle_store(v1, bz1, q2 + 8);
             }
-            worker_bar(w);
+            worker_bar<kWT>(w);
             if (last_frame && refill[w]) refill_tile(buf, ti + 2);
 
             // ================= pass 3: residues tA, tB; untangle; X to shared memory
@@ -434,7 +491,7 @@ stft_reassign_r16(const StftArgs a_in, const int tile_T) {
             for (int j = 0; j < 16; ++j) { za[j] = Zb[zA + j]; zb[j] = Zb[zB + j]; }
             dft16(za); dft16(zb);
             // 2 X[k] = Z[k] + conj Z[N-k],  2 X_th'[k] = (Z[k] - conj Z[N-k]) / j
-            float2 xa[8], xb[8], ta[8], tb[8];     // bins tA + 256 c and tB + 256 c, c = 0..7
+            float2 xa[8], xb[8], ta[8], tb[8];     // bins tA + kRes c and tB + kRes c, c = 0..7
             if (p != 0) {
                 static_for<8>([&](auto cc) {
                     constexpr int c = decltype(cc)::value;
@@ -442,30 +499,30 @@ stft_reassign_r16(const StftArgs a_in, const int tile_T) {
                     const float2 zb_c = zb[o16(c)], za_n = cj(za[o16(15 - c)]);
                     xa[c] = za_c + zb_n; ta[c] = mulmj(za_c - zb_n);
                     xb[c] = zb_c + za_n; tb[c] = mulmj(zb_c - za_n);
-                    Xs[1 + tA + 256 * c] = xa[c];
-                    Xs[1 + tB + 256 * c] = xb[c];
+                    Xs[1 + tA + kRes * c] = xa[c];
+                    Xs[1 + tB + kRes * c] = xb[c];
                 });
                 if (p == 1) {      // Hermitian mirrors: X[-1] = conj X[1], X[N/2+1] = conj X[N/2-1]
                     Xs[0] = cj(xa[0]);
-                    Xs[2050] = cj(xb[7]);
+                    Xs[N / 2 + 2] = cj(xb[7]);
                 }
             } else {
-                // residues 0 (bins 256 c, c = 0..8) and 128 (bins 128 + 256 c) pair with themselves
+                // residues 0 (bins kRes c, c = 0..8) and kRes/2 (bins kRes/2 + kRes c) pair with themselves
                 static_for<9>([&](auto cc) {
                     constexpr int c = decltype(cc)::value;
                     const float2 z = za[o16(c & 15)], zn = cj(za[o16((16 - c) & 15)]);
-                    Xs[1 + 256 * c] = z + zn;
+                    Xs[1 + kRes * c] = z + zn;
                     Sc[c] = mulmj(z - zn);
                 });
                 static_for<8>([&](auto cc) {
                     constexpr int c = decltype(cc)::value;
                     const float2 z = zb[o16(c)], zn = cj(zb[o16(15 - c)]);
-                    Xs[1 + 128 + 256 * c] = z + zn;
+                    Xs[1 + kRes / 2 + kRes * c] = z + zn;
                     Sc[9 + c] = mulmj(z - zn);
                     xa[c] = z; xb[c] = z; ta[c] = z; tb[c] = z;        // placeholders, never stored
                 });
             }
-            worker_bar(w);      // X visible; the Z buffer is free for the next frame's pass 1
+            worker_bar<kWT>(w);      // X visible; the Z buffer is free for the next frame's pass 1
 
             // ================= epilogue on the thread's own bins
             FrameCtx fc;
@@ -476,13 +533,13 @@ stft_reassign_r16(const StftArgs a_in, const int tile_T) {
             fc.pd = a.dt_cols + row0; fc.pk = a.dk_bins + row0; fc.pe = a.energy + row0;
             static_for<8>([&](auto cc) {
                 constexpr int c = decltype(cc)::value;
-                bin_emit<MODE>(a, fc, owner, tA + 256 * c, tAf + (float)(256 * c), xa[c],
-                               Xs[tA + 256 * c], Xs[tA + 256 * c + 2], ta[c]);
-                bin_emit<MODE>(a, fc, owner, tB + 256 * c, tBf + (float)(256 * c), xb[c],
-                               Xs[tB + 256 * c], Xs[tB + 256 * c + 2], tb[c]);
+                bin_emit<N, MODE>(a, fc, owner, tA + kRes * c, tAf + (float)(kRes * c), xa[c],
+                                  Xs[tA + kRes * c], Xs[tA + kRes * c + 2], ta[c]);
+                bin_emit<N, MODE>(a, fc, owner, tB + kRes * c, tBf + (float)(kRes * c), xb[c],
+                                  Xs[tB + kRes * c], Xs[tB + kRes * c + 2], tb[c]);
             });
             if (p < 32)   // the 17 self-paired bins, one per lane (the rest of the warp tags along)
-                bin_emit<MODE>(a, fc, p <= 16, ks, (float)ks, Xs[ks + 1], Xs[ks], Xs[ks + 2], Sc[ls]);
+                bin_emit<N, MODE>(a, fc, p <= 16, ks, (float)ks, Xs[ks + 1], Xs[ks], Xs[ks + 2], Sc[ls]);
         }
     }
 }

@@ -111,9 +111,36 @@ def check_grid_rows(grid_gpu, x: np.ndarray, prm: orc.Params):
     return w1 / tot, grid_o
 
 
-def check_index(idx_gpu, grid_o: np.ndarray, prm: orc.Params):
+def boundary_cells(x: np.ndarray, prm: orc.Params) -> np.ndarray:
+    """Cells a point may land in or leave because nearest-cell deposit is discontinuous: the
+    oracle's point sits within the coordinate tolerance of a rounding boundary (x.5 columns or
+    bins), so the fp32 coordinate may round to the neighbouring cell.  The tolerance is the
+    north_star 1e-3 plus the fp32 noise floor of the operators at that bin's level (same slack
+    as the validity flips in check_points).  Bin-per-row axis only."""
+    assert prm.display_rows == 0
+    dt_o, dk_o, e_o, raw = orc.reassign_points(x, prm, return_raw=True)
+    F, B = e_o.shape
+    valid = e_o > 0
+    slack = 2e-6 * np.sqrt(raw.max() / np.maximum(raw, 1e-300))
+    tol_t = COORD_TOL + slack * (prm.n_fft / 2) / prm.hop
+    tol_k = COORD_TOL + slack
+    near_t = valid & (np.abs(dt_o - np.rint(dt_o)) > 0.5 - tol_t)
+    near_k = valid & (np.abs(dk_o - np.rint(dk_o)) > 0.5 - tol_k)
+    mask = np.zeros((F, B), bool)
+    for f, k in np.argwhere(near_t | near_k):
+        cols = {f + int(np.floor(dt_o[f, k])), f + int(np.ceil(dt_o[f, k]))} if near_t[f, k] else {f + int(np.rint(dt_o[f, k]))}
+        rows = {k + int(np.floor(dk_o[f, k])), k + int(np.ceil(dk_o[f, k]))} if near_k[f, k] else {k + int(np.rint(dk_o[f, k]))}
+        for c in cols:
+            for r in rows:
+                if 0 <= c < F and 0 <= r < B:
+                    mask[c, r] = True
+    return mask
+
+
+def check_index(idx_gpu, grid_o: np.ndarray, prm: orc.Params, x: np.ndarray | None = None):
     """u8 colour index: a quantised float -> +-1 at rounding boundaries, flips allowed only
-    for cells whose level sits on the gate."""
+    for cells whose level sits on the gate.  With `x` given, cells fed by a point that sits on
+    a deposit rounding boundary (boundary_cells) are exempt, at most 1e-4 of the image."""
     idx_o = orc.postpass(grid_o, prm)
     E = orc.shaped_energy(grid_o, prm)
     with np.errstate(divide="ignore"):
@@ -121,6 +148,11 @@ def check_index(idx_gpu, grid_o: np.ndarray, prm: orc.Params):
     on_gate = np.abs(db - prm.noise_gate_db) < 1e-3
     d = np.abs(idx_gpu.astype(np.int32) - idx_o.astype(np.int32))
     d = np.where(on_gate, 0, d)
+    if x is not None and d.max() > 1:
+        amb = boundary_cells(x, prm)
+        excused = (d > 1) & amb
+        assert excused.mean() <= 1e-4, f"{excused.mean()} of cells moved across a deposit rounding boundary"
+        d = np.where(amb, 0, d)
     assert d.max() <= 1, f"colour index differs by {d.max()}"
     frac = float((d > 0).mean())
     assert frac <= 1e-3, f"{frac} of cells off by one"

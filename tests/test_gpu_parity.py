@@ -126,7 +126,7 @@ def test_grid_and_index_vs_oracle(emspec, n_fft, hop):
     prm = orc.Params(n_fft=n_fft, hop=hop)
     g, idx = run_grid(emspec, x, prm)
     err, grid_o, _ = check_grid(g, x, prm)
-    check_index(idx, grid_o, prm)
+    check_index(idx, grid_o, prm, x)
     # energy conservation: the grid holds exactly the kept point energy
     dt, dk, e = run_points(emspec, x, prm)
     assert abs(g.sum(dtype=np.float64) - e.sum(dtype=np.float64)) <= 1e-5 * e.sum(dtype=np.float64)
@@ -397,6 +397,38 @@ def test_tuned_kernel_odd_hops(emspec, hop):
     x = orc.synth_signal(SR // 2, SR, seed=18)
     prm = orc.Params(n_fft=4096, hop=hop)
     check_points(run_points(emspec, x, prm), x, prm)
+
+
+@pytest.mark.parametrize("n_fft,hop", [(1024, 100), (1024, 257), (1024, 1024), (2048, 96), (2048, 515), (2048, 1400)])
+def test_tuned_family_hops(emspec, n_fft, hop):
+    """The radix-R x 16 x 16 kernels (n_fft = 1024, 2048): hops that are multiples of 4 (16-byte
+    tile copies), odd (4-byte copies) and so large that a tile holds fewer frames than workers."""
+    x = orc.synth_signal(SR // 2, SR, seed=19)
+    prm = orc.Params(n_fft=n_fft, hop=hop)
+    check_points(run_points(emspec, x, prm), x, prm)
+
+
+@pytest.mark.parametrize("n_fft", [1024, 2048, 4096])
+def test_tuned_family_matches_generic_and_unaligned_channels(emspec, n_fft, monkeypatch):
+    """Stereo with an odd sample count: channel 1 starts off a 16-byte boundary, so one channel
+    takes the 16-byte and the other the 4-byte tile copies.  Both must give the oracle's points,
+    and the deterministic grid must be bit-identical to the generic kernel's decisions up to
+    fp32 rounding of the energies (same cells: checked through the u8 image within +-1)."""
+    S = SR // 2 + 1
+    x = np.stack([orc.synth_signal(S, SR, seed=20), orc.synth_signal(S, SR, seed=21)])
+    prm = orc.Params(n_fft=n_fft, hop=n_fft // 8)
+    eng = emspec.Engine(n_fft=n_fft, hop=prm.hop, channels=2, flags=prm.flags | emspec.FLAG_SYNC)
+    pts = eng.process_points(torch.from_numpy(x).cuda())
+    for ch in range(2):
+        check_points(tuple(p[ch].cpu().numpy() for p in pts), x[ch], prm)
+    _, idx = eng.process_grid(torch.from_numpy(x).cuda(), want_grid=False)
+    eng.close()
+    monkeypatch.setenv("EMS_FORCE_GENERIC", "1")
+    eng = emspec.Engine(n_fft=n_fft, hop=prm.hop, channels=2, flags=prm.flags | emspec.FLAG_SYNC)
+    _, idx_g = eng.process_grid(torch.from_numpy(x).cuda(), want_grid=False)
+    eng.close()
+    a, b = idx.cpu().numpy().astype(np.int16), idx_g.cpu().numpy().astype(np.int16)
+    assert np.mean(np.abs(a - b) > 1) < 1e-3
 
 
 def test_host_chunking_with_tuned_kernel(emspec, monkeypatch):
