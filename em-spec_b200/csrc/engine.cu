@@ -215,6 +215,25 @@ static ems_status launch_r16(ems_handle* h, const StftArgs& a) {
     return EMS_OK;
 }
 
+// Tuned kernels for n_fft = 4096 R0 (R0 = 2, 4): frames read straight from global memory.
+template <int R0>
+static ems_status launch_r16_large(ems_handle* h, const StftArgs& a) {
+    using C = r16::CfgL<R0>;
+    void (*kern)(const StftArgs) =
+        a.mode == kStorePoints ? r16::stft_reassign_r16_large<R0, kStorePoints>
+        : a.mode == kDepositU64 ? r16::stft_reassign_r16_large<R0, kDepositU64>
+                                : r16::stft_reassign_r16_large<R0, kDepositF32>;
+    EMS_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+    const long long total = (a.f_end - a.f_begin) * a.channels;
+    long long grid = h->sm_count;
+    if (grid > total) grid = total;
+    if (grid < 1) return EMS_OK;
+    kern<<<(unsigned)grid, C::kThreads, C::kSmemBytes, h->stream>>>(a);
+    ++h->launches;
+    EMS_CUDA(h, cudaGetLastError());
+    return EMS_OK;
+}
+
 static ems_status launch_stft(ems_handle* h, const StftArgs& a) {
     if (!h->force_generic) {
         ems_status s = EMS_ERR_UNSUPPORTED;
@@ -222,6 +241,8 @@ static ems_status launch_stft(ems_handle* h, const StftArgs& a) {
             case 1024: s = launch_r16<4>(h, a); break;
             case 2048: s = launch_r16<8>(h, a); break;
             case 4096: s = launch_r16<16>(h, a); break;
+            case 8192: s = launch_r16_large<2>(h, a); break;
+            case 16384: s = launch_r16_large<4>(h, a); break;
             default: break;
         }
         if (s != EMS_ERR_UNSUPPORTED) return s;

@@ -281,13 +281,161 @@ __device__ __forceinline__ void bin_emit(const StftArgs& a, const FrameCtx& fc, 
 // conj(a)
 __device__ __forceinline__ float2 cj(float2 a) { return make_float2(a.x, -a.y); }
 
+// ---- the pieces of one frame, shared by the tiled kernel (n_fft <= 4096) and the large one
+
+// Roles of one thread inside its worker (frame-independent).
+struct Geom {
+    int p;              // role index, 0 .. kWT - 1
+    int tA, tB;         // output residues of the last pass: bins tA + kRes c and tB + kRes c
+    int zA, zB;         // where their 16 inputs start in the Z buffer
+    int i1, q2;         // pass-2 butterflies (i1, q2) and (i1, q2 + 8)
+    int ls, ks;         // self-paired bins: lane ls <= 16 of the first warp finishes bin ks
+    float tAf, tBf;
+    bool owner;         // thread 0's residues pair with themselves
+};
+template <int R, int kSI, int kS16>
+__device__ __forceinline__ Geom make_geom(int p) {
+    constexpr int kRes = 16 * R;
+    Geom g;
+    g.p = p;
+    g.tA = p; g.tB = p ? kRes - p : kRes / 2;
+    // residue t = i + R i' holds the outputs of row i' of sub-FFT i
+    g.zA = kSI * (g.tA & (R - 1)) + kS16 * (g.tA / R);
+    g.zB = kSI * (g.tB & (R - 1)) + kS16 * (g.tB / R);
+    g.i1 = p & (R - 1); g.q2 = p / R;
+    g.owner = p != 0;
+    g.tAf = (float)g.tA; g.tBf = (float)g.tB;
+    // residues 0 and 8R: lane l <= 8 takes bin kRes l, lanes 9..16 bins kRes/2 + kRes (l - 9)
+    g.ls = min(p, 16);
+    g.ks = g.ls <= 8 ? kRes * g.ls : kRes / 2 + kRes * (g.ls - 9);
+    return g;
+}
+
+// Twiddle the outputs of a radix-RR butterfly by W^{b i} and store output i at zo[STRIDE i].
+// log2 RR exact values come from the table rows tab[l][b] = W^{b 2^l}, the others are products
+// (<= 3 multiplies deep): two fewer shared-memory wavefronts per product.
+template <int RR, int STRIDE>
+__device__ __forceinline__ void twiddle_store_rows(float2 (&v)[RR], const float2* tab, int b, float2* zo) {
+    constexpr int kLog = RR == 4 ? 2 : RR == 8 ? 3 : 4;
+    float2 tw[RR];
+    static_for<kLog>([&](auto lc) {
+        constexpr int l = decltype(lc)::value;
+        tw[1 << l] = tab[l * 256 + b];
+    });
+    static_for<RR>([&](auto ic) {
+        constexpr int i = decltype(ic)::value;
+        constexpr int hb = i >= 8 ? 8 : i >= 4 ? 4 : i >= 2 ? 2 : 1;     // highest set bit
+        if constexpr (i > hb && i >= 3) tw[i] = cmul2(tw[i - hb], tw[hb]);
+    });
+    zo[0] = v[oR<RR>(0)];
+#pragma unroll
+    for (int i = 1; i < RR; ++i) zo[STRIDE * i] = cmul2(v[oR<RR>(i)], tw[i]);
+}
+
+// Pass 2: sub-FFTs of length 256, butterflies (i1, q2), (i1, q2 + 8), software-pipelined by
+// hand: the second butterfly's loads fly while the first computes.
+template <int kSI, int kS16>
+__device__ __forceinline__ void pass2(float2* Zb, const float2* T2, const Geom& g) {
+    float2* bz0 = Zb + kSI * g.i1 + g.q2;
+    float2* bz1 = bz0 + 8;
+    float2 v0[16], v1[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v0[j] = bz0[kS16 * j];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v1[j] = bz1[kS16 * j];
+    // twiddles W_256^{p2 i}: the 16 of a butterfly are contiguous, two per 128-bit load
+    // (the whole warp reads two addresses: one wavefront per load)
+    auto twiddle_store = [&](float2 (&v)[16], float2* base, int p2) {
+        const float4* t4 = reinterpret_cast<const float4*>(T2 + 16 * p2);
+#pragma unroll
+        for (int h = 0; h < 8; ++h) {
+            const float4 t = t4[h];
+            if (h == 0) base[0] = v[o16(0)];
+            else base[kS16 * (2 * h)] = cmul2(v[o16(2 * h)], make_float2(t.x, t.y));
+            base[kS16 * (2 * h + 1)] = cmul2(v[o16(2 * h + 1)], make_float2(t.z, t.w));
+        }
+    };
+    dft16(v0);
+    twiddle_store(v0, bz0, g.q2);
+    dft16(v1);
+    twiddle_store(v1, bz1, g.q2 + 8);
+}
+
+// Pass 3: residues tA, tB; untangle in registers; 2 X to shared memory (Xs[k + 1]).
+//   2 X[k] = Z[k] + conj Z[N-k],  2 X_th'[k] = (Z[k] - conj Z[N-k]) / j
+template <int R>
+__device__ __forceinline__ void pass3_untangle(const float2* Zb, float2* Xs, float2* Sc, const Geom& g,
+                                               float2 (&xa)[8], float2 (&xb)[8], float2 (&ta)[8], float2 (&tb)[8]) {
+    constexpr int kRes = 16 * R, N = 256 * R;
+    const int tA = g.tA, tB = g.tB;
+    float2 za[16], zb[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) { za[j] = Zb[g.zA + j]; zb[j] = Zb[g.zB + j]; }
+    dft16(za); dft16(zb);
+    if (g.p != 0) {
+        static_for<8>([&](auto cc) {
+            constexpr int c = decltype(cc)::value;
+            const float2 za_c = za[o16(c)], zb_n = cj(zb[o16(15 - c)]);
+            const float2 zb_c = zb[o16(c)], za_n = cj(za[o16(15 - c)]);
+            xa[c] = za_c + zb_n; ta[c] = mulmj(za_c - zb_n);
+            xb[c] = zb_c + za_n; tb[c] = mulmj(zb_c - za_n);
+            Xs[1 + tA + kRes * c] = xa[c];
+            Xs[1 + tB + kRes * c] = xb[c];
+        });
+        if (g.p == 1) {      // Hermitian mirrors: X[-1] = conj X[1], X[N/2+1] = conj X[N/2-1]
+            Xs[0] = cj(xa[0]);
+            Xs[N / 2 + 2] = cj(xb[7]);
+        }
+    } else {
+        // residues 0 (bins kRes c, c = 0..8) and kRes/2 (bins kRes/2 + kRes c) pair with themselves
+        static_for<9>([&](auto cc) {
+            constexpr int c = decltype(cc)::value;
+            const float2 z = za[o16(c & 15)], zn = cj(za[o16((16 - c) & 15)]);
+            Xs[1 + kRes * c] = z + zn;
+            Sc[c] = mulmj(z - zn);
+        });
+        static_for<8>([&](auto cc) {
+            constexpr int c = decltype(cc)::value;
+            const float2 z = zb[o16(c)], zn = cj(zb[o16(15 - c)]);
+            Xs[1 + kRes / 2 + kRes * c] = z + zn;
+            Sc[9 + c] = mulmj(z - zn);
+            xa[c] = z; xb[c] = z; ta[c] = z; tb[c] = z;        // placeholders, never stored
+        });
+    }
+}
+
+// Epilogue of frame f of channel ch on the thread's own bins (after the barrier that makes X visible).
+template <int R, int MODE>
+__device__ __forceinline__ void epilogue(const StftArgs& a, int ch, long long f, const float2* Xs, const float2* Sc,
+                                         const Geom& g, const float2 (&xa)[8], const float2 (&xb)[8],
+                                         const float2 (&ta)[8], const float2 (&tb)[8]) {
+    constexpr int kRes = 16 * R, N = 256 * R, B = N / 2 + 1;
+    FrameCtx fc;
+    fc.lo = (float)max(-f, -1048576LL);
+    fc.hi = (float)min(a.F - 1 - f, 1048576LL);
+    fc.f = f; fc.ch = ch;
+    const long long row0 = ((a.ring ? 0 : (long long)ch * a.F) + f) * B;
+    fc.pd = a.dt_cols + row0; fc.pk = a.dk_bins + row0; fc.pe = a.energy + row0;
+    const int tA = g.tA, tB = g.tB;
+    static_for<8>([&](auto cc) {
+        constexpr int c = decltype(cc)::value;
+        bin_emit<N, MODE>(a, fc, g.owner, tA + kRes * c, g.tAf + (float)(kRes * c), xa[c],
+                          Xs[tA + kRes * c], Xs[tA + kRes * c + 2], ta[c]);
+        bin_emit<N, MODE>(a, fc, g.owner, tB + kRes * c, g.tBf + (float)(kRes * c), xb[c],
+                          Xs[tB + kRes * c], Xs[tB + kRes * c + 2], tb[c]);
+    });
+    if (g.p < 32)   // the 17 self-paired bins, one per lane (the rest of the warp tags along)
+        bin_emit<N, MODE>(a, fc, g.p <= 16, g.ks, (float)g.ks, Xs[g.ks + 1], Xs[g.ks], Xs[g.ks + 2], Sc[g.ls]);
+}
+
+// ---------------------------------------------------------------- n_fft = 1024, 2048, 4096
 template <int R, int MODE>
 __global__ void __launch_bounds__(kThreads, 1)
 stft_reassign_r16(const StftArgs a_in, const int tile_T) {
     using C = Cfg<R>;
-    constexpr int N = C::N, kWT = C::kWT, kWorkers = C::kWorkers, kRes = C::kRes, kZBuf = C::kZBuf,
+    constexpr int N = C::N, kWT = C::kWT, kWorkers = C::kWorkers, kZBuf = C::kZBuf,
                   kXBuf = C::kXBuf, kZtab = C::kZtab, kTileFloats = C::kTileFloats, kSI = C::kSI,
-                  kS16 = C::kS16, kU = C::kU, kLogR = C::kLogR;
+                  kS16 = C::kS16, kU = C::kU;
     StftArgs a = a_in;
     if (!stream_decode(a)) return;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -318,22 +466,13 @@ stft_reassign_r16(const StftArgs a_in, const int tile_T) {
     for (int u = 0; u < kU; ++u)
 #pragma unroll
         for (int j = 0; j < R; ++j) thw[u][j] = __ldg(&a.thw[p + kWT * u + 256 * j]);
-    const int tA = p, tB = p ? kRes - p : kRes / 2;        // output residues of this thread
-    // residue t = i + R i' holds the outputs of row i' of sub-FFT i
-    const int zA = kSI * (tA & (R - 1)) + kS16 * (tA / R), zB = kSI * (tB & (R - 1)) + kS16 * (tB / R);
-    const int i1 = p & (R - 1), q2 = p / R;                // pass-2 butterfly coordinates
-    const bool owner = p != 0;                              // thread 0's residues pair with themselves
-    const float tAf = (float)tA, tBf = (float)tB;
-    // self-paired bins (residues 0 and 8R): lane l <= 8 takes bin kRes l, lanes 9..16 bins kRes/2 + kRes (l - 9)
-    const int ls = min(p, 16);
-    const int ks = ls <= 8 ? kRes * ls : kRes / 2 + kRes * (ls - 9);
+    const Geom g = make_geom<R, kSI, kS16>(p);
 
     const long long per_ch = a.f_end - a.f_begin;
     const long long tiles_per_ch = (per_ch + tile_T - 1) / tile_T;
     const long long n_tiles = tiles_per_ch * a.channels;
-    constexpr int B = N / 2 + 1;
 
-    // Tiles are double-buffered and handed over without any CTA-wide barrier, so the three
+    // Tiles are double-buffered and handed over without any CTA-wide barrier, so the
     // workers drift apart and their FP-heavy and shared-memory-heavy phases interleave (in
     // lockstep they collide: measured +13 %).  Protocol per buffer b:
     //   * a worker that has read its last sample of the tile in b bumps done[b]; the last one
@@ -410,7 +549,6 @@ stft_reassign_r16(const StftArgs a_in, const int tile_T) {
         int ch, nf; long long f0;
         tile_geom(tl, ch, f0, nf);
         const float* tile = tile0 + buf * kTileFloats;
-        const long long chan_off = a.ring ? 0 : (long long)ch * a.F;
         if (w >= nf) {                      // no frame for this worker in a short tile: just release it
             if (p == 0) release_tile(buf);
             worker_bar<kWT>(w);
@@ -435,112 +573,138 @@ stft_reassign_r16(const StftArgs a_in, const int tile_T) {
                     v[j] = make_float2(x, x * thw[u][j]);
                 }
                 dftR(v);
-                // twiddles W^{b i}: log2 R exact values from the table, the others as products
-                // (<= 3 multiplies deep): two fewer shared-memory wavefronts per product
-                float2 tw[R];
-                static_for<kLogR>([&](auto lc) {
-                    constexpr int l = decltype(lc)::value;
-                    tw[1 << l] = Ztab[l * 256 + b];
-                });
-                static_for<R>([&](auto ic) {
-                    constexpr int i = decltype(ic)::value;
-                    constexpr int hb = i >= 8 ? 8 : i >= 4 ? 4 : i >= 2 ? 2 : 1;     // highest set bit
-                    if constexpr (i > hb && hb > 0 && i >= 3) tw[i] = cmul2(tw[i - hb], tw[hb]);
-                });
-                float2* zo = Zb + b + (b >> 4) * (kS16 - 16);
-                zo[0] = v[oR<R>(0)];
-#pragma unroll
-                for (int i = 1; i < R; ++i) zo[kSI * i] = cmul2(v[oR<R>(i)], tw[i]);
+                twiddle_store_rows<R, kSI>(v, Ztab, b, Zb + b + (b >> 4) * (kS16 - 16));
             });
             worker_bar<kWT>(w);
             if (last_frame && p == 0) release_tile(buf);   // every sample of the tile has been read
 
-            // ================= pass 2: sub-FFTs of length 256, butterflies (i1, q2), (i1, q2 + 8),
-            // software-pipelined by hand: the second butterfly's loads fly while the first computes
-            {
-                float2* bz0 = Zb + kSI * i1 + q2;
-                float2* bz1 = bz0 + 8;
-                float2 v0[16], v1[16];
-#pragma unroll
-                for (int j = 0; j < 16; ++j) v0[j] = bz0[kS16 * j];
-#pragma unroll
-                for (int j = 0; j < 16; ++j) v1[j] = bz1[kS16 * j];
-                // twiddles W_256^{p2 i}: the 16 of a butterfly are contiguous, two per 128-bit load
-                // (the whole warp reads two addresses: one wavefront per load)
-                auto twiddle_store = [&](float2 (&v)[16], float2* base, int p2) {
-                    const float4* t4 = reinterpret_cast<const float4*>(T2 + 16 * p2);
-#pragma unroll
-                    for (int h = 0; h < 8; ++h) {
-                        const float4 t = t4[h];
-                        if (h == 0) base[0] = v[o16(0)];
-                        else base[kS16 * (2 * h)] = cmul2(v[o16(2 * h)], make_float2(t.x, t.y));
-                        base[kS16 * (2 * h + 1)] = cmul2(v[o16(2 * h + 1)], make_float2(t.z, t.w));
-                    }
-                };
-                dft16(v0);
-                twiddle_store(v0, bz0, q2);
-                dft16(v1);
-                twiddle_store(v1, bz1, q2 + 8);
-            }
+            pass2<kSI, kS16>(Zb, T2, g);
             worker_bar<kWT>(w);
             if (last_frame && refill[w]) refill_tile(buf, ti + 2);
 
-            // ================= pass 3: residues tA, tB; untangle; X to shared memory
-            float2 za[16], zb[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) { za[j] = Zb[zA + j]; zb[j] = Zb[zB + j]; }
-            dft16(za); dft16(zb);
-            // 2 X[k] = Z[k] + conj Z[N-k],  2 X_th'[k] = (Z[k] - conj Z[N-k]) / j
             float2 xa[8], xb[8], ta[8], tb[8];     // bins tA + kRes c and tB + kRes c, c = 0..7
-            if (p != 0) {
-                static_for<8>([&](auto cc) {
-                    constexpr int c = decltype(cc)::value;
-                    const float2 za_c = za[o16(c)], zb_n = cj(zb[o16(15 - c)]);
-                    const float2 zb_c = zb[o16(c)], za_n = cj(za[o16(15 - c)]);
-                    xa[c] = za_c + zb_n; ta[c] = mulmj(za_c - zb_n);
-                    xb[c] = zb_c + za_n; tb[c] = mulmj(zb_c - za_n);
-                    Xs[1 + tA + kRes * c] = xa[c];
-                    Xs[1 + tB + kRes * c] = xb[c];
-                });
-                if (p == 1) {      // Hermitian mirrors: X[-1] = conj X[1], X[N/2+1] = conj X[N/2-1]
-                    Xs[0] = cj(xa[0]);
-                    Xs[N / 2 + 2] = cj(xb[7]);
-                }
-            } else {
-                // residues 0 (bins kRes c, c = 0..8) and kRes/2 (bins kRes/2 + kRes c) pair with themselves
-                static_for<9>([&](auto cc) {
-                    constexpr int c = decltype(cc)::value;
-                    const float2 z = za[o16(c & 15)], zn = cj(za[o16((16 - c) & 15)]);
-                    Xs[1 + kRes * c] = z + zn;
-                    Sc[c] = mulmj(z - zn);
-                });
-                static_for<8>([&](auto cc) {
-                    constexpr int c = decltype(cc)::value;
-                    const float2 z = zb[o16(c)], zn = cj(zb[o16(15 - c)]);
-                    Xs[1 + kRes / 2 + kRes * c] = z + zn;
-                    Sc[9 + c] = mulmj(z - zn);
-                    xa[c] = z; xb[c] = z; ta[c] = z; tb[c] = z;        // placeholders, never stored
-                });
-            }
+            pass3_untangle<R>(Zb, Xs, Sc, g, xa, xb, ta, tb);
             worker_bar<kWT>(w);      // X visible; the Z buffer is free for the next frame's pass 1
 
-            // ================= epilogue on the thread's own bins
-            FrameCtx fc;
-            fc.lo = (float)max(-f, -1048576LL);
-            fc.hi = (float)min(a.F - 1 - f, 1048576LL);
-            fc.f = f; fc.ch = ch;
-            const long long row0 = (chan_off + f) * B;
-            fc.pd = a.dt_cols + row0; fc.pk = a.dk_bins + row0; fc.pe = a.energy + row0;
-            static_for<8>([&](auto cc) {
-                constexpr int c = decltype(cc)::value;
-                bin_emit<N, MODE>(a, fc, owner, tA + kRes * c, tAf + (float)(kRes * c), xa[c],
-                                  Xs[tA + kRes * c], Xs[tA + kRes * c + 2], ta[c]);
-                bin_emit<N, MODE>(a, fc, owner, tB + kRes * c, tBf + (float)(kRes * c), xb[c],
-                                  Xs[tB + kRes * c], Xs[tB + kRes * c + 2], tb[c]);
-            });
-            if (p < 32)   // the 17 self-paired bins, one per lane (the rest of the warp tags along)
-                bin_emit<N, MODE>(a, fc, p <= 16, ks, (float)ks, Xs[ks + 1], Xs[ks], Xs[ks + 2], Sc[ls]);
+            epilogue<R, MODE>(a, ch, f, Xs, Sc, g, xa, xb, ta, tb);
         }
+    }
+}
+
+// ---------------------------------------------------------------- n_fft = 8192, 16384
+// Same radix-16 passes and epilogue, but pass 1 (radix R = 16 R0) is split in two — a radix-R0
+// pass over samples 4096 apart, read straight from global memory / L2 (with hop = n_fft/4 and
+// frames this long a shared-memory tile has no room and little reuse to offer), then a radix-16
+// pass — so a thread never holds more than 16 values.  4 worker barriers per frame.
+// One CTA per SM: 2 workers x 256 threads (8192) or 1 x 512 (16384); frames are strided over
+// CTAs first, then workers, so short launches (streaming: one frame per channel) spread over SMs.
+template <int R0_>
+struct CfgL {
+    static_assert(R0_ == 2 || R0_ == 4, "radix of the pre-pass");
+    static constexpr int R0 = R0_;
+    static constexpr int R = 16 * R0;
+    static constexpr int N = 256 * R;
+    static constexpr int kWT = 8 * R;
+    static constexpr int kThreads = 512;
+    static constexpr int kWorkers = kThreads / kWT;
+    static constexpr int kUA = 32 / R0;             // radix-R0 butterflies per thread
+    static constexpr int kSI = 257, kS16 = 16;
+    static constexpr int kZBuf = R * kSI;
+    static constexpr int kXBuf = N / 2 + 4;
+    static constexpr int kZtab = 4 * 256;           // W_4096^{b i}, i = 1, 2, 4, 8
+    static constexpr int kSmemBytes = (kWorkers * (kZBuf + kXBuf + kScratch) + kZtab + kT2) * 8;
+    static_assert(kSmemBytes <= kMaxSmem, "shared memory");
+};
+
+template <int R0, int MODE>
+__global__ void __launch_bounds__(CfgL<R0>::kThreads, 1)
+stft_reassign_r16_large(const StftArgs a_in) {
+    using C = CfgL<R0>;
+    constexpr int R = C::R, kWT = C::kWT, kWorkers = C::kWorkers, kZBuf = C::kZBuf, kXBuf = C::kXBuf,
+                  kZtab = C::kZtab, kSI = C::kSI, kS16 = C::kS16, kUA = C::kUA, kThreads = C::kThreads;
+    StftArgs a = a_in;
+    if (!stream_decode(a)) return;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* sm = reinterpret_cast<float2*>(smem_raw);
+    float2* Ztab = sm;                         // [4][256]: W_4096^{b 2^l}
+    float2* T2 = Ztab + kZtab;                 // [16][16]
+    float2* wbuf = T2 + kT2;
+
+    const int tid = threadIdx.x;
+    const int w = tid / kWT;
+    const int p = (tid + 32 * w) & (kWT - 1);
+    float2* Zb = wbuf + w * (kZBuf + kXBuf + kScratch);
+    float2* Xs = Zb + kZBuf;
+    float2* Sc = Xs + kXBuf;
+
+    for (int e = tid; e < kZtab; e += kThreads) { const int i = 1 << (e / 256), b = e % 256; Ztab[e] = __ldg(&a.tw[R0 * b * i]); }
+    for (int e = tid; e < kT2; e += kThreads) { const int q = e / 16, i = e % 16; T2[e] = __ldg(&a.tw[R * q * i]); }
+    __syncthreads();
+    const Geom g = make_geom<R, kSI, kS16>(p);
+
+    const long long per_ch = a.f_end - a.f_begin;
+    const long long total = per_ch * a.channels;
+    for (long long it = blockIdx.x + (long long)gridDim.x * w; it < total; it += (long long)gridDim.x * kWorkers) {
+        const int ch = (int)(it / per_ch);
+        const long long f = a.f_begin + (it - (long long)ch * per_ch);
+        const float* xs = a.pcm + (long long)ch * a.S + f * a.hop + a.samp_off;
+
+        // ================= pass A: radix-R0 butterflies b = p + kWT u over n = b + 4096 j0,
+        // z[n] = x[n] (1 + j th'[n]); output i0 of butterfly b = b1 + 256 j1 goes to the slot
+        // pass B reads it from: Zb[kSI (i0 + R0 j1) + b1]
+        {
+            float xr[kUA][R0], tr[kUA][R0];
+#pragma unroll
+            for (int u = 0; u < kUA; ++u)
+#pragma unroll
+                for (int j = 0; j < R0; ++j) {
+                    xr[u][j] = __ldg(xs + p + kWT * u + 4096 * j);
+                    tr[u][j] = __ldg(a.thw + p + kWT * u + 4096 * j);
+                }
+            static_for<kUA>([&](auto uc) {
+                constexpr int u = decltype(uc)::value;
+                const int b = p + kWT * u;
+                float2 v[R0];
+#pragma unroll
+                for (int j = 0; j < R0; ++j) v[j] = make_float2(xr[u][j], xr[u][j] * tr[u][j]);
+                float2* zo = Zb + kSI * (R0 * (b >> 8)) + (b & 255);
+                const float2 w1 = __ldg(&a.tw[b]);                 // W_N^b
+                if constexpr (R0 == 2) {
+                    zo[0] = v[0] + v[1];
+                    zo[kSI] = cmul2(v[0] - v[1], w1);
+                } else {
+                    dft4(v[0], v[1], v[2], v[3]);
+                    const float2 w2 = cmul2(w1, w1);
+                    zo[0] = v[0];
+                    zo[kSI] = cmul2(v[1], w1);
+                    zo[2 * kSI] = cmul2(v[2], w2);
+                    zo[3 * kSI] = cmul2(v[3], cmul2(w1, w2));
+                }
+            });
+        }
+        worker_bar<kWT>(w);
+
+        // ================= pass B: R0 x 256 radix-16 butterflies (i0, b1) over j1, twiddle W_4096^{b1 i1}
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int e = p + kWT * u, b1 = e & 255, i0 = e >> 8;
+            float2* zb = Zb + kSI * i0 + b1;
+            float2 v[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = zb[kSI * R0 * j];
+            dft16(v);
+            twiddle_store_rows<16, kSI * R0>(v, Ztab, b1, zb);
+        }
+        worker_bar<kWT>(w);
+
+        pass2<kSI, kS16>(Zb, T2, g);
+        worker_bar<kWT>(w);
+
+        float2 xa[8], xb[8], ta[8], tb[8];
+        pass3_untangle<R>(Zb, Xs, Sc, g, xa, xb, ta, tb);
+        worker_bar<kWT>(w);
+
+        epilogue<R, MODE>(a, ch, f, Xs, Sc, g, xa, xb, ta, tb);
     }
 }
 

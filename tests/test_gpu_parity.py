@@ -399,22 +399,23 @@ def test_tuned_kernel_odd_hops(emspec, hop):
     check_points(run_points(emspec, x, prm), x, prm)
 
 
-@pytest.mark.parametrize("n_fft,hop", [(1024, 100), (1024, 257), (1024, 1024), (2048, 96), (2048, 515), (2048, 1400)])
+@pytest.mark.parametrize("n_fft,hop", [(1024, 100), (1024, 257), (1024, 1024), (2048, 96), (2048, 515), (2048, 1400),
+                                       (8192, 333), (8192, 8192), (16384, 1000)])
 def test_tuned_family_hops(emspec, n_fft, hop):
     """The radix-R x 16 x 16 kernels (n_fft = 1024, 2048): hops that are multiples of 4 (16-byte
     tile copies), odd (4-byte copies) and so large that a tile holds fewer frames than workers."""
-    x = orc.synth_signal(SR // 2, SR, seed=19)
+    x = orc.synth_signal(max(SR // 2, 3 * n_fft), SR, seed=19)
     prm = orc.Params(n_fft=n_fft, hop=hop)
     check_points(run_points(emspec, x, prm), x, prm)
 
 
-@pytest.mark.parametrize("n_fft", [1024, 2048, 4096])
+@pytest.mark.parametrize("n_fft", [1024, 2048, 4096, 8192, 16384])
 def test_tuned_family_matches_generic_and_unaligned_channels(emspec, n_fft, monkeypatch):
     """Stereo with an odd sample count: channel 1 starts off a 16-byte boundary, so one channel
     takes the 16-byte and the other the 4-byte tile copies.  Both must give the oracle's points,
     and the deterministic grid must be bit-identical to the generic kernel's decisions up to
     fp32 rounding of the energies (same cells: checked through the u8 image within +-1)."""
-    S = SR // 2 + 1
+    S = max(SR // 2, 4 * n_fft) + 1
     x = np.stack([orc.synth_signal(S, SR, seed=20), orc.synth_signal(S, SR, seed=21)])
     prm = orc.Params(n_fft=n_fft, hop=n_fft // 8)
     eng = emspec.Engine(n_fft=n_fft, hop=prm.hop, channels=2, flags=prm.flags | emspec.FLAG_SYNC)
