@@ -476,9 +476,8 @@ stft_reassign_r16(const StftArgs a_in, const int tile_T) {
     // workers drift apart and their FP-heavy and shared-memory-heavy phases interleave (in
     // lockstep they collide: measured +13 %).  Protocol per buffer b:
     //   * a worker that has read its last sample of the tile in b bumps done[b]; the last one
-    //     to do so refills b with the tile after next (cp.async from its own threads, 16-byte
-    //     copies when the tile starts on a 16-byte boundary and hop is a multiple of 4, else
-    //     4-byte ones) and the copies arrive on the mbarrier full[b];
+    //     to do so refills b with the tile after next (cp.async from its own threads, 4-byte
+    //     copies, or 16-byte ones for large aligned hops) and the copies arrive on the mbarrier full[b];
     //   * a worker waits on full[b] before it reads a refilled buffer.
     unsigned long long* full = reinterpret_cast<unsigned long long*>(tile0 + 2 * kTileFloats);   // [2]
     unsigned* done = reinterpret_cast<unsigned*>(full + 2);                                     // [2]
@@ -495,7 +494,10 @@ stft_reassign_r16(const StftArgs a_in, const int tile_T) {
         const int n_samp = (nf - 1) * a.hop + N;
         const float* src = a.pcm + (long long)ch * a.S + f0 * a.hop + a.samp_off;
         const unsigned d0 = (unsigned)__cvta_generic_to_shared(dst);
-        if ((((unsigned long long)src | (unsigned long long)(unsigned)a.hop * 4ull) & 15ull) == 0) {
+        // 16-byte copies pay when tiles turn over quickly (hop >= N/8: +7 % at 4096/1024); with a
+        // small hop the copy volume is negligible and the slower 4-byte loop keeps the workers
+        // out of phase (4096/128: 92.2 M frames/s against 87.4 M with 16-byte copies, measured)
+        if (a.hop * 8 >= N && (((unsigned long long)src | (unsigned long long)(unsigned)a.hop * 4ull) & 15ull) == 0) {
             for (int s = 4 * t0; s < n_samp; s += 4 * nth)
                 asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d0 + 4u * s), "l"(src + s) : "memory");
         } else {

@@ -11,7 +11,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libemspec.so")
+# EMS_LIB_PATH: A/B runs of two builds of the same C-ABI (tools/ab_kernel.py); never a CPU path
+LIB_PATH = os.environ.get("EMS_LIB_PATH") or os.path.join(_HERE, "libemspec.so")
 
 FLAG_REASSIGN = 1
 FLAG_DETERMINISTIC = 2
