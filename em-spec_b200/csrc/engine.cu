@@ -197,7 +197,8 @@ static ems_status launch_r16(ems_handle* h, const StftArgs& a) {
     // short inputs: smaller tiles so that every SM gets one
     const long long per_ch = a.f_end - a.f_begin;
     const long long want = (per_ch * a.channels + h->sm_count - 1) / h->sm_count;
-    const long long t = ((want + C::kWorkers - 1) / C::kWorkers) * C::kWorkers;
+    constexpr int kPer = C::kWorkers * C::kG;          // frames in flight per CTA
+    const long long t = ((want + kPer - 1) / kPer) * kPer;
     if (t < tile_T) tile_T = (int)std::max<long long>(t, 1);
     const size_t smem = (size_t)C::kFixedBytes + 2 * (size_t)C::kTileFloats * sizeof(float) + r16::kSyncBytes;
     void (*kern)(const StftArgs, const int) =
@@ -238,6 +239,8 @@ static ems_status launch_stft(ems_handle* h, const StftArgs& a) {
     if (!h->force_generic) {
         ems_status s = EMS_ERR_UNSUPPORTED;
         switch (h->prm.n_fft) {
+            case 256: s = launch_r16<1>(h, a); break;
+            case 512: s = launch_r16<2>(h, a); break;
             case 1024: s = launch_r16<4>(h, a); break;
             case 2048: s = launch_r16<8>(h, a); break;
             case 4096: s = launch_r16<16>(h, a); break;

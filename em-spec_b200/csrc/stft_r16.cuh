@@ -1,5 +1,5 @@
 // stft_r16.cuh — tuned fused frame gather + 3-window STFT + reassignment for
-// n_fft = 256 R, R = 4, 8, 16 (1024, 2048, 4096).
+// n_fft = 256 R, R = 1 .. 16 (256 .. 4096); 8192 and 16384 at the end of the file.
 //
 // ONE complex FFT per frame.  Z = FFT_N(x + j*x*th'), th' = th*(2/N): the real part is the
 // *unwindowed* frame, so the untangle gives the rectangular-window spectrum X and X_th'.
@@ -47,12 +47,15 @@ constexpr int kThreads = 384;
 
 template <int R_>
 struct Cfg {
-    static_assert(R_ == 4 || R_ == 8 || R_ == 16, "pass-1 radix");
+    static_assert(R_ == 1 || R_ == 2 || R_ == 4 || R_ == 8 || R_ == 16, "pass-1 radix");
     static constexpr int R = R_;                    // radix of pass 1; passes 2 and 3 are radix 16
-    static constexpr int kLogR = R == 4 ? 2 : R == 8 ? 3 : 4;
+    static constexpr int kLogR = R == 1 ? 0 : R == 2 ? 1 : R == 4 ? 2 : R == 8 ? 3 : 4;
     static constexpr int N = 256 * R;
-    static constexpr int kWT = 8 * R;               // threads per worker
-    static constexpr int kWorkers = kThreads / kWT;
+    static constexpr int kWT = 8 * R;               // threads per frame
+    // a worker is kWT threads, or one warp analysing kG frames side by side when kWT < 32
+    static constexpr int kG = kWT < 32 ? 32 / kWT : 1;
+    static constexpr int kWorkerThreads = kWT * kG;
+    static constexpr int kWorkers = kThreads / kWorkerThreads;
     static constexpr int kU = 32 / R;               // pass-1 butterflies per thread
     static constexpr int kRes = 16 * R;             // output residues of the last pass: k = t + kRes c
     // Z buffer: element b of sub-FFT i sits at kSI i + b + (b >> 4) (kS16 - 16).  With R = 16 the
@@ -60,17 +63,19 @@ struct Cfg {
     // into one half-warp, so every 16 elements get one slot of padding and kSI = 16/R (mod 16).
     static constexpr int kS16 = R >= 16 ? 16 : 17;
     static constexpr int kSI = R >= 16 ? 257 : 272 + 16 / R;
-    static constexpr int kZBuf = R >= 16 ? 4112 : R * kSI;
+    static constexpr int kZBuf = R >= 16 ? 4112 : R * kSI;    // (R = 1: 288 makes the slot size 8 mod 16, so the
+                                                              //  frames of one half-warp sit in different banks)
     static constexpr int kXBuf = N / 2 + 4;         // float2: 2 X[k] at index k + 1, mirrors at 0 and N/2 + 2
     static constexpr int kZtab = kLogR * 256;       // W_N^{b i}, i = 1, 2, 4, .., b < 256 (the other powers are products)
     static constexpr int kTabFloat2 = kZtab + kT2;
-    static constexpr int kFixedBytes = (kWorkers * (kZBuf + kXBuf + kScratch) + kTabFloat2) * 8;
+    static constexpr int kSlot = kZBuf + kXBuf + kScratch;      // per frame in flight: Z, X, scratch
+    static constexpr int kFixedBytes = (kWorkers * kG * kSlot + kTabFloat2) * 8;
     static constexpr int kTileFloats = ((kMaxSmem - kFixedBytes - kSyncBytes) / 8) & ~3;   // per buffer, two buffers
-    static constexpr int kMaxTile = 12 * kWorkers;
+    static constexpr int kMaxTile = 12 * kWorkers * kG;
     // frames per tile: both tile buffers must hold (T-1)*hop + N samples
     __host__ __device__ static constexpr int tile_frames(int hop) {
         int t = (kTileFloats - N) / hop + 1;
-        if (t > kWorkers) t -= t % kWorkers;
+        if (t > kWorkers * kG) t -= t % (kWorkers * kG);
         return t > kMaxTile ? kMaxTile : t;
     }
     __host__ __device__ static constexpr int zpos(int i, int b) { return kSI * i + b + (b >> 4) * (kS16 - 16); }
@@ -173,6 +178,8 @@ __device__ __forceinline__ void dft8(float2 (&a)[8]) {
 
 // radix-R butterfly of pass 1; output i sits in a[oR<R>(i)]
 template <int R> __host__ __device__ constexpr int oR(int i) { return R == 16 ? o16(i) : R == 8 ? o8(i) : i; }
+__device__ __forceinline__ void dftR(float2 (&a)[1]) {}
+__device__ __forceinline__ void dftR(float2 (&a)[2]) { const float2 s = a[0] + a[1], d = a[0] - a[1]; a[0] = s; a[1] = d; }
 __device__ __forceinline__ void dftR(float2 (&a)[16]) { dft16(a); }
 __device__ __forceinline__ void dftR(float2 (&a)[8]) { dft8(a); }
 __device__ __forceinline__ void dftR(float2 (&a)[4]) { dft4(a[0], a[1], a[2], a[3]); }
@@ -180,7 +187,7 @@ __device__ __forceinline__ void dftR(float2 (&a)[4]) { dft4(a[0], a[1], a[2], a[
 // barrier of one worker (a single warp when n_fft = 1024)
 template <int WT>
 __device__ __forceinline__ void worker_bar(int w) {
-    if constexpr (WT == 32) __syncwarp();
+    if constexpr (WT <= 32) __syncwarp();
     else asm volatile("bar.sync %0, %1;" ::"r"(w + 1), "r"(WT) : "memory");
 }
 
@@ -289,7 +296,7 @@ struct Geom {
     int tA, tB;         // output residues of the last pass: bins tA + kRes c and tB + kRes c
     int zA, zB;         // where their 16 inputs start in the Z buffer
     int i1, q2;         // pass-2 butterflies (i1, q2) and (i1, q2 + 8)
-    int ls, ks;         // self-paired bins: lane ls <= 16 of the first warp finishes bin ks
+    int ls, ks;         // self-paired bins: lane ls <= 16 of the first warp finishes bin ks (kWT >= 32)
     float tAf, tBf;
     bool owner;         // thread 0's residues pair with themselves
 };
@@ -316,7 +323,7 @@ __device__ __forceinline__ Geom make_geom(int p) {
 // (<= 3 multiplies deep): two fewer shared-memory wavefronts per product.
 template <int RR, int STRIDE>
 __device__ __forceinline__ void twiddle_store_rows(float2 (&v)[RR], const float2* tab, int b, float2* zo) {
-    constexpr int kLog = RR == 4 ? 2 : RR == 8 ? 3 : 4;
+    constexpr int kLog = RR == 1 ? 0 : RR == 2 ? 1 : RR == 4 ? 2 : RR == 8 ? 3 : 4;
     float2 tw[RR];
     static_for<kLog>([&](auto lc) {
         constexpr int l = decltype(lc)::value;
@@ -405,11 +412,14 @@ __device__ __forceinline__ void pass3_untangle(const float2* Zb, float2* Xs, flo
 }
 
 // Epilogue of frame f of channel ch on the thread's own bins (after the barrier that makes X visible).
+// `active` is false for the lanes of a sub-warp worker whose frame slot is past the end of the tile:
+// they tag along (the warp votes in bin_emit) and emit nothing.
 template <int R, int MODE>
 __device__ __forceinline__ void epilogue(const StftArgs& a, int ch, long long f, const float2* Xs, const float2* Sc,
                                          const Geom& g, const float2 (&xa)[8], const float2 (&xb)[8],
-                                         const float2 (&ta)[8], const float2 (&tb)[8]) {
-    constexpr int kRes = 16 * R, N = 256 * R, B = N / 2 + 1;
+                                         const float2 (&ta)[8], const float2 (&tb)[8], bool active = true) {
+    constexpr int kRes = 16 * R, N = 256 * R, B = N / 2 + 1, kWT = 8 * R;
+    const bool owner = g.owner && active;
     FrameCtx fc;
     fc.lo = (float)max(-f, -1048576LL);
     fc.hi = (float)min(a.F - 1 - f, 1048576LL);
@@ -419,23 +429,33 @@ __device__ __forceinline__ void epilogue(const StftArgs& a, int ch, long long f,
     const int tA = g.tA, tB = g.tB;
     static_for<8>([&](auto cc) {
         constexpr int c = decltype(cc)::value;
-        bin_emit<N, MODE>(a, fc, g.owner, tA + kRes * c, g.tAf + (float)(kRes * c), xa[c],
+        bin_emit<N, MODE>(a, fc, owner, tA + kRes * c, g.tAf + (float)(kRes * c), xa[c],
                           Xs[tA + kRes * c], Xs[tA + kRes * c + 2], ta[c]);
-        bin_emit<N, MODE>(a, fc, g.owner, tB + kRes * c, g.tBf + (float)(kRes * c), xb[c],
+        bin_emit<N, MODE>(a, fc, owner, tB + kRes * c, g.tBf + (float)(kRes * c), xb[c],
                           Xs[tB + kRes * c], Xs[tB + kRes * c + 2], tb[c]);
     });
-    if (g.p < 32)   // the 17 self-paired bins, one per lane (the rest of the warp tags along)
-        bin_emit<N, MODE>(a, fc, g.p <= 16, g.ks, (float)g.ks, Xs[g.ks + 1], Xs[g.ks], Xs[g.ks + 2], Sc[g.ls]);
+    if constexpr (kWT >= 32) {
+        if (g.p < 32)   // the 17 self-paired bins, one per lane (the rest of the warp tags along)
+            bin_emit<N, MODE>(a, fc, g.p <= 16, g.ks, (float)g.ks, Xs[g.ks + 1], Xs[g.ks], Xs[g.ks + 2], Sc[g.ls]);
+    } else {
+        // fewer lanes than self-paired bins: lane p takes bins p, p + kWT, .. of the 17
+#pragma unroll
+        for (int r = 0; r < (17 + kWT - 1) / kWT; ++r) {
+            const int ls = min(g.p + kWT * r, 16);
+            const int ks = ls <= 8 ? kRes * ls : kRes / 2 + kRes * (ls - 9);
+            bin_emit<N, MODE>(a, fc, active && g.p + kWT * r <= 16, ks, (float)ks, Xs[ks + 1], Xs[ks], Xs[ks + 2], Sc[ls]);
+        }
+    }
 }
 
-// ---------------------------------------------------------------- n_fft = 1024, 2048, 4096
+// ---------------------------------------------------------------- n_fft = 256 .. 4096
 template <int R, int MODE>
 __global__ void __launch_bounds__(kThreads, 1)
 stft_reassign_r16(const StftArgs a_in, const int tile_T) {
     using C = Cfg<R>;
     constexpr int N = C::N, kWT = C::kWT, kWorkers = C::kWorkers, kZBuf = C::kZBuf,
                   kXBuf = C::kXBuf, kZtab = C::kZtab, kTileFloats = C::kTileFloats, kSI = C::kSI,
-                  kS16 = C::kS16, kU = C::kU;
+                  kS16 = C::kS16, kU = C::kU, kG = C::kG, kSlot = C::kSlot, kWTh = C::kWorkerThreads;
     StftArgs a = a_in;
     if (!stream_decode(a)) return;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -443,14 +463,16 @@ stft_reassign_r16(const StftArgs a_in, const int tile_T) {
     float2* Ztab = sm;                         // [log2 R][256]: rows i = 1, 2, 4, ..
     float2* T2 = Ztab + kZtab;                 // [16][16]
     float2* wbuf = T2 + kT2;                   // per worker: Z, X, scratch
-    float* tile0 = reinterpret_cast<float*>(wbuf + kWorkers * (kZBuf + kXBuf + kScratch));   // 2 x kTileFloats
+    float* tile0 = reinterpret_cast<float*>(wbuf + kWorkers * kG * kSlot);   // 2 x kTileFloats
 
     const int tid = threadIdx.x;
-    const int w = tid / kWT;                   // worker
-    // role of this thread inside its worker; rotated by one warp per worker so that the warp
+    const int w = tid / kWTh;                  // worker
+    const int wl = tid - w * kWTh;             // thread of the worker
+    const int gs = kG > 1 ? wl / kWT : 0;      // frame slot of this thread (sub-warp workers)
+    // role of this thread for its frame; rotated by one warp per worker so that the warp
     // carrying the self-paired bins lands on a different scheduler in each worker
-    const int p = (tid + 32 * w) & (kWT - 1);
-    float2* Zb = wbuf + w * (kZBuf + kXBuf + kScratch);
+    const int p = kG > 1 ? wl % kWT : (tid + 32 * w) & (kWT - 1);
+    float2* Zb = wbuf + (w * kG + gs) * kSlot;
     float2* Xs = Zb + kZBuf;                   // 2 X[k] at Xs[k + 1]
     float2* Sc = Xs + kXBuf;
 
@@ -511,8 +533,8 @@ stft_reassign_r16(const StftArgs a_in, const int tile_T) {
     if ((long long)blockIdx.x + tile_step < n_tiles) copy_tile(blockIdx.x + tile_step, tile0 + kTileFloats, tid, kThreads);
     asm volatile("cp.async.commit_group;" ::: "memory");
     if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(full_sm), "r"(kWT));
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(full_sm + 8), "r"(kWT));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(full_sm), "r"(kWTh));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(full_sm + 8), "r"(kWTh));
         done[0] = 0; done[1] = 0;
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -533,7 +555,7 @@ stft_reassign_r16(const StftArgs a_in, const int tile_T) {
     auto refill_tile = [&](int b, long long ti_next) {
         const long long tl2 = blockIdx.x + ti_next * tile_step;
         if (tl2 >= n_tiles) return;
-        copy_tile(tl2, tile0 + b * kTileFloats, p, kWT);
+        copy_tile(tl2, tile0 + b * kTileFloats, wl, kWTh);
         asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(full_sm + 8u * b) : "memory");
     };
 
@@ -551,18 +573,21 @@ stft_reassign_r16(const StftArgs a_in, const int tile_T) {
         int ch, nf; long long f0;
         tile_geom(tl, ch, f0, nf);
         const float* tile = tile0 + buf * kTileFloats;
-        if (w >= nf) {                      // no frame for this worker in a short tile: just release it
-            if (p == 0) release_tile(buf);
+        if (w * kG >= nf) {                 // no frame for this worker in a short tile: just release it
+            if (wl == 0) release_tile(buf);
             worker_bar<kWT>(w);
             if (refill[w]) refill_tile(buf, ti + 2);
             worker_bar<kWT>(w);
             continue;
         }
 
-        for (int fi = w; fi < nf; fi += kWorkers) {
+        for (int fi0 = w * kG; fi0 < nf; fi0 += kWorkers * kG) {
+            // sub-warp workers: slots past the end of the tile redo its last frame and emit nothing
+            const bool active = kG == 1 || fi0 + gs < nf;
+            const int fi = kG == 1 ? fi0 : min(fi0 + gs, nf - 1);
             const float* xs = tile + fi * a.hop;
             const long long f = f0 + fi;
-            const bool last_frame = fi + kWorkers >= nf;
+            const bool last_frame = fi0 + kWorkers * kG >= nf;
 
             // ================= pass 1: radix-R butterflies b = p + kWT u on z[n] = x[n] (1 + j th'[n])
             static_for<kU>([&](auto uc) {
@@ -578,7 +603,7 @@ stft_reassign_r16(const StftArgs a_in, const int tile_T) {
                 twiddle_store_rows<R, kSI>(v, Ztab, b, Zb + b + (b >> 4) * (kS16 - 16));
             });
             worker_bar<kWT>(w);
-            if (last_frame && p == 0) release_tile(buf);   // every sample of the tile has been read
+            if (last_frame && wl == 0) release_tile(buf);  // every sample of the tile has been read
 
             pass2<kSI, kS16>(Zb, T2, g);
             worker_bar<kWT>(w);
@@ -588,7 +613,7 @@ stft_reassign_r16(const StftArgs a_in, const int tile_T) {
             pass3_untangle<R>(Zb, Xs, Sc, g, xa, xb, ta, tb);
             worker_bar<kWT>(w);      // X visible; the Z buffer is free for the next frame's pass 1
 
-            epilogue<R, MODE>(a, ch, f, Xs, Sc, g, xa, xb, ta, tb);
+            epilogue<R, MODE>(a, ch, f, Xs, Sc, g, xa, xb, ta, tb, active);
         }
     }
 }
