@@ -235,6 +235,30 @@ static ems_status launch_r16_large(ems_handle* h, const StftArgs& a) {
     return EMS_OK;
 }
 
+// n_fft = 32768: two sequential 16384-point complex FFTs per frame, 2 X parked in an L2-resident scratch.
+static ems_status launch_r16_32k(ems_handle* h, const StftArgs& a) {
+    using C = r16::CfgL<4>;
+    void (*kern)(const StftArgs, float2*) =
+        a.mode == kStorePoints ? r16::stft_reassign_r16_32k<kStorePoints>
+        : a.mode == kDepositU64 ? r16::stft_reassign_r16_32k<kDepositU64>
+                                : r16::stft_reassign_r16_32k<kDepositF32>;
+    constexpr int smem = (C::kZBuf + C::kZtab + r16::kT2) * 8;
+    EMS_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    const long long total = (a.f_end - a.f_begin) * a.channels;
+    long long grid = h->sm_count;
+    if (grid > total) grid = total;
+    if (grid < 1) return EMS_OK;
+    const size_t need = (size_t)h->sm_count * r16::k32kScratch * sizeof(float2);
+    if (h->big_scratch.bytes < need) {     // never reallocated inside a stream capture: stream_init sizes it
+        ems_status s = ensure(h, h->big_scratch, need);
+        if (s != EMS_OK) return s;
+    }
+    kern<<<(unsigned)grid, 512, smem, h->stream>>>(a, (float2*)h->big_scratch.p);
+    ++h->launches;
+    EMS_CUDA(h, cudaGetLastError());
+    return EMS_OK;
+}
+
 static ems_status launch_stft(ems_handle* h, const StftArgs& a) {
     if (!h->force_generic) {
         ems_status s = EMS_ERR_UNSUPPORTED;
@@ -246,6 +270,7 @@ static ems_status launch_stft(ems_handle* h, const StftArgs& a) {
             case 4096: s = launch_r16<16>(h, a); break;
             case 8192: s = launch_r16_large<2>(h, a); break;
             case 16384: s = launch_r16_large<4>(h, a); break;
+            case 32768: s = launch_r16_32k(h, a); break;
             default: break;
         }
         if (s != EMS_ERR_UNSUPPORTED) return s;
@@ -476,7 +501,7 @@ static ems_status stream_init(ems_handle* h) {
     EMS_CUDA(h, cudaHostGetDevicePointer((void**)&st.out_dev, st.out_pin, 0));
     ems_status s = stream_zero(h);
     if (s != EMS_OK) return s;
-    if (N == 32768 && (s = ensure(h, h->big_scratch, (size_t)h->sm_count * (N / 2 + 3) * sizeof(float2))) != EMS_OK) return s;
+    if (N == 32768 && (s = ensure(h, h->big_scratch, (size_t)h->sm_count * r16::k32kScratch * sizeof(float2))) != EMS_OK) return s;
     st.ready = true;
     return EMS_OK;
 }

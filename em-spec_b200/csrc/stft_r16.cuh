@@ -1,5 +1,5 @@
 // stft_r16.cuh — tuned fused frame gather + 3-window STFT + reassignment for
-// n_fft = 256 R, R = 1 .. 16 (256 .. 4096); 8192 and 16384 at the end of the file.
+// n_fft = 256 R, R = 1 .. 16 (256 .. 4096); 8192, 16384 and 32768 at the end of the file.
 //
 // ONE complex FFT per frame.  Z = FFT_N(x + j*x*th'), th' = th*(2/N): the real part is the
 // *unwindowed* frame, so the untangle gives the rectangular-window spectrum X and X_th'.
@@ -732,6 +732,204 @@ stft_reassign_r16_large(const StftArgs a_in) {
         worker_bar<kWT>(w);
 
         epilogue<R, MODE>(a, ch, f, Xs, Sc, g, xa, xb, ta, tb);
+    }
+}
+
+// ---------------------------------------------------------------- n_fft = 32768
+// The packed spectrum (256 KB) does not fit an SM, so the two real FFTs — x, then x th' — run one
+// after the other as 16384-point complex FFTs of y[m] = r[2m] + j r[2m+1] (the passes of the
+// 16384 kernel above), each followed by the even/odd split
+//     2 R[k]     = 2E + W_N^k 2O,   2E = Y[k] + conj Y[M-k],  2O = -j (Y[k] - conj Y[M-k])
+//     2 R[M - k] = conj(2E - W_N^k 2O)                                        (M = N/2)
+// in the registers of the thread that holds residues t and 1024 - t.  2 X waits in a per-CTA
+// scratch that stays in L2 (131 KB) and comes back into the (by then free) Z buffer for the
+// neighbour reads of the Hann stencils; 2 X_th' never leaves the registers.
+constexpr int k32kScratch = 16384 + 4;      // float2 per CTA: 2 X[k] at [k + 1], mirrors at [0], [M + 2]
+
+template <int MODE>
+__global__ void __launch_bounds__(512, 1)
+stft_reassign_r16_32k(const StftArgs a_in, float2* __restrict__ scratch_all) {
+    using C = CfgL<4>;
+    constexpr int N = 32768, M = 16384, R0 = 4, R = 64, kWT = 512, kSI = C::kSI, kS16 = C::kS16,
+                  kRes = 1024, kZtab = C::kZtab, kThreads = 512;
+    StftArgs a = a_in;
+    if (!stream_decode(a)) return;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* sm = reinterpret_cast<float2*>(smem_raw);
+    float2* Ztab = sm;                         // [4][256]: W_4096^{b 2^l}
+    float2* T2 = Ztab + kZtab;                 // [16][16]
+    float2* Zb = T2 + kT2;                     // R * kSI = 16448
+    float2* Xs = Zb;                           // 2 X[k] at Xs[k + 1], staged after the last pass of x th'
+    float2* Sc = Zb + k32kScratch;             // 2 X_th' of the 33 self-paired bins (the Z buffer has 60 spare slots)
+    float2* X2 = scratch_all + (size_t)blockIdx.x * k32kScratch;
+
+    const int tid = threadIdx.x, p = tid;
+    for (int e = tid; e < kZtab; e += kThreads) { const int i = 1 << (e / 256), b = e % 256; Ztab[e] = __ldg(&a.tw[8 * b * i]); }
+    for (int e = tid; e < kT2; e += kThreads) { const int q = e / 16, i = e % 16; T2[e] = __ldg(&a.tw[128 * q * i]); }
+    __syncthreads();
+    const Geom g = make_geom<R, kSI, kS16>(p);
+    const int tA = g.tA, tB = g.tB;
+    const float2 wA = __ldg(&a.tw[tA]);          // W_N^tA (1 for thread 0)
+    const float2 w512 = __ldg(&a.tw[512]);
+
+    // even/odd split of the pair (Y[k], Y[M-k]) with W_N^k = w * W_32^c
+    auto split = [](float2 y, float2 yn_conj, float2 wk, float2& rk, float2& rmk) {
+        const float2 e2 = y + yn_conj, wo = cmul2(mulmj(y - yn_conj), wk);
+        rk = e2 + wo;
+        rmk = cj(e2 - wo);
+    };
+
+    const long long per_ch = a.f_end - a.f_begin;
+    const long long total = per_ch * a.channels;
+    for (long long it = blockIdx.x; it < total; it += gridDim.x) {
+        const int ch = (int)(it / per_ch);
+        const long long f = a.f_begin + (it - (long long)ch * per_ch);
+        const float* xs = a.pcm + (long long)ch * a.S + f * a.hop + a.samp_off;
+
+#pragma unroll 1
+        for (int phase = 0; phase < 2; ++phase) {
+            // ================= pass A: radix-4 butterflies b = p + 512 u over m = b + 4096 j0 on
+            // y[m] = r[2m] + j r[2m+1], in two batches of four (registers)
+#pragma unroll 1
+            for (int half = 0; half < 2; ++half) {
+                float2 v[4][4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int n = 2 * (p + kWT * (4 * half + u) + 4096 * j);
+                        v[u][j] = make_float2(__ldg(xs + n), __ldg(xs + n + 1));
+                    }
+                if (phase) {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const int n = 2 * (p + kWT * (4 * half + u) + 4096 * j);
+                            v[u][j] = mul2(v[u][j], make_float2(__ldg(a.thw + n), __ldg(a.thw + n + 1)));
+                        }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int b = p + kWT * (4 * half + u);
+                    float2* zo = Zb + kSI * (R0 * (b >> 8)) + (b & 255);
+                    const float2 w1 = __ldg(&a.tw[2 * b]);             // W_M^b
+                    dft4(v[u][0], v[u][1], v[u][2], v[u][3]);
+                    const float2 w2 = cmul2(w1, w1);
+                    zo[0] = v[u][0];
+                    zo[kSI] = cmul2(v[u][1], w1);
+                    zo[2 * kSI] = cmul2(v[u][2], w2);
+                    zo[3 * kSI] = cmul2(v[u][3], cmul2(w1, w2));
+                }
+            }
+            __syncthreads();
+
+            // ================= pass B, pass 2: as in the 16384 kernel
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int e = p + kWT * u, b1 = e & 255, i0 = e >> 8;
+                float2* zb = Zb + kSI * i0 + b1;
+                float2 v[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = zb[kSI * R0 * j];
+                dft16(v);
+                twiddle_store_rows<16, kSI * R0>(v, Ztab, b1, zb);
+            }
+            __syncthreads();
+            pass2<kSI, kS16>(Zb, T2, g);
+            __syncthreads();
+
+            // ================= pass 3: Y[tA + 1024 c] = za[o16(c)], Y[tB + 1024 c] = zb[o16(c)]
+            float2 za[16], zb[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) { za[j] = Zb[g.zA + j]; zb[j] = Zb[g.zB + j]; }
+            dft16(za); dft16(zb);
+
+            if (phase == 0) {
+                // ---- 2 X to the scratch
+                if (p != 0) {
+                    static_for<16>([&](auto cc) {
+                        constexpr int c = decltype(cc)::value;
+                        float2 rk, rmk;
+                        split(za[o16(c)], cj(zb[o16(15 - c)]), cmul2(wA, make_float2(c32(c), -s32(c))), rk, rmk);
+                        X2[1 + tA + kRes * c] = rk;
+                        X2[1 + tB + kRes * (15 - c)] = rmk;
+                        if (c == 0 && p == 1) {        // Hermitian mirrors X[-1], X[M+1]
+                            X2[0] = cj(rk);
+                            X2[M + 2] = cj(rmk);
+                        }
+                    });
+                } else {
+                    static_for<9>([&](auto cc) {       // residue 0: bins 1024 c and 1024 (16 - c)
+                        constexpr int c = decltype(cc)::value;
+                        float2 rk, rmk;
+                        split(za[o16(c)], cj(za[o16((16 - c) & 15)]), make_float2(c32(c), -s32(c)), rk, rmk);
+                        X2[1 + kRes * c] = rk;
+                        if (c != 8) X2[1 + kRes * (16 - c)] = rmk;
+                    });
+                    static_for<8>([&](auto cc) {       // residue 512: bins 512 + 1024 c and 512 + 1024 (15 - c)
+                        constexpr int c = decltype(cc)::value;
+                        float2 rk, rmk;
+                        split(zb[o16(c)], cj(zb[o16(15 - c)]), cmul2(w512, make_float2(c32(c), -s32(c))), rk, rmk);
+                        X2[1 + 512 + kRes * c] = rk;
+                        X2[1 + 512 + kRes * (15 - c)] = rmk;
+                    });
+                }
+                __syncthreads();      // Z is free for the passes of x th'; the scratch writes are ordered before the reads below
+            } else {
+                __syncthreads();      // every thread holds its Y values: Z becomes the X buffer
+                {
+                    const unsigned d0 = (unsigned)__cvta_generic_to_shared(Xs);
+                    for (int e = tid; e < k32kScratch / 2; e += kThreads)
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d0 + 16u * e), "l"(X2 + 2 * e) : "memory");
+                    asm volatile("cp.async.commit_group;" ::: "memory");
+                }
+                if (p == 0) {         // 2 X_th' of the self-paired residues go through shared memory
+                    static_for<9>([&](auto cc) {
+                        constexpr int c = decltype(cc)::value;
+                        float2 rk, rmk;
+                        split(za[o16(c)], cj(za[o16((16 - c) & 15)]), make_float2(c32(c), -s32(c)), rk, rmk);
+                        Sc[c] = rk;
+                        if (c != 8) Sc[16 - c] = rmk;
+                    });
+                    static_for<8>([&](auto cc) {
+                        constexpr int c = decltype(cc)::value;
+                        float2 rk, rmk;
+                        split(zb[o16(c)], cj(zb[o16(15 - c)]), cmul2(w512, make_float2(c32(c), -s32(c))), rk, rmk);
+                        Sc[17 + c] = rk;
+                        Sc[17 + 15 - c] = rmk;
+                    });
+                }
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+                __syncthreads();
+
+                // ---- epilogue: 2 X_th' of the thread's pairs, then the shared bin code
+                constexpr int B = N / 2 + 1;
+                FrameCtx fc;
+                fc.lo = (float)max(-f, -1048576LL);
+                fc.hi = (float)min(a.F - 1 - f, 1048576LL);
+                fc.f = f; fc.ch = ch;
+                const long long row0 = ((a.ring ? 0 : (long long)ch * a.F) + f) * B;
+                fc.pd = a.dt_cols + row0; fc.pk = a.dk_bins + row0; fc.pe = a.energy + row0;
+                static_for<16>([&](auto cc) {
+                    constexpr int c = decltype(cc)::value;
+                    float2 rk, rmk;
+                    split(za[o16(c)], cj(zb[o16(15 - c)]), cmul2(wA, make_float2(c32(c), -s32(c))), rk, rmk);
+                    const int kA = tA + kRes * c, kB = tB + kRes * (15 - c);
+                    bin_emit<N, MODE>(a, fc, g.owner, kA, g.tAf + (float)(kRes * c), Xs[kA + 1], Xs[kA], Xs[kA + 2], rk);
+                    bin_emit<N, MODE>(a, fc, g.owner, kB, g.tBf + (float)(kRes * (15 - c)), Xs[kB + 1], Xs[kB], Xs[kB + 2], rmk);
+                });
+                if (p < 32) {         // the 33 self-paired bins: lane l takes bins l and (lane 0) 32 of the list
+#pragma unroll
+                    for (int r = 0; r < 2; ++r) {
+                        const int ls = min(p + 32 * r, 32);
+                        const int ks = ls <= 16 ? kRes * ls : 512 + kRes * (ls - 17);
+                        bin_emit<N, MODE>(a, fc, p + 32 * r <= 32, ks, (float)ks, Xs[ks + 1], Xs[ks], Xs[ks + 2], Sc[ls]);
+                    }
+                }
+                __syncthreads();      // the X buffer becomes Z again
+            }
+        }
     }
 }
 

@@ -401,7 +401,7 @@ def test_tuned_kernel_odd_hops(emspec, hop):
 
 @pytest.mark.parametrize("n_fft,hop", [(256, 17), (256, 64), (256, 256), (512, 33), (512, 100), (512, 512),
                                        (1024, 100), (1024, 257), (1024, 1024), (2048, 96), (2048, 515), (2048, 1400),
-                                       (8192, 333), (8192, 8192), (16384, 1000)])
+                                       (8192, 333), (8192, 8192), (16384, 1000), (32768, 777), (32768, 4096)])
 def test_tuned_family_hops(emspec, n_fft, hop):
     """The radix-R x 16 x 16 kernels away from 4096: hops that are multiples of 4 (16-byte tile
     copies), odd (4-byte copies) and so large that a tile holds fewer frames than workers; frame
@@ -411,7 +411,7 @@ def test_tuned_family_hops(emspec, n_fft, hop):
     check_points(run_points(emspec, x, prm), x, prm)
 
 
-@pytest.mark.parametrize("n_fft", [256, 512, 1024, 2048, 4096, 8192, 16384])
+@pytest.mark.parametrize("n_fft", [256, 512, 1024, 2048, 4096, 8192, 16384, 32768])
 def test_tuned_family_matches_generic_and_unaligned_channels(emspec, n_fft, monkeypatch):
     """Stereo with an odd sample count: channel 1 starts off a 16-byte boundary, so one channel
     takes the 16-byte and the other the 4-byte tile copies.  Both must give the oracle's points,
