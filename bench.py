@@ -164,7 +164,7 @@ def synth_device(S: int, seed: int, device):
 
 # dram__bytes_read.sum + dram__bytes_write.sum of stft_reassign_r16<store>, one `ncu --set full`
 # capture of a 224,969-frame launch (profiles/r01_ncu_stft_reassign_r16.txt): 5.6072 GB
-NCU_DRAM_BYTES_PER_FRAME = (126.921216e6 + 5.480240e9) / 224969
+NCU_DRAM_BYTES_PER_FRAME = (128.511488e6 + 5.482603e9) / 224969
 
 
 def peaks():
@@ -350,6 +350,34 @@ def run_ours(args):
                   "what": "wall time of ems_stream_push incl. H2D of the hop, CUDA-graph launch, D2H of the column"}
         seng.close()
 
+    # ---- extra: configs[4] n_fft sweep (hop = n_fft/4, display controls on), device-resident
+    # ems_process_points per n_fft on a 600 s stream, CUDA events on the launching stream
+    sweep = None
+    if rank == 0 and world == 1 and not args.no_sweep:
+        sweep = []
+        S4 = min(S, 600 * SR)
+        for n4 in (256, 512, 1024, 2048, 4096, 8192, 16384, 32768):
+            h4 = n4 // 4
+            e4 = emspec.Engine(n_fft=n4, hop=h4, low_end_boost=3.9, smoothing=0.5, noise_gate_db=-65.0)
+            e4.use_torch_stream()
+            F4 = frame_count(S4, n4, h4)
+            o4 = tuple(torch.empty((1, F4, n4 // 2 + 1), dtype=torch.float32, device=dev) for _ in range(3))
+            for _ in range(3):
+                e4.process_points(pcm[:S4], out=o4)
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record()
+            for _ in range(5):
+                e4.process_points(pcm[:S4], out=o4)
+            s1.record()
+            torch.cuda.synchronize()
+            ms4 = s0.elapsed_time(s1) / 5
+            gbs = b_points(n4, h4) * F4 / (ms4 * 1e-3) / 1e9
+            sweep.append({"n_fft": n4, "hop": h4, "frames": F4, "frames_per_s": F4 / (ms4 * 1e-3),
+                          "algorithmic_GBs": gbs, "frac_of_peak": gbs / peak})
+            e4.close()
+            del o4
+        torch.cuda.empty_cache()
+
     # ---- extra (not the headline): capture-format int16 PCM in,
     # 546 display rows of the warped frequency axis out — 6 x fewer PCIe bytes per frame
     e2e_display = None
@@ -406,7 +434,7 @@ def run_ours(args):
                          "bytes_per_frame": b_points(N_FFT, HOP),
                          "frac_of_nominal_8TBs": achieved / 8000.0,
                          "fp32_frac_of_74.45TF": (F / (kern_ms * 1e-3)) * 483378 / 74.45e12},
-            "cpu_baseline": cpu, "e2e": e2e, "pipeline_u8": pipe, "e2e_display_rows": e2e_display, "stream_latency": stream, "gpu_launches": int(launches),
+            "cpu_baseline": cpu, "e2e": e2e, "pipeline_u8": pipe, "e2e_display_rows": e2e_display, "stream_latency": stream, "nfft_sweep": sweep, "gpu_launches": int(launches),
             "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
@@ -431,6 +459,7 @@ def main():
     ap.add_argument("--no-pipeline", action="store_true")
     ap.add_argument("--no-stream", action="store_true")
     ap.add_argument("--no-display", action="store_true")
+    ap.add_argument("--no-sweep", action="store_true")
     ap.add_argument("--stream-pushes", type=int, default=5000)
     args = ap.parse_args()
     return run_reference(args) if args.impl == "reference" else run_ours(args)
