@@ -1,5 +1,6 @@
 """A/B timing of ems_process_points at n_fft=4096 hop=128 for two builds of libemspec.so.
-Usage: python tools/ab_kernel.py libA.so libB.so ...   (each timed in its own subprocess, interleaved twice)"""
+Usage: python tools/ab_kernel.py libA.so libB.so@ENV=VAL ...   (each timed in its own subprocess, interleaved
+twice; `@ENV=VAL` sets an environment variable for that arm, e.g. an experimental dispatch switch)"""
 import json
 import os
 import subprocess
@@ -23,18 +24,22 @@ for it in range(12):
     e0.record(); eng.process_points(pcm, out=pts); e1.record(); torch.cuda.synchronize()
     ms.append(e0.elapsed_time(e1))
 ms = sorted(ms[2:])
-print("RESULT", F / ms[len(ms) // 2] / 1e3, F / ms[0] / 1e3)
+print("RESULT", F / ms[len(ms) // 2] / 1e3, F / ms[0] / 1e3, "checks", float(pts[2].double().sum()), float(pts[0].double().abs().sum()), float(pts[1].double().abs().sum()))
 '''
 
 
 def main():
     libs = sys.argv[1:]
     for rnd in range(2):
-        for lib in libs:
+        for spec in libs:
+            lib, _, kv = spec.partition("@")
             env = dict(os.environ, EMS_LIB_PATH=os.path.abspath(lib))
+            if kv:
+                k, _, v = kv.partition("=")
+                env[k] = v
             out = subprocess.run([sys.executable, "-c", CHILD % {"root": ROOT}], env=env, capture_output=True, text=True)
             res = [l for l in out.stdout.splitlines() if l.startswith("RESULT")]
-            print(os.path.basename(lib), res[0] if res else out.stderr[-400:], flush=True)
+            print(os.path.basename(spec), res[0] if res else out.stderr[-400:], flush=True)
 
 
 if __name__ == "__main__":
