@@ -259,12 +259,15 @@ template <int N>
 __device__ __forceinline__ float bin_energy(float2 A2) {
     return __fmaf_rn(A2.x, A2.x, __fmul_rn(A2.y, A2.y)) * (float)(4.0 / ((double)N * (double)N));
 }
+// `off` is the bin's index relative to the row pointers of fc (k itself, or a compile-time
+// multiple of the residue stride when fc points at the thread's residue: the stores then take
+// immediate offsets from six live base pointers instead of a 64-bit address computation each).
 template <int MODE>
-__device__ __forceinline__ void bin_dead(const FrameCtx& fc, bool owner, int k) {
-    if (MODE == kStorePoints && owner) { fc.pd[k] = 0.f; fc.pk[k] = 0.f; fc.pe[k] = 0.f; }
+__device__ __forceinline__ void bin_dead(const FrameCtx& fc, bool owner, int off) {
+    if (MODE == kStorePoints && owner) { fc.pd[off] = 0.f; fc.pk[off] = 0.f; fc.pe[off] = 0.f; }
 }
 template <int N, int MODE>
-__device__ __forceinline__ void bin_tail(const StftArgs& a, const FrameCtx& fc, bool owner, bool live, int k,
+__device__ __forceinline__ void bin_tail(const StftArgs& a, const FrameCtx& fc, bool owner, bool live, int k, int off,
                                          float kf, float2 A2, float2 xm, float2 xp, float2 t2) {
     // explicit fused multiply-adds: every instantiation (store / deposit, every n_fft) rounds alike,
     // so a grid deposited by the fused kernel equals the scatter of the stored points bit for bit
@@ -287,7 +290,7 @@ __device__ __forceinline__ void bin_tail(const StftArgs& a, const FrameCtx& fc, 
         dk = ok ? dk : 0.f;
     }
     if (MODE == kStorePoints) {
-        if (owner) { fc.pd[k] = dtc; fc.pk[k] = dk; fc.pe[k] = ok ? e : 0.f; }
+        if (owner) { fc.pd[off] = dtc; fc.pk[off] = dk; fc.pe[off] = ok ? e : 0.f; }
     } else if (ok && owner) {
         const DepositCtx d{a.acc, a.flags, a.F, a.ring, a.rows, a.warp_mode, a.warp_a, a.warp_c, a.inv_half};
         deposit_point<MODE>(d, fc.ch, fc.f + (long long)rc, k, dk, wh, e);
@@ -301,7 +304,7 @@ __device__ __forceinline__ void bin_emit(const StftArgs& a, const FrameCtx& fc, 
     const float2 A2 = hann_stencil(xk, xm, xp);                          // 2 X_h
     const bool live = bin_energy<N>(A2) > a.gate_lin;
     if (!__any_sync(0xffffffffu, live)) { bin_dead<MODE>(fc, owner, k); return; }
-    bin_tail<N, MODE>(a, fc, owner, live, k, kf, A2, xm, xp, t2);
+    bin_tail<N, MODE>(a, fc, owner, live, k, k, kf, A2, xm, xp, t2);
 }
 
 // conj(a)
@@ -449,6 +452,13 @@ __device__ __forceinline__ void epilogue(const StftArgs& a, int ch, long long f,
     const long long row0 = ((a.ring ? 0 : (long long)ch * a.F) + f) * B;
     fc.pd = a.dt_cols + row0; fc.pk = a.dk_bins + row0; fc.pe = a.energy + row0;
     const int tA = g.tA, tB = g.tB;
+    // row pointers at the thread's two residues, opaque to the compiler so that it keeps them
+    // in registers (it otherwise rebuilds a 64-bit address for every store: 7 IADD3 per bin)
+    FrameCtx fA = fc, fB = fc;
+    if (MODE == kStorePoints) {
+        fA.pd += tA; fA.pk += tA; fA.pe += tA; fB.pd += tB; fB.pk += tB; fB.pe += tB;
+        asm volatile("" : "+l"(fA.pd), "+l"(fA.pk), "+l"(fA.pe), "+l"(fB.pd), "+l"(fB.pk), "+l"(fB.pe));
+    }
     constexpr int GC = 2;     // residue pairs per vote: 4 bins, 8 neighbour loads in flight (8 bins spill: measured -10 %)
     static_for<8 / GC>([&](auto cc) {
         constexpr int c0 = GC * decltype(cc)::value;
@@ -472,15 +482,15 @@ __device__ __forceinline__ void epilogue(const StftArgs& a, int ch, long long f,
         if (!__any_sync(0xffffffffu, any)) {
 #pragma unroll
             for (int i = 0; i < GC; ++i) {
-                bin_dead<MODE>(fc, owner, tA + kRes * (c0 + i));
-                bin_dead<MODE>(fc, owner, tB + kRes * (c0 + i));
+                bin_dead<MODE>(fA, owner, kRes * (c0 + i));
+                bin_dead<MODE>(fB, owner, kRes * (c0 + i));
             }
         } else {
 #pragma unroll
             for (int i = 0; i < GC; ++i) {
-                bin_tail<N, MODE>(a, fc, owner, lv[2 * i], tA + kRes * (c0 + i), g.tAf + (float)(kRes * (c0 + i)),
+                bin_tail<N, MODE>(a, fA, owner, lv[2 * i], tA + kRes * (c0 + i), kRes * (c0 + i), g.tAf + (float)(kRes * (c0 + i)),
                                   A2[2 * i], xm[2 * i], xp[2 * i], ta[c0 + i]);
-                bin_tail<N, MODE>(a, fc, owner, lv[2 * i + 1], tB + kRes * (c0 + i), g.tBf + (float)(kRes * (c0 + i)),
+                bin_tail<N, MODE>(a, fB, owner, lv[2 * i + 1], tB + kRes * (c0 + i), kRes * (c0 + i), g.tBf + (float)(kRes * (c0 + i)),
                                   A2[2 * i + 1], xm[2 * i + 1], xp[2 * i + 1], tb[c0 + i]);
             }
         }
