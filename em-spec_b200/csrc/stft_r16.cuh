@@ -972,13 +972,31 @@ stft_reassign_r16_32k(const StftArgs a_in, float2* __restrict__ scratch_all) {
                 fc.f = f; fc.ch = ch;
                 const long long row0 = ((a.ring ? 0 : (long long)ch * a.F) + f) * B;
                 fc.pd = a.dt_cols + row0; fc.pk = a.dk_bins + row0; fc.pe = a.energy + row0;
-                static_for<16>([&](auto cc) {
-                    constexpr int c = decltype(cc)::value;
-                    float2 rk, rmk;
-                    split(za[o16(c)], cj(zb[o16(15 - c)]), cmul2(wA, make_float2(c32(c), -s32(c))), rk, rmk);
-                    const int kA = tA + kRes * c, kB = tB + kRes * (15 - c);
-                    bin_emit<N, MODE>(a, fc, g.owner, kA, g.tAf + (float)(kRes * c), Xs[kA + 1], Xs[kA], Xs[kA + 2], rk);
-                    bin_emit<N, MODE>(a, fc, g.owner, kB, g.tBf + (float)(kRes * (15 - c)), Xs[kB + 1], Xs[kB], Xs[kB + 2], rmk);
+                static_for<8>([&](auto cc) {        // four bins per vote, as in epilogue()
+                    constexpr int c = 2 * decltype(cc)::value;
+                    float2 t2[4], xk[4], xm[4], xp[4], A2[4];
+                    int kk[4];
+                    bool lv[4], any = false;
+                    split(za[o16(c)], cj(zb[o16(15 - c)]), cmul2(wA, make_float2(c32(c), -s32(c))), t2[0], t2[1]);
+                    split(za[o16(c + 1)], cj(zb[o16(14 - c)]), cmul2(wA, make_float2(c32(c + 1), -s32(c + 1))), t2[2], t2[3]);
+                    kk[0] = tA + kRes * c; kk[1] = tB + kRes * (15 - c);
+                    kk[2] = tA + kRes * (c + 1); kk[3] = tB + kRes * (14 - c);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) { xm[i] = Xs[kk[i]]; xk[i] = Xs[kk[i] + 1]; xp[i] = Xs[kk[i] + 2]; }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        A2[i] = hann_stencil(xk[i], xm[i], xp[i]);
+                        lv[i] = bin_energy<N>(A2[i]) > a.gate_lin;
+                        any = any || lv[i];
+                    }
+                    if (!__any_sync(0xffffffffu, any)) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) bin_dead<MODE>(fc, g.owner, kk[i]);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            bin_tail<N, MODE>(a, fc, g.owner, lv[i], kk[i], kk[i], (float)kk[i], A2[i], xm[i], xp[i], t2[i]);
+                    }
                 });
                 if (p < 32) {         // the 33 self-paired bins: lane l takes bins l and (lane 0) 32 of the list
 #pragma unroll

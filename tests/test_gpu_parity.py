@@ -510,11 +510,12 @@ def test_long_stream_properties(emspec):
 
 @pytest.mark.parametrize("n_fft,hop,channels,smoothing", [
     (2048, 256, 2, 0.0), (4096, 128, 1, 0.0), (1024, 300, 1, 0.0), (8192, 256, 2, 0.4),
+    (256, 64, 2, 0.0), (512, 100, 1, 0.3), (16384, 2048, 1, 0.0), (32768, 4096, 1, 0.0),
 ])
 def test_streaming_matches_offline(emspec, n_fft, hop, channels, smoothing):
     """ems_stream_push (one frame per push, CUDA graph) emits, R pushes late, exactly the columns
     the offline call computes for the same samples (configs[1] geometry is the last case)."""
-    S = int(0.6 * SR) // hop * hop
+    S = int(max(0.6 * SR, 2.5 * n_fft)) // hop * hop
     x = np.stack([orc.synth_signal(S, SR, seed=20 + c) for c in range(channels)])
     eng = emspec.Engine(n_fft=n_fft, hop=hop, channels=channels, smoothing=smoothing,
                         flags=emspec.FLAG_REASSIGN | emspec.FLAG_DETERMINISTIC | emspec.FLAG_SYNC)
