@@ -559,8 +559,9 @@ stft_reassign_r16(const StftArgs a_in, const int tile_T) {
     // workers drift apart and their FP-heavy and shared-memory-heavy phases interleave (in
     // lockstep they collide: measured +13 %).  Protocol per buffer b:
     //   * a worker that has read its last sample of the tile in b bumps done[b]; the last one
-    //     to do so refills b with the tile after next (cp.async from its own threads, 4-byte
-    //     copies, or 16-byte ones for large aligned hops) and the copies arrive on the mbarrier full[b];
+    //     to do so refills b with the tile after next (4-byte cp.async from its own threads: no
+    //     alignment demands; one TMA bulk copy for large aligned hops) and the copies arrive on
+    //     the mbarrier full[b];
     //   * a worker waits on full[b] before it reads a refilled buffer.
     unsigned long long* full = reinterpret_cast<unsigned long long*>(tile0 + 2 * kTileFloats);   // [2]
     unsigned* done = reinterpret_cast<unsigned*>(full + 2);                                     // [2]
@@ -577,16 +578,8 @@ stft_reassign_r16(const StftArgs a_in, const int tile_T) {
         const int n_samp = (nf - 1) * a.hop + N;
         const float* src = a.pcm + (long long)ch * a.S + f0 * a.hop + a.samp_off;
         const unsigned d0 = (unsigned)__cvta_generic_to_shared(dst);
-        // 16-byte copies pay when tiles turn over quickly (hop >= N/8: +7 % at 4096/1024); with a
-        // small hop the copy volume is negligible and the slower 4-byte loop keeps the workers
-        // out of phase (4096/128: 92.2 M frames/s against 87.4 M with 16-byte copies, measured)
-        if (a.hop * 8 >= N && (((unsigned long long)src | (unsigned long long)(unsigned)a.hop * 4ull) & 15ull) == 0) {
-            for (int s = 4 * t0; s < n_samp; s += 4 * nth)
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d0 + 4u * s), "l"(src + s) : "memory");
-        } else {
-            for (int s = t0; s < n_samp; s += nth)
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d0 + 4u * s), "l"(src + s) : "memory");
-        }
+        for (int s = t0; s < n_samp; s += nth)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d0 + 4u * s), "l"(src + s) : "memory");
     };
     // prologue: the first two tiles by all threads
     const long long tile_step = gridDim.x;
@@ -616,6 +609,31 @@ stft_reassign_r16(const StftArgs a_in, const int tile_T) {
     auto refill_tile = [&](int b, long long ti_next) {
         const long long tl2 = blockIdx.x + ti_next * tile_step;
         if (tl2 >= n_tiles) return;
+        // Tiles that turn over quickly (hop >= N/8) and start on a 16-byte boundary come in as one
+        // TMA bulk copy issued by a single thread (+3..6 % over per-thread copies at hop = N/4).
+        // With a small hop the copy volume is negligible and the slower 4-byte loop is kept on
+        // purpose: the delay it costs the refilling worker keeps the workers out of phase
+        // (4096/128: 97.6 M frames/s, 94.2 M with a bulk copy, 97.7 M with a bulk copy and a 1 us
+        // sleep — measured with tools/ab_kernel.py).
+        if (a.hop * 8 >= N) {
+            int ch2, nf2; long long f02;
+            tile_geom(tl2, ch2, f02, nf2);
+            const unsigned bytes = 4u * (unsigned)((nf2 - 1) * a.hop + N);
+            const float* src = a.pcm + (long long)ch2 * a.S + f02 * a.hop + a.samp_off;
+            if ((((unsigned long long)src | (unsigned long long)(unsigned)a.hop * 4ull) & 15ull) == 0) {
+                const unsigned bar = full_sm + 8u * b;
+                if (wl == 0) {
+                    const unsigned d0 = (unsigned)__cvta_generic_to_shared(tile0 + b * kTileFloats);
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                 ::"r"(d0), "l"(src), "r"(bytes), "r"(bar) : "memory");
+                } else {
+                    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+                }
+                return;
+            }
+        }
         copy_tile(tl2, tile0 + b * kTileFloats, wl, kWTh);
         asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(full_sm + 8u * b) : "memory");
     };
