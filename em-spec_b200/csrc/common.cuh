@@ -19,6 +19,19 @@ __device__ __forceinline__ unsigned long long fix_energy(float e) {
     return __float2ull_rn(fminf(e, kFixMaxEnergy) * kFixScale);
 }
 
+// Deposits are reductions into global memory: spelled as red.global so that pointers that
+// reach the call as generic addresses (kernel-argument structs passed through a non-inlined
+// function) do not compile to a returning ATOM with a shared-memory fallback loop.
+__device__ __forceinline__ void red_add_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("red.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void red_add_f32(float* p, float v) {
+    asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+__device__ __forceinline__ void flag_set(unsigned char* p) {
+    asm volatile("st.global.u8 [%0], %1;" ::"l"(p), "r"(1) : "memory");
+}
+
 enum DepositMode : int {
     kStorePoints = 0,   // write (dt_cols, dk_bins, energy) triples
     kDepositU64  = 1,   // red.global.add.u64 into the fixed-point accumulator

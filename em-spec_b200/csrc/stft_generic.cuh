@@ -111,11 +111,10 @@ __device__ __forceinline__ void reassign_emit(const StftArgs& a, int ch,
         const int row = out_row(a.warp_mode, a.warp_a, a.warp_c, a.inv_half, k, dk, wh);
         const long long o = acc_cell(a, ch, col, row);
         if (a.mode == kDepositU64)
-            atomicAdd(reinterpret_cast<unsigned long long*>(a.acc) + o,
-                      fix_energy(e));
+            red_add_u64(reinterpret_cast<unsigned long long*>(a.acc) + o, fix_energy(e));
         else
-            atomicAdd(reinterpret_cast<float*>(a.acc) + o, e);
-        if (a.flags) a.flags[flag_index(ch, a.F, a.rows, col, row)] = 1;
+            red_add_f32(reinterpret_cast<float*>(a.acc) + o, e);
+        if (a.flags) flag_set(a.flags + flag_index(ch, a.F, a.rows, col, row));
     }
 }
 

@@ -24,7 +24,14 @@ for it in range(12):
     e0.record(); eng.process_points(pcm, out=pts); e1.record(); torch.cuda.synchronize()
     ms.append(e0.elapsed_time(e1))
 ms = sorted(ms[2:])
-print("RESULT", F / ms[len(ms) // 2] / 1e3, F / ms[0] / 1e3, "checks", float(pts[2].double().sum()), float(pts[0].double().abs().sum()), float(pts[1].double().abs().sum()))
+idx = torch.empty((1, F, 2049), dtype=torch.uint8, device="cuda")
+gms = []
+for it in range(8):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); eng.process_grid(pcm, out=(None, idx)); e1.record(); torch.cuda.synchronize()
+    gms.append(e0.elapsed_time(e1))
+gms = sorted(gms[2:])
+print("RESULT", "grid", round(F / gms[len(gms) // 2] / 1e3, 2), "points", F / ms[len(ms) // 2] / 1e3, F / ms[0] / 1e3, "checks", float(pts[2].double().sum()), float(pts[0].double().abs().sum()), float(pts[1].double().abs().sum()))
 '''
 
 
