@@ -26,8 +26,8 @@
 //     Z[N-k] of its 16 bins are in its own registers: untangle in registers, X (N/2+1 values)
 //     goes to shared memory once so that each bin can read its two neighbours, then the
 //     Auger-Flandrin epilogue runs on the thread's own bins.  3 worker barriers per frame.
-//     Residues 0 and 8R pair with themselves (17 bins): one thread untangles them, 17 lanes of
-//     its warp finish them.
+//     Residues 0 and 8R pair with themselves: thread 0 selects its partners inside the common
+//     instruction stream and finishes the one extra bin (N/2) on the side.
 // Decisions (gate, drop rule, deposit) are those of stft_generic.cuh::reassign_emit.
 #pragma once
 #include "common.cuh"
@@ -42,7 +42,7 @@ namespace r16 {
 constexpr int kMaxSmem = 232448;       // 227 KB
 constexpr int kSyncBytes = 128;        // 2 mbarriers, 2 release counters, kWorkers refill flags
 constexpr int kT2 = 16 * 16;           // W_256^{p2 i} as [p2][i]: a butterfly's 16 twiddles are contiguous
-constexpr int kScratch = 20;           // 2 X_th' of the 17 self-paired bins
+constexpr int kScratch = 20;           // 2 X_th' of bin N/2 (and padding: the slot size stays 8 mod 16)
 constexpr int kThreads = 384;
 
 template <int R_>
@@ -320,9 +320,7 @@ struct Geom {
     int tA, tB;         // output residues of the last pass: bins tA + kRes c and tB + kRes c
     int zA, zB;         // where their 16 inputs start in the Z buffer
     int i1, q2;         // pass-2 butterflies (i1, q2) and (i1, q2 + 8)
-    int ls, ks;         // self-paired bins: lane ls <= 16 of the first warp finishes bin ks (kWT >= 32)
     float tAf, tBf;
-    bool owner;         // thread 0's residues pair with themselves
 };
 template <int R, int kSI, int kS16>
 __device__ __forceinline__ Geom make_geom(int p) {
@@ -334,11 +332,7 @@ __device__ __forceinline__ Geom make_geom(int p) {
     g.zA = kSI * (g.tA & (R - 1)) + kS16 * (g.tA / R);
     g.zB = kSI * (g.tB & (R - 1)) + kS16 * (g.tB / R);
     g.i1 = p & (R - 1); g.q2 = p / R;
-    g.owner = p != 0;
     g.tAf = (float)g.tA; g.tBf = (float)g.tB;
-    // residues 0 and 8R: lane l <= 8 takes bin kRes l, lanes 9..16 bins kRes/2 + kRes (l - 9)
-    g.ls = min(p, 16);
-    g.ks = g.ls <= 8 ? kRes * g.ls : kRes / 2 + kRes * (g.ls - 9);
     return g;
 }
 
@@ -394,6 +388,10 @@ __device__ __forceinline__ void pass2(float2* Zb, const float2* T2, const Geom& 
 
 // Pass 3: residues tA, tB; untangle in registers; 2 X to shared memory (Xs[k + 1]).
 //   2 X[k] = Z[k] + conj Z[N-k],  2 X_th'[k] = (Z[k] - conj Z[N-k]) / j
+// Thread 0's residues (0 and 8R) pair with themselves; it picks its conjugate partners with
+// selects inside the common instruction stream (a divergent branch here would put both paths
+// on the critical warp of the worker, and the other warps wait for it at the next barrier).
+// Residue 0 has a ninth bin, N/2: thread 0 untangles it on the side (Xs, Sc[0]).
 template <int R>
 __device__ __forceinline__ void pass3_untangle(const float2* Zb, float2* Xs, float2* Sc, const Geom& g,
                                                float2 (&xa)[8], float2 (&xb)[8], float2 (&ta)[8], float2 (&tb)[8]) {
@@ -403,35 +401,26 @@ __device__ __forceinline__ void pass3_untangle(const float2* Zb, float2* Xs, flo
 #pragma unroll
     for (int j = 0; j < 16; ++j) { za[j] = Zb[g.zA + j]; zb[j] = Zb[g.zB + j]; }
     dft16(za); dft16(zb);
-    if (g.p != 0) {
-        static_for<8>([&](auto cc) {
-            constexpr int c = decltype(cc)::value;
-            const float2 za_c = za[o16(c)], zb_n = cj(zb[o16(15 - c)]);
-            const float2 zb_c = zb[o16(c)], za_n = cj(za[o16(15 - c)]);
-            xa[c] = za_c + zb_n; ta[c] = mulmj(za_c - zb_n);
-            xb[c] = zb_c + za_n; tb[c] = mulmj(zb_c - za_n);
-            Xs[1 + tA + kRes * c] = xa[c];
-            Xs[1 + tB + kRes * c] = xb[c];
-        });
-        if (g.p == 1) {      // Hermitian mirrors: X[-1] = conj X[1], X[N/2+1] = conj X[N/2-1]
-            Xs[0] = cj(xa[0]);
-            Xs[N / 2 + 2] = cj(xb[7]);
-        }
-    } else {
-        // residues 0 (bins kRes c, c = 0..8) and kRes/2 (bins kRes/2 + kRes c) pair with themselves
-        static_for<9>([&](auto cc) {
-            constexpr int c = decltype(cc)::value;
-            const float2 z = za[o16(c & 15)], zn = cj(za[o16((16 - c) & 15)]);
-            Xs[1 + kRes * c] = z + zn;
-            Sc[c] = mulmj(z - zn);
-        });
-        static_for<8>([&](auto cc) {
-            constexpr int c = decltype(cc)::value;
-            const float2 z = zb[o16(c)], zn = cj(zb[o16(15 - c)]);
-            Xs[1 + kRes / 2 + kRes * c] = z + zn;
-            Sc[9 + c] = mulmj(z - zn);
-            xa[c] = z; xb[c] = z; ta[c] = z; tb[c] = z;        // placeholders, never stored
-        });
+    const bool self = g.p == 0;
+    static_for<8>([&](auto cc) {
+        constexpr int c = decltype(cc)::value;
+        const float2 za_c = za[o16(c)], zb_c = zb[o16(c)];
+        const float2 pa = self ? za[o16((16 - c) & 15)] : zb[o16(15 - c)];      // Z[N - (tA + kRes c)]
+        const float2 pb = self ? zb[o16(15 - c)] : za[o16(15 - c)];              // Z[N - (tB + kRes c)]
+        const float2 zb_n = cj(pa), za_n = cj(pb);
+        xa[c] = za_c + zb_n; ta[c] = mulmj(za_c - zb_n);
+        xb[c] = zb_c + za_n; tb[c] = mulmj(zb_c - za_n);
+        Xs[1 + tA + kRes * c] = xa[c];
+        Xs[1 + tB + kRes * c] = xb[c];
+    });
+    if (g.p == 1) {      // Hermitian mirrors: X[-1] = conj X[1], X[N/2+1] = conj X[N/2-1]
+        Xs[0] = cj(xa[0]);
+        Xs[N / 2 + 2] = cj(xb[7]);
+    }
+    if (self) {
+        const float2 z = za[o16(8)], zn = cj(z);
+        Xs[1 + N / 2] = z + zn;
+        Sc[0] = mulmj(z - zn);
     }
 }
 
@@ -446,7 +435,7 @@ __device__ __forceinline__ void epilogue(const StftArgs& a, int ch, long long f,
                                          const Geom& g, const float2 (&xa)[8], const float2 (&xb)[8],
                                          const float2 (&ta)[8], const float2 (&tb)[8], bool active = true) {
     constexpr int kRes = 16 * R, N = 256 * R, B = N / 2 + 1, kWT = 8 * R;
-    const bool owner = g.owner && active;
+    const bool owner = active;
     FrameCtx fc;
     fc.lo = (float)max(-f, -1048576LL);
     fc.hi = (float)min(a.F - 1 - f, 1048576LL);
@@ -506,18 +495,9 @@ __device__ __forceinline__ void epilogue(const StftArgs& a, int ch, long long f,
             }
         }
     });
-    if constexpr (kWT >= 32) {
-        if (g.p < 32)   // the 17 self-paired bins, one per lane (the rest of the warp tags along)
-            bin_emit<N, MODE>(a, fc, g.p <= 16, g.ks, (float)g.ks, Xs[g.ks + 1], Xs[g.ks], Xs[g.ks + 2], Sc[g.ls]);
-    } else {
-        // fewer lanes than self-paired bins: lane p takes bins p, p + kWT, .. of the 17
-#pragma unroll
-        for (int r = 0; r < (17 + kWT - 1) / kWT; ++r) {
-            const int ls = min(g.p + kWT * r, 16);
-            const int ks = ls <= 8 ? kRes * ls : kRes / 2 + kRes * (ls - 9);
-            bin_emit<N, MODE>(a, fc, active && g.p + kWT * r <= 16, ks, (float)ks, Xs[ks + 1], Xs[ks], Xs[ks + 2], Sc[ls]);
-        }
-    }
+    // bin N/2, the ninth of residue 0: thread 0 of the frame (its warp tags along)
+    if (kWT < 32 || g.p < 32)
+        bin_emit<N, MODE>(a, fc, owner && g.p == 0, N / 2, (float)(N / 2), Xs[N / 2 + 1], Xs[N / 2], Xs[N / 2 + 2], Sc[0]);
 }
 
 // ---------------------------------------------------------------- n_fft = 256 .. 4096
@@ -1020,11 +1000,11 @@ stft_reassign_r16_32k(const StftArgs a_in, float2* __restrict__ scratch_all) {
                     }
                     if (!__any_sync(0xffffffffu, any)) {
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) bin_dead<MODE>(fc, g.owner, kk[i]);
+                        for (int i = 0; i < 4; ++i) bin_dead<MODE>(fc, p != 0, kk[i]);
                     } else {
 #pragma unroll
                         for (int i = 0; i < 4; ++i)
-                            bin_tail<N, MODE>(a, fc, g.owner, lv[i], kk[i], kk[i], (float)kk[i], A2[i], xm[i], xp[i], t2[i]);
+                            bin_tail<N, MODE>(a, fc, p != 0, lv[i], kk[i], kk[i], (float)kk[i], A2[i], xm[i], xp[i], t2[i]);
                     }
                 });
                 if (p < 32) {         // the 33 self-paired bins: lane l takes bins l and (lane 0) 32 of the list
