@@ -368,22 +368,29 @@ __device__ __forceinline__ void pass2(float2* Zb, const float2* T2, const Geom& 
     for (int j = 0; j < 16; ++j) v0[j] = bz0[kS16 * j];
 #pragma unroll
     for (int j = 0; j < 16; ++j) v1[j] = bz1[kS16 * j];
-    // twiddles W_256^{p2 i}: the 16 of a butterfly are contiguous, two per 128-bit load
-    // (the whole warp reads two addresses: one wavefront per load)
-    auto twiddle_store = [&](float2 (&v)[16], float2* base, int p2) {
+    // twiddles W_256^{p2 i}: the 16 of a butterfly are contiguous, two per 128-bit load (the whole
+    // warp reads two addresses: one wavefront per load); loaded before the butterfly they belong
+    // to, so that their latency hides behind its arithmetic
+    auto twiddle_load = [&](float4 (&t)[8], int p2) {
         const float4* t4 = reinterpret_cast<const float4*>(T2 + 16 * p2);
 #pragma unroll
+        for (int h = 0; h < 8; ++h) t[h] = t4[h];
+    };
+    auto twiddle_store = [&](float2 (&v)[16], const float4 (&t)[8], float2* base) {
+#pragma unroll
         for (int h = 0; h < 8; ++h) {
-            const float4 t = t4[h];
             if (h == 0) base[0] = v[o16(0)];
-            else base[kS16 * (2 * h)] = cmul2(v[o16(2 * h)], make_float2(t.x, t.y));
-            base[kS16 * (2 * h + 1)] = cmul2(v[o16(2 * h + 1)], make_float2(t.z, t.w));
+            else base[kS16 * (2 * h)] = cmul2(v[o16(2 * h)], make_float2(t[h].x, t[h].y));
+            base[kS16 * (2 * h + 1)] = cmul2(v[o16(2 * h + 1)], make_float2(t[h].z, t[h].w));
         }
     };
+    float4 tw[8];
     dft16(v0);
-    twiddle_store(v0, bz0, g.q2);
+    twiddle_load(tw, g.q2);
+    twiddle_store(v0, tw, bz0);
     dft16(v1);
-    twiddle_store(v1, bz1, g.q2 + 8);
+    twiddle_load(tw, g.q2 + 8);
+    twiddle_store(v1, tw, bz1);
 }
 
 // Pass 3: residues tA, tB; untangle in registers; 2 X to shared memory (Xs[k + 1]).
