@@ -76,6 +76,49 @@ def test_kat_linear_chirp_on_if_line():
             assert abs((kk + dk[m, kk]) * SR / 4096 - (f0 + (f1 - f0) * tt)) < 1e-3
 
 
+def test_operators_equal_phase_derivatives_of_the_stft():
+    """Independent route to the same quantities: the reassigned coordinates are, by definition
+    (Kodera et al. 1976; Auger & Flandrin 1995 eq. 1-2), the local group delay -dphi/domega and
+    the instantaneous frequency dphi/dt of the STFT.  Here both come from finite differences of
+    the STFT phase — frames one sample apart, and a 32x zero-padded spectrum — on the bench
+    signal (log chirp + two tones + noise), and must agree with the three-window operators of
+    the oracle at every strong bin.  Pins signs, scales and the frame-local phase reference
+    without any analytic model of the signal."""
+    N = 2048
+    x = orc.synth_signal(6 * N, SR, seed=3).astype(np.float64)
+    h, _, _ = orc.windows(N)
+    starts = np.array([1000, 2500, 4000, 5500, 7000])
+    Xh, Xth, Xdh = orc.stft3(x, N, 1, 0, starts.max() + 2)          # hop 1: frame m starts at sample m
+    e, dts, dkb = orc.reassign_operators(Xh, Xth, Xdh, N)
+    k = np.arange(N // 2 + 1)
+    checked = 0
+    errs_t = []
+    for m in starts:
+        strong = (e[m] > e[m].max() * 1e-2) & (k > 2) & (k < N // 2 - 2)      # main lobes: within 20 dB of the peak
+        # instantaneous frequency: central difference of the phase over frames m-1, m+1
+        dphi_dt = np.angle(Xh[m + 1] * np.conj(Xh[m - 1])) / 2.0                   # rad / sample, |.| < pi/2
+        # the principal value sits within pi/2 of the bin's own frequency 2 pi k / N (mod pi)
+        w_bin = 2 * np.pi * k / N
+        dphi_dt = w_bin + (dphi_dt - w_bin + np.pi / 2) % np.pi - np.pi / 2
+        if_bins = dphi_dt * N / (2 * np.pi)
+        err_w = np.abs(if_bins - (k + dkb[m]))[strong]
+        # group delay: central difference of the phase over +-1 bin of a 32x finer frequency grid
+        P = 32
+        Z = np.fft.rfft(x[m:m + N] * h, P * N)
+        dphi_dw = np.angle(Z[P * k[1:-1] + 1] * np.conj(Z[P * k[1:-1] - 1])) / (2 * 2 * np.pi / (P * N))   # samples
+        n_hat = -dphi_dw                                                                              # from the frame start
+        err_t = np.abs((n_hat - N / 2) - dts[m][1:-1])[strong[1:-1]]
+        assert err_w.max() < 2e-3, err_w.max()          # bins   (finite-difference error of a chirp: O(rate^2))
+        assert np.median(err_w) < 1e-4
+        errs_t.append(err_t)
+        checked += int(strong.sum())
+    # samples, of a 2048-sample window.  The difference quotient in frequency breaks down where two
+    # components interfere (the phase turns by pi across a spectral zero), hence quantiles, not the max
+    errs_t = np.concatenate(errs_t)
+    assert np.median(errs_t) < 5e-3 and np.quantile(errs_t, 0.9) < 0.1, (np.median(errs_t), np.quantile(errs_t, 0.9))
+    assert checked > 100
+
+
 def test_energy_conservation_and_drop_rule():
     x = orc.synth_signal(SR, SR, seed=0)
     prm = orc.Params(n_fft=2048, hop=512)
