@@ -757,22 +757,32 @@ stft_reassign_r16_large(const StftArgs a_in) {
         // z[n] = x[n] (1 + j th'[n]); output i0 of butterfly b = b1 + 256 j1 goes to the slot
         // pass B reads it from: Zb[kSI (i0 + R0 j1) + b1]
         {
-            float xr[kUA][R0], tr[kUA][R0];
+            float xr[kUA][R0];
+            float2 w1s[kUA];                                   // W_N^b = (cos, -sin)(2 pi b / N)
 #pragma unroll
-            for (int u = 0; u < kUA; ++u)
+            for (int u = 0; u < kUA; ++u) {
 #pragma unroll
-                for (int j = 0; j < R0; ++j) {
-                    xr[u][j] = __ldg(xs + p + kWT * u + 4096 * j);
-                    tr[u][j] = __ldg(a.thw + p + kWT * u + 4096 * j);
-                }
+                for (int j = 0; j < R0; ++j) xr[u][j] = __ldg(xs + p + kWT * u + 4096 * j);
+                w1s[u] = __ldg(&a.tw[p + kWT * u]);
+            }
             static_for<kUA>([&](auto uc) {
                 constexpr int u = decltype(uc)::value;
+                constexpr int N = C::N;
                 const int b = p + kWT * u;
+                const float2 w1 = w1s[u];
+                // th'[n] = (n - N/2)(2/N)(0.5 - 0.5 cos(2 pi n/N)) at n = b + 4096 j without a table read:
+                // cos(2 pi n/N) = cos(theta_b + 2 pi j/R0) is +-cos / +-sin of the twiddle already in hand,
+                // and (n - N/2)(2/N) is exact in fp32
+                const float bf = (float)b * (2.0f / N);
                 float2 v[R0];
 #pragma unroll
-                for (int j = 0; j < R0; ++j) v[j] = make_float2(xr[u][j], xr[u][j] * tr[u][j]);
+                for (int j = 0; j < R0; ++j) {
+                    const float cs = R0 == 2 ? (j ? -w1.x : w1.x)
+                                             : (j == 0 ? w1.x : j == 1 ? w1.y : j == 2 ? -w1.x : -w1.y);
+                    const float t = (bf + (float)(4096 * j - N / 2) * (2.0f / N)) * fmaf(-0.5f, cs, 0.5f);
+                    v[j] = make_float2(xr[u][j], xr[u][j] * t);
+                }
                 float2* zo = Zb + kSI * (R0 * (b >> 8)) + (b & 255);
-                const float2 w1 = __ldg(&a.tw[b]);                 // W_N^b
                 if constexpr (R0 == 2) {
                     zo[0] = v[0] + v[1];
                     zo[kSI] = cmul2(v[0] - v[1], w1);
@@ -877,20 +887,35 @@ stft_reassign_r16_32k(const StftArgs a_in, float2* __restrict__ scratch_all) {
                         const int n = 2 * (p + kWT * (4 * half + u) + 4096 * j);
                         v[u][j] = make_float2(__ldg(xs + n), __ldg(xs + n + 1));
                     }
-                if (phase) {
+                float2 w1s[4];                                          // W_M^b = W_N^{2b}
 #pragma unroll
-                    for (int u = 0; u < 4; ++u)
+                for (int u = 0; u < 4; ++u) w1s[u] = __ldg(&a.tw[2 * (p + kWT * (4 * half + u))]);
+                if (phase) {
+                    // x th' without a table read: th'[n] = (n - N/2)(2/N)(0.5 - 0.5 cos(2 pi n/N)) at
+                    // n = 2 (b + 4096 j) and n + 1; cos(2 pi n/N) = cos(theta_b + j pi/2) comes from the
+                    // twiddle in hand, the odd sample is one rotation by 2 pi/N further
+                    constexpr float Cd = 0.99999998161642933f, Sd = 1.9174759731070331e-4f;   // cos, sin(2 pi / 32768)
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int b = p + kWT * (4 * half + u);
+                        const float c = w1s[u].x, sn = -w1s[u].y;      // cos, sin(theta_b)
+                        const float bf = (float)(2 * b) * (2.0f / N);
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
-                            const int n = 2 * (p + kWT * (4 * half + u) + 4096 * j);
-                            v[u][j] = mul2(v[u][j], make_float2(__ldg(a.thw + n), __ldg(a.thw + n + 1)));
+                            const float cj_ = j == 0 ? c : j == 1 ? -sn : j == 2 ? -c : sn;     // cos(theta_b + j pi/2)
+                            const float sj_ = j == 0 ? sn : j == 1 ? c : j == 2 ? -sn : -c;     // sin(theta_b + j pi/2)
+                            const float nf = bf + (float)(8192 * j - N / 2) * (2.0f / N);
+                            const float t0 = nf * fmaf(-0.5f, cj_, 0.5f);
+                            const float t1 = (nf + 2.0f / N) * fmaf(-0.5f, fmaf(cj_, Cd, -sj_ * Sd), 0.5f);
+                            v[u][j] = mul2(v[u][j], make_float2(t0, t1));
                         }
+                    }
                 }
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     const int b = p + kWT * (4 * half + u);
                     float2* zo = Zb + kSI * (R0 * (b >> 8)) + (b & 255);
-                    const float2 w1 = __ldg(&a.tw[2 * b]);             // W_M^b
+                    const float2 w1 = w1s[u];                          // W_M^b
                     dft4(v[u][0], v[u][1], v[u][2], v[u][3]);
                     const float2 w2 = cmul2(w1, w1);
                     zo[0] = v[u][0];
