@@ -458,25 +458,39 @@ __device__ __forceinline__ void epilogue(const StftArgs& a, int ch, long long f,
         asm volatile("" : "+l"(fA.pd), "+l"(fA.pk), "+l"(fA.pe), "+l"(fB.pd), "+l"(fB.pk), "+l"(fB.pe));
     }
     constexpr int GC = 2;     // residue pairs per vote: 4 bins, 8 neighbour loads in flight (8 bins spill: measured -10 %)
-    static_for<8 / GC>([&](auto cc) {
-        constexpr int c0 = GC * decltype(cc)::value;
-        float2 xm[2 * GC], xp[2 * GC], A2[2 * GC];
-        bool lv[2 * GC];
-        bool any = false;
+    // Store mode, software-pipelined by hand: the neighbour loads of the next four bins are issued
+    // before the vote and the stores of the current four.  The slow path then reads its two
+    // neighbours again (X is still in shared memory), so the prefetch costs no registers (+1.2 %).
+    // The deposit modes have no stores to hide the loads behind and keep them in program order.
+    constexpr bool kPrefetch = MODE == kStorePoints;
+    float2 nm[2 * GC], np_[2 * GC];
+    auto load_group = [&](int c0) {
 #pragma unroll
         for (int i = 0; i < GC; ++i) {
             const int kA = tA + kRes * (c0 + i), kB = tB + kRes * (c0 + i);
-            xm[2 * i] = Xs[kA]; xp[2 * i] = Xs[kA + 2];
-            xm[2 * i + 1] = Xs[kB]; xp[2 * i + 1] = Xs[kB + 2];
+            nm[2 * i] = Xs[kA]; np_[2 * i] = Xs[kA + 2];
+            nm[2 * i + 1] = Xs[kB]; np_[2 * i + 1] = Xs[kB + 2];
         }
+    };
+    if (kPrefetch) load_group(0);
+    static_for<8 / GC>([&](auto cc) {
+        constexpr int c0 = GC * decltype(cc)::value;
+        float2 A2[2 * GC];
+        bool lv[2 * GC];
+        bool any = false;
+        if (!kPrefetch) load_group(c0);
+        float2 cm[2 * GC], cp[2 * GC];          // the current four's neighbours for the slow path (deposit modes)
+#pragma unroll
+        for (int i = 0; i < 2 * GC; ++i) { cm[i] = nm[i]; cp[i] = np_[i]; }
 #pragma unroll
         for (int i = 0; i < GC; ++i) {
-            A2[2 * i] = hann_stencil(xa[c0 + i], xm[2 * i], xp[2 * i]);                  // 2 X_h
-            A2[2 * i + 1] = hann_stencil(xb[c0 + i], xm[2 * i + 1], xp[2 * i + 1]);
+            A2[2 * i] = hann_stencil(xa[c0 + i], nm[2 * i], np_[2 * i]);                  // 2 X_h
+            A2[2 * i + 1] = hann_stencil(xb[c0 + i], nm[2 * i + 1], np_[2 * i + 1]);
             lv[2 * i] = bin_energy<N>(A2[2 * i]) > a.gate_lin;
             lv[2 * i + 1] = bin_energy<N>(A2[2 * i + 1]) > a.gate_lin;
             any = any || lv[2 * i] || lv[2 * i + 1];
         }
+        if constexpr (kPrefetch && c0 + GC < 8) load_group(c0 + GC);
         if (!__any_sync(0xffffffffu, any)) {
 #pragma unroll
             for (int i = 0; i < GC; ++i) {
@@ -489,14 +503,15 @@ __device__ __forceinline__ void epilogue(const StftArgs& a, int ch, long long f,
             // one of them spends on atomics here, the other three wait; +3.9 % on the image path)
 #pragma unroll
             for (int i = 0; i < GC; ++i) {
+                const int kA = tA + kRes * (c0 + i), kB = tB + kRes * (c0 + i);
                 if (MODE == kStorePoints || __any_sync(0xffffffffu, lv[2 * i]))
-                    bin_tail<N, MODE>(a, fA, owner, lv[2 * i], tA + kRes * (c0 + i), kRes * (c0 + i), g.tAf + (float)(kRes * (c0 + i)),
-                                      A2[2 * i], xm[2 * i], xp[2 * i], ta[c0 + i]);
+                    bin_tail<N, MODE>(a, fA, owner, lv[2 * i], kA, kRes * (c0 + i), g.tAf + (float)(kRes * (c0 + i)),
+                                      A2[2 * i], kPrefetch ? Xs[kA] : cm[2 * i], kPrefetch ? Xs[kA + 2] : cp[2 * i], ta[c0 + i]);
                 else
                     bin_dead<MODE>(fA, owner, kRes * (c0 + i));
                 if (MODE == kStorePoints || __any_sync(0xffffffffu, lv[2 * i + 1]))
-                    bin_tail<N, MODE>(a, fB, owner, lv[2 * i + 1], tB + kRes * (c0 + i), kRes * (c0 + i), g.tBf + (float)(kRes * (c0 + i)),
-                                      A2[2 * i + 1], xm[2 * i + 1], xp[2 * i + 1], tb[c0 + i]);
+                    bin_tail<N, MODE>(a, fB, owner, lv[2 * i + 1], kB, kRes * (c0 + i), g.tBf + (float)(kRes * (c0 + i)),
+                                      A2[2 * i + 1], kPrefetch ? Xs[kB] : cm[2 * i + 1], kPrefetch ? Xs[kB + 2] : cp[2 * i + 1], tb[c0 + i]);
                 else
                     bin_dead<MODE>(fB, owner, kRes * (c0 + i));
             }
