@@ -543,7 +543,10 @@ static ems_status stream_capture(ems_handle* h) {
     }
     stream_ingest_kernel<<<(H * C + 255) / 256, 256, 0, h->stream>>>(sa);
     ems_status ls = launch_stft(h, a);
-    stream_finish_kernel<<<C, 1024, 0, h->stream>>>(sa);
+    if (sa.agc_strength > 0.f)
+        stream_finish_kernel<<<dim3(C, 1), 1024, 0, h->stream>>>(sa);          // channel peak = one block reduction
+    else
+        stream_finish_kernel<<<dim3(C, (B + 255) / 256), 256, 0, h->stream>>>(sa);
     cudaError_t ce = cudaStreamEndCapture(h->stream, &g);
     h->stream = user;
     h->launches -= 1;                                  // counted per push below, not at capture

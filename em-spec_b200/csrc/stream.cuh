@@ -38,7 +38,9 @@ __global__ void stream_ingest_kernel(const StreamArgs s) {
     }
 }
 
-// One block per channel finishes the push.  Column cf = f - R can no longer receive energy once
+// Finishes the push: grid (channels, slices).  With the AGC on a channel is one block (its peak is a
+// block reduction); without it the bins of a channel are sliced over gridDim.y blocks, which cuts
+// the latency of this last kernel of the push.  Column cf = f - R can no longer receive energy once
 // frame f is in: shape it (weights, EMA), take its peak for the AGC, emit the colour index
 // straight into the caller-visible pinned column (mapped host memory: no copy node), clear
 // the slot for column cf + ring_cols.  The last block to finish advances the AGC level and the
@@ -50,10 +52,11 @@ stream_finish_kernel(const StreamArgs s) {
     const long long i = s.sstate[0];
     const long long cf = i + 1 - s.M - s.R;
     const int ch = blockIdx.x, t = threadIdx.x;
+    const int k0 = blockIdx.y * blockDim.x + t, kstep = gridDim.y * blockDim.x;
     if (cf >= 0) {
         const int slot = (int)(cf % s.ring_cols);
         float peak = 0.f;
-        for (int k = t; k < s.B; k += blockDim.x) {
+        for (int k = k0; k < s.B; k += kstep) {
             const int e = ch * s.B + k;
             const long long o = ((long long)ch * s.ring_cols + slot) * s.B + k;
             float E = acc_load(s.acc, s.acc_is_u64, o) * s.weight[k];
@@ -86,7 +89,7 @@ stream_finish_kernel(const StreamArgs s) {
         }
         PostArgs pa{};
         pa.db_floor = s.db_floor; pa.inv_range = s.inv_range; pa.gate_db = s.gate_db;
-        for (int k = t; k < s.B; k += blockDim.x) {
+        for (int k = k0; k < s.B; k += kstep) {
             const int e = ch * s.B + k;
             s.out[e] = s.agc_strength > 0.f ? colour_index(s.etmp[e], scale, pa) : colour_index(s.etmp[e], pa);
         }
@@ -94,7 +97,7 @@ stream_finish_kernel(const StreamArgs s) {
     __syncthreads();
     if (t == 0) {
         __threadfence();
-        if (atomicAdd(reinterpret_cast<unsigned long long*>(s.sstate + 1), 1ull) == (unsigned long long)gridDim.x - 1) {
+        if (atomicAdd(reinterpret_cast<unsigned long long*>(s.sstate + 1), 1ull) == (unsigned long long)(gridDim.x * gridDim.y) - 1) {
             s.sstate[1] = 0;
             s.sstate[0] = i + 1;
         }
