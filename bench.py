@@ -178,6 +178,25 @@ def peaks():
 
 
 # ------------------------------------------------------------------ arms
+# stdout carries exactly one JSON line: file descriptor 1 is pointed at stderr for the whole run
+# (NCCL's version banner and any other library chatter go there) and the line is written to the
+# saved descriptor at the end.
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit_json(line):
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, (json.dumps(line) + "\n").encode())
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -205,7 +224,7 @@ def run_reference(args):
         "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "stand-in: EM-Spec ships no runnable source; this is the oracle port",
     }
-    print(json.dumps(line), flush=True)
+    emit_json(line)
     return 0
 
 
@@ -222,8 +241,6 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        # NCCL's own log lines (its version banner included) go to stderr: stdout carries the one JSON line
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     def barrier():
@@ -439,7 +456,7 @@ def run_ours(args):
             "cpu_baseline": cpu, "e2e": e2e, "pipeline_u8": pipe, "e2e_display_rows": e2e_display, "stream_latency": stream, "nfft_sweep": sweep, "gpu_launches": int(launches),
             "clocks": clocks,
         }
-        print(json.dumps(line), flush=True)
+        emit_json(line)
     eng.close()
     if world > 1:
         dist.destroy_process_group()
@@ -464,6 +481,7 @@ def main():
     ap.add_argument("--no-sweep", action="store_true")
     ap.add_argument("--stream-pushes", type=int, default=5000)
     args = ap.parse_args()
+    claim_stdout()
     return run_reference(args) if args.impl == "reference" else run_ours(args)
 
 
