@@ -682,15 +682,18 @@ stft_reassign_r16(const StftArgs a_in, const int tile_T) {
             const bool last_frame = fi0 + kWorkers * kG >= nf;
 
             // ================= pass 1: radix-R butterflies b = p + kWT u on z[n] = x[n] (1 + j th'[n])
+            // (all 32 samples of the thread are requested before the first butterfly starts)
+            float xr[kU][R];
+#pragma unroll
+            for (int u = 0; u < kU; ++u)
+#pragma unroll
+                for (int j = 0; j < R; ++j) xr[u][j] = xs[p + kWT * u + 256 * j];   // n = b + 256 j
             static_for<kU>([&](auto uc) {
                 constexpr int u = decltype(uc)::value;
                 const int b = p + kWT * u;
                 float2 v[R];
 #pragma unroll
-                for (int j = 0; j < R; ++j) {
-                    const float x = xs[b + 256 * j];                   // n = b + 256 j
-                    v[j] = make_float2(x, x * thw[u][j]);
-                }
+                for (int j = 0; j < R; ++j) v[j] = make_float2(xr[u][j], xr[u][j] * thw[u][j]);
                 dftR(v);
                 twiddle_store_rows<R, kSI>(v, Ztab, b, Zb + b + (b >> 4) * (kS16 - 16));
             });
