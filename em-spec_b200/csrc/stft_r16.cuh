@@ -249,16 +249,19 @@ __device__ __noinline__ void deposit_point(const DepositCtx d, int ch, long long
 // Auger-Flandrin operators and the emit — same decisions as reassign_emit (stft_generic.cuh).
 //   xk, xm, xp = 2 X[k], 2 X[k-1], 2 X[k+1];  t2 = 2 X_th'[k]
 // Split in three so that the epilogue can run the gate of all its bins before any branch:
-//   hann_stencil  2 X_h from the three rectangular bins
+//   hann_stencil  4 X_h from the three rectangular bins (one add, one fused multiply-add: every
+//                 scale from here on is a power of two, folded into the constants, and exact)
+//   bin_power     |4 X_h|^2; the gate compares it with gate * N^2 (energy = |4 X_h|^2 / N^2)
 //   bin_dead      a bin nobody in the warp keeps: zeros in store mode, nothing otherwise
 //   bin_tail      reassignment operators, drop rule, store / deposit (predicated, no divergence)
 __device__ __forceinline__ float2 hann_stencil(float2 xk, float2 xm, float2 xp) {
-    return fma2(xm + xp, make_float2(-0.25f, -0.25f), mul2(xk, make_float2(0.5f, 0.5f)));
+    return fma2(xm + xp, make_float2(-0.5f, -0.5f), xk);
+}
+__device__ __forceinline__ float bin_power(float2 A4) {
+    return __fmaf_rn(A4.x, A4.x, __fmul_rn(A4.y, A4.y));
 }
 template <int N>
-__device__ __forceinline__ float bin_energy(float2 A2) {
-    return __fmaf_rn(A2.x, A2.x, __fmul_rn(A2.y, A2.y)) * (float)(4.0 / ((double)N * (double)N));
-}
+__device__ __forceinline__ float gate_power(const StftArgs& a) { return a.gate_lin * (float)N * (float)N; }
 // `off` is the bin's index relative to the row pointers of fc (k itself, or a compile-time
 // multiple of the residue stride when fc points at the thread's residue: the stores then take
 // immediate offsets from six live base pointers instead of a 64-bit address computation each).
@@ -270,19 +273,19 @@ __device__ __forceinline__ void bin_dead(const FrameCtx& fc, bool owner, int off
 }
 template <int N, int MODE>
 __device__ __forceinline__ void bin_tail(const StftArgs& a, const FrameCtx& fc, bool owner, bool live, int k, int off,
-                                         float kf, float2 A2, float2 xm, float2 xp, float2 t2) {
+                                         float kf, float2 A4, float2 xm, float2 xp, float2 t2) {
     // explicit fused multiply-adds: every instantiation (store / deposit, every n_fft) rounds alike,
     // so a grid deposited by the fused kernel equals the scatter of the stored points bit for bit
-    const float p2 = __fmaf_rn(A2.x, A2.x, __fmul_rn(A2.y, A2.y));
-    const float e = p2 * (float)(4.0 / ((double)N * (double)N));
+    const float p4 = bin_power(A4);
+    const float e = p4 * (float)(1.0 / ((double)N * (double)N));
     bool ok = live;
     float dtc = 0.f, dk = 0.f, rc = 0.f, wh = kf;
     if (a.reassign) {
         const float2 d = xm - xp;                                        // 2 X_dh' = d / (2j)
         const float2 D2 = make_float2(0.5f * d.y, -0.5f * d.x);
-        const float inv = rcp_approx(p2);
-        const float dts = __fmaf_rn(t2.x, A2.x, __fmul_rn(t2.y, A2.y)) * inv * (float)(N / 2);   // samples
-        dk = __fmaf_rn(D2.y, A2.x, -__fmul_rn(D2.x, A2.y)) * inv * -0.5f;                          // bins
+        const float inv = rcp_approx(p4);
+        const float dts = __fmaf_rn(t2.x, A4.x, __fmul_rn(t2.y, A4.y)) * inv * (float)N;          // samples
+        dk = __fmaf_rn(D2.y, A4.x, -__fmul_rn(D2.x, A4.y)) * inv * -1.0f;                          // bins
         dtc = dts * a.inv_hop;
         rc = rintf(dtc);
         wh = kf + dk;
@@ -303,8 +306,8 @@ __device__ __forceinline__ void bin_tail(const StftArgs& a, const FrameCtx& fc, 
 template <int N, int MODE>
 __device__ __forceinline__ void bin_emit(const StftArgs& a, const FrameCtx& fc, bool owner, int k,
                                          float kf, float2 xk, float2 xm, float2 xp, float2 t2) {
-    const float2 A2 = hann_stencil(xk, xm, xp);                          // 2 X_h
-    const bool live = bin_energy<N>(A2) > a.gate_lin;
+    const float2 A2 = hann_stencil(xk, xm, xp);                          // 4 X_h
+    const bool live = bin_power(A2) > gate_power<N>(a);
     if (!__any_sync(0xffffffffu, live)) { bin_dead<MODE>(fc, owner, k); return; }
     bin_tail<N, MODE>(a, fc, owner, live, k, k, kf, A2, xm, xp, t2);
 }
@@ -463,6 +466,7 @@ __device__ __forceinline__ void epilogue(const StftArgs& a, int ch, long long f,
     // neighbours again (X is still in shared memory), so the prefetch costs no registers (+1.2 %).
     // The deposit modes have no stores to hide the loads behind and keep them in program order.
     constexpr bool kPrefetch = MODE == kStorePoints;
+    const float gate_p = gate_power<N>(a);
     float2 nm[2 * GC], np_[2 * GC];
     auto load_group = [&](int c0) {
 #pragma unroll
@@ -484,10 +488,10 @@ __device__ __forceinline__ void epilogue(const StftArgs& a, int ch, long long f,
         for (int i = 0; i < 2 * GC; ++i) { cm[i] = nm[i]; cp[i] = np_[i]; }
 #pragma unroll
         for (int i = 0; i < GC; ++i) {
-            A2[2 * i] = hann_stencil(xa[c0 + i], nm[2 * i], np_[2 * i]);                  // 2 X_h
+            A2[2 * i] = hann_stencil(xa[c0 + i], nm[2 * i], np_[2 * i]);                  // 4 X_h
             A2[2 * i + 1] = hann_stencil(xb[c0 + i], nm[2 * i + 1], np_[2 * i + 1]);
-            lv[2 * i] = bin_energy<N>(A2[2 * i]) > a.gate_lin;
-            lv[2 * i + 1] = bin_energy<N>(A2[2 * i + 1]) > a.gate_lin;
+            lv[2 * i] = bin_power(A2[2 * i]) > gate_p;
+            lv[2 * i + 1] = bin_power(A2[2 * i + 1]) > gate_p;
             any = any || lv[2 * i] || lv[2 * i + 1];
         }
         if constexpr (kPrefetch && c0 + GC < 8) load_group(c0 + GC);
@@ -1045,7 +1049,7 @@ stft_reassign_r16_32k(const StftArgs a_in, float2* __restrict__ scratch_all) {
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         A2[i] = hann_stencil(xk[i], xm[i], xp[i]);
-                        lv[i] = bin_energy<N>(A2[i]) > a.gate_lin;
+                        lv[i] = bin_power(A2[i]) > gate_power<N>(a);
                         any = any || lv[i];
                     }
                     if (!__any_sync(0xffffffffu, any)) {
