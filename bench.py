@@ -164,7 +164,7 @@ def synth_device(S: int, seed: int, device):
 
 # dram__bytes_read.sum + dram__bytes_write.sum of stft_reassign_r16<store>, one `ncu --set full`
 # capture of a 224,969-frame launch (profiles/r01_ncu_stft_reassign_r16.txt): 5.6072 GB
-NCU_DRAM_BYTES_PER_FRAME = (128.427520e6 + 5.482475e9) / 224969
+NCU_DRAM_BYTES_PER_FRAME = (129.329152e6 + 5.481495e9) / 224969
 
 
 def peaks():
