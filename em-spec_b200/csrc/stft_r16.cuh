@@ -79,6 +79,13 @@ struct Cfg {
         return t > kMaxTile ? kMaxTile : t;
     }
     __host__ __device__ static constexpr int zpos(int i, int b) { return kSI * i + b + (b >> 4) * (kS16 - 16); }
+    static_assert(kThreads % kWorkerThreads == 0, "workers tile the CTA");
+    static_assert(kZBuf >= zpos(R - 1, 255) + 1, "Z buffer holds every sub-FFT");
+    static_assert(kTileFloats >= N && kTileFloats % 4 == 0, "each tile buffer holds at least one frame, 16-byte granular");
+    static_assert(kFixedBytes % 16 == 0, "tile buffers (TMA / cp.async destinations) start on a 16-byte boundary");
+    static_assert(kFixedBytes + 2 * kTileFloats * 4 + kSyncBytes <= kMaxSmem, "shared memory");
+    static_assert(kG == 1 || kSlot % 16 == 8, "frames of one half-warp sit in different banks");
+    static_assert(16 + 8 + 4 * kWorkers <= kSyncBytes, "mbarriers, release counters and refill flags fit their block");
 };
 
 template <int... Is, class Fn>
