@@ -369,15 +369,28 @@ __device__ __forceinline__ void twiddle_store_rows(float2 (&v)[RR], const float2
 
 // Pass 2: sub-FFTs of length 256, butterflies (i1, q2), (i1, q2 + 8), software-pipelined by
 // hand: the second butterfly's loads fly while the first computes.
+// n_fft = 256 has no pass 1 (R = 1): its two butterflies take their inputs straight from the tile,
+// z[n] = x[n] (1 + j th'[n]) at n = q2 + 8 u, u even for the first butterfly, odd for the second
+// (xs, thw given), and only their outputs go through the Z buffer.
 template <int kSI, int kS16>
-__device__ __forceinline__ void pass2(float2* Zb, const float2* T2, const Geom& g) {
+__device__ __forceinline__ void pass2(float2* Zb, const float2* T2, const Geom& g, const float* xs = nullptr,
+                                      const float (*thw)[1] = nullptr) {
     float2* bz0 = Zb + kSI * g.i1 + g.q2;
     float2* bz1 = bz0 + 8;
     float2 v0[16], v1[16];
+    if (xs) {
 #pragma unroll
-    for (int j = 0; j < 16; ++j) v0[j] = bz0[kS16 * j];
+        for (int j = 0; j < 16; ++j) {
+            const float x0 = xs[g.q2 + 16 * j], x1 = xs[g.q2 + 8 + 16 * j];
+            v0[j] = make_float2(x0, x0 * thw[2 * j][0]);
+            v1[j] = make_float2(x1, x1 * thw[2 * j + 1][0]);
+        }
+    } else {
 #pragma unroll
-    for (int j = 0; j < 16; ++j) v1[j] = bz1[kS16 * j];
+        for (int j = 0; j < 16; ++j) v0[j] = bz0[kS16 * j];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v1[j] = bz1[kS16 * j];
+    }
     // twiddles W_256^{p2 i}: the 16 of a butterfly are contiguous, two per 128-bit load (the whole
     // warp reads two addresses: one wavefront per load); loaded before the butterfly they belong
     // to, so that their latency hides behind its arithmetic
@@ -692,6 +705,17 @@ stft_reassign_r16(const StftArgs a_in, const int tile_T) {
             const long long f = f0 + fi;
             const bool last_frame = fi0 + kWorkers * kG >= nf;
 
+            if constexpr (R == 1) {
+                // no pass 1: pass 2 reads the tile; the tile is released after it
+                pass2<kSI, kS16>(Zb, T2, g, xs, thw);
+                worker_bar<kWT>(w);
+                if (last_frame && wl == 0) release_tile(buf);
+                float2 xa[8], xb[8], ta[8], tb[8];
+                pass3_untangle<R>(Zb, Xs, Sc, g, xa, xb, ta, tb);
+                worker_bar<kWT>(w);
+                if (last_frame && refill[w]) refill_tile(buf, ti + 2);
+                epilogue<R, MODE>(a, ch, f, Xs, Sc, g, xa, xb, ta, tb, active);
+            } else {
             // ================= pass 1: radix-R butterflies b = p + kWT u on z[n] = x[n] (1 + j th'[n])
             // (all 32 samples of the thread are requested before the first butterfly starts)
             float xr[kU][R];
@@ -720,6 +744,7 @@ stft_reassign_r16(const StftArgs a_in, const int tile_T) {
             worker_bar<kWT>(w);      // X visible; the Z buffer is free for the next frame's pass 1
 
             epilogue<R, MODE>(a, ch, f, Xs, Sc, g, xa, xb, ta, tb, active);
+            }
         }
     }
 }
