@@ -332,15 +332,21 @@ def run_ours(args):
             heng.process_host(pcm_host, index_out=idx_host)
         barrier()
         t0 = time.perf_counter()
+        step_s = []
         for _ in range(args.steps):
-            heng.process_host(pcm_host, index_out=idx_host)
+            ts = time.perf_counter()
+            heng.process_host(pcm_host, index_out=idx_host)      # returns with the image in host memory
+            step_s.append(time.perf_counter() - ts)
         torch.cuda.synchronize()
+        wall_s = time.perf_counter() - t0        # the K steps, not the teardown (freeing 26 GB can take a second)
         heng.close()
-        wall = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        wall = torch.tensor([wall_s], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(wall, op=dist.ReduceOp.MAX)
         e2e = {"value": frames_all * args.steps / wall.item(), "unit": UNIT,
                "h2d_bytes_per_step": S * 4 * world, "d2h_bytes_per_step": F * B * world,
+               "step_ms": {"min": 1e3 * min(step_s), "median": 1e3 * sorted(step_s)[len(step_s) // 2],
+                           "max": 1e3 * max(step_s), "first": 1e3 * step_s[0]},
                "what": "ems_process_host: pinned host fp32 PCM -> pinned host u8 colour-index "
                        "image [F][B] (a1-a5), chunked copies overlapped with compute"}
 
