@@ -14,8 +14,9 @@
 // Layout of the work (DESIGN.md "K1-K3"):
 //   * persistent CTAs, one per SM, 48/R workers x 8R threads (3 x 128 at n_fft = 4096); a CTA
 //     walks tiles of T consecutive frames whose samples ((T-1)*hop + N floats) sit once in
-//     shared memory, double-buffered with cp.async; buffers are handed over through an
-//     mbarrier and a release counter, never a CTA-wide barrier, so the workers run out of phase;
+//     shared memory, double-buffered with cp.async (one TMA bulk copy per tile for large aligned
+//     hops); buffers are handed over through an mbarrier and a release counter, never a CTA-wide
+//     barrier, so the workers run out of phase;
 //   * a worker analyses one frame at a time, entirely on-chip: Z as R x 16 x 16 — pass 1 is
 //     32/R radix-R butterflies per thread straight from the tile, passes 2 and 3 two radix-16
 //     butterflies per thread — in packed fp32x2 arithmetic, in-place decimation-in-frequency
