@@ -11,6 +11,8 @@
 #include <new>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "common.cuh"
 #include "scatter_post.cuh"
 #include "stft_generic.cuh"
@@ -443,10 +445,17 @@ static ems_status reset_carry(ems_handle* h) {
     return EMS_OK;
 }
 
-static void stage_begin(ems_handle* h, int st) { cudaEventRecord(h->ev[st][0], h->stream); }
+// Stage brackets: CUDA events for ems_stage_ms and an NVTX range (header-only NVTX3: a no-op
+// unless a profiler is attached) so that timelines show a1-a3 / a4 / a5 by name.
+static const char* const kStageName[EMS_STAGE_COUNT] = {"ems:stft+reassign", "ems:scatter", "ems:post"};
+static void stage_begin(ems_handle* h, int st) {
+    nvtxRangePushA(kStageName[st]);
+    cudaEventRecord(h->ev[st][0], h->stream);
+}
 static void stage_end(ems_handle* h, int st) {
     cudaEventRecord(h->ev[st][1], h->stream);
     h->ev_valid[st] = true;
+    nvtxRangePop();
 }
 
 static ems_status finish(ems_handle* h) {
