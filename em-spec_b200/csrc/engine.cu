@@ -329,6 +329,17 @@ static PostArgs make_post(ems_handle* h, long long F, float* grid, uint8_t* inde
 
 static ems_status clear_flags(ems_handle* h, long long F, long long c0, long long c1, int B);
 
+// Zero-fills columns [col_begin, col_end) of every channel of a [channels][F][col_bytes] array:
+// one memset when the range is the whole stream, one pitched memset otherwise (never one call
+// per channel: a batch maps clips to channels, up to 65535 of them).
+static cudaError_t zero_cols(ems_handle* h, void* base, size_t col_bytes, const PostArgs& p) {
+    const size_t ncols = (size_t)(p.col_end - p.col_begin);
+    char* b0 = (char*)base + (size_t)p.col_begin * col_bytes;
+    if (p.channels == 1 || ncols == (size_t)p.F)
+        return cudaMemsetAsync(b0, 0, (p.channels - 1) * (size_t)p.F * col_bytes + ncols * col_bytes, h->stream);
+    return cudaMemset2DAsync(b0, (size_t)p.F * col_bytes, 0, ncols * col_bytes, (size_t)p.channels, h->stream);
+}
+
 // Post-pass over columns [col_begin, col_end) of every channel; h->carry holds the EMA
 // state entering col_begin and leaves with the state after col_end - 1.
 static ems_status run_post(ems_handle* h, PostArgs p) {
@@ -342,9 +353,7 @@ static ems_status run_post(ems_handle* h, PostArgs p) {
         ems_status s = ensure(h, h->colscale, (size_t)p.channels * p.F * sizeof(float));
         if (s != EMS_OK) return s;
         p.colscale = (float*)h->colscale.p;
-        for (int ch = 0; ch < p.channels; ++ch)
-            EMS_CUDA(h, cudaMemsetAsync(p.colscale + (size_t)ch * p.F + p.col_begin, 0,
-                                        (size_t)ncols * sizeof(float), h->stream));
+        EMS_CUDA(h, zero_cols(h, p.colscale, sizeof(float), p));
     }
     auto agc_scan = [&]() {
         agc_scan_kernel<<<p.channels, 1024, 0, h->stream>>>(p.colscale, (float*)h->agc_level.p, p.F,
@@ -354,11 +363,8 @@ static ems_status run_post(ems_handle* h, PostArgs p) {
     };
     if (!ema) {
         // no recurrence along time: zero-fill the outputs, then visit only the dirty blocks
-        for (int ch = 0; ch < p.channels; ++ch) {
-            const size_t off = ((size_t)ch * p.F + p.col_begin) * p.B, cnt = (size_t)ncols * p.B;
-            if (p.index) EMS_CUDA(h, cudaMemsetAsync(p.index + off, 0, cnt, h->stream));
-            if (p.grid) EMS_CUDA(h, cudaMemsetAsync(p.grid + off, 0, cnt * sizeof(float), h->stream));
-        }
+        if (p.index) EMS_CUDA(h, zero_cols(h, p.index, (size_t)p.B, p));
+        if (p.grid) EMS_CUDA(h, zero_cols(h, p.grid, (size_t)p.B * sizeof(float), p));
         const dim3 g((unsigned)((ncols + 255) / 256), p.channels * p.NB);
         if (agc) {
             post_sparse_kernel<<<g, 256, 0, h->stream>>>(p, 1);
@@ -452,6 +458,7 @@ static void stage_begin(ems_handle* h, int st) {
     nvtxRangePushA(kStageName[st]);
     cudaEventRecord(h->ev[st][0], h->stream);
 }
+static void stage_abort() { nvtxRangePop(); }      // error return between stage_begin and stage_end
 static void stage_end(ems_handle* h, int st) {
     cudaEventRecord(h->ev[st][1], h->stream);
     h->ev_valid[st] = true;
@@ -685,6 +692,9 @@ ems_status ems_update_display(ems_handle* h, const ems_params* p) {
 
 ems_status ems_set_stream(ems_handle* h, void* s) {
     if (!h) return EMS_ERR_INVALID_ARG;
+    // work queued on the old stream may still use scratch that the next call on the new stream
+    // reallocates or overwrites: drain it first
+    if (h->stream != (cudaStream_t)s) EMS_CUDA(h, cudaStreamSynchronize(h->stream));
     h->stream = (cudaStream_t)s;   // NULL is the CUDA default stream, taken literally
     return EMS_OK;
 }
@@ -725,7 +735,7 @@ ems_status ems_process_points(ems_handle* h, const float* pcm, size_t S, float* 
     a.dt_cols = dt_cols; a.dk_bins = dk_bins; a.energy = energy; a.mode = kStorePoints;
     stage_begin(h, EMS_STAGE_POINTS);
     ems_status s = launch_stft(h, a);
-    if (s != EMS_OK) return s;
+    if (s != EMS_OK) { stage_abort(); return s; }
     stage_end(h, EMS_STAGE_POINTS);
     return finish(h);
 }
@@ -753,10 +763,13 @@ ems_status ems_scatter_points(ems_handle* h, const float* dt_cols, const float* 
         dt_cols, dk_bins, energy, h->acc.p, det, (unsigned char*)h->flags.p, F, B, C, R,
         wa.warp_mode, wa.warp_a, wa.warp_c, wa.inv_half);
     ++h->launches;
-    EMS_CUDA(h, cudaGetLastError());
+    if (cudaError_t le = cudaGetLastError(); le != cudaSuccess) {
+        stage_abort();
+        return fail(h, EMS_ERR_CUDA, "scatter_points_kernel: %s", cudaGetErrorString(le));
+    }
     stage_end(h, EMS_STAGE_SCATTER);
     stage_begin(h, EMS_STAGE_POST);
-    if ((s = run_post(h, make_post(h, F, grid, index))) != EMS_OK) return s;
+    if ((s = run_post(h, make_post(h, F, grid, index))) != EMS_OK) { stage_abort(); return s; }
     h->acc_clean = true;
     stage_end(h, EMS_STAGE_POST);
     return finish(h);
@@ -779,10 +792,10 @@ ems_status ems_process_grid(ems_handle* h, const float* pcm, size_t S, float* gr
     StftArgs a = make_args(h, pcm, S, F);
     a.acc = h->acc.p; a.flags = (unsigned char*)h->flags.p; a.mode = det ? kDepositU64 : kDepositF32;
     stage_begin(h, EMS_STAGE_POINTS);
-    if ((s = launch_stft(h, a)) != EMS_OK) return s;
+    if ((s = launch_stft(h, a)) != EMS_OK) { stage_abort(); return s; }
     stage_end(h, EMS_STAGE_POINTS);
     stage_begin(h, EMS_STAGE_POST);
-    if ((s = run_post(h, make_post(h, F, grid, index))) != EMS_OK) return s;
+    if ((s = run_post(h, make_post(h, F, grid, index))) != EMS_OK) { stage_abort(); return s; }
     h->acc_clean = true;
     stage_end(h, EMS_STAGE_POST);
     return finish(h);
@@ -1024,7 +1037,8 @@ ems_status ems_stream_load(ems_handle* h, const void* blob, size_t bytes) {
     const StreamBlobHeader mine = blob_header(h);
     if (b.magic != kBlobMagic || b.abi != mine.abi || b.n_fft != mine.n_fft || b.hop != mine.hop ||
         b.channels != mine.channels || b.rows != mine.rows || b.det != mine.det ||
-        b.ring_bytes != mine.ring_bytes || b.acc_bytes != mine.acc_bytes || bytes < blob_size(b) ||
+        b.ring_bytes != mine.ring_bytes || b.acc_bytes != mine.acc_bytes ||
+        b.carry_bytes != mine.carry_bytes || b.agc_bytes != mine.agc_bytes || bytes < blob_size(mine) ||
         b.pushes < 0)
         return fail(h, EMS_ERR_INVALID_ARG, "stream blob does not match this handle");
     auto& st = h->st;

@@ -27,11 +27,8 @@ scatter_points_kernel(const float* __restrict__ dt_cols, const float* __restrict
         const int row = out_row(warp_mode, warp_a, warp_c, inv_half, k, dk, (float)k + dk);
         if (col < 0 || col >= F || row < 0 || row >= rows) continue;   // caller-made points
         const long long o = (ch * F + col) * rows + row;
-        if (acc_is_u64)
-            atomicAdd(reinterpret_cast<unsigned long long*>(acc) + o,
-                      fix_energy(e));
-        else
-            atomicAdd(reinterpret_cast<float*>(acc) + o, e);
+        if (acc_is_u64) red_add_u64(reinterpret_cast<unsigned long long*>(acc) + o, fix_energy(e));
+        else red_add_f32(reinterpret_cast<float*>(acc) + o, e);
         flags[flag_index((int)ch, F, rows, col, row)] = 1;
     }
 }

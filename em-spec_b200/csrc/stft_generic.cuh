@@ -98,7 +98,8 @@ __device__ __forceinline__ void reassign_emit(const StftArgs& a, int ch,
         wh = (float)k + dk;
         const float rc = rintf(dtc);
         col = f + (long long)rc;
-        ok = (fabsf(dts) <= (float)(N / 2)) && (wh >= -0.5f) && (wh <= (float)(N / 2) + 0.5f) &&
+        const float rowf = (float)k + rintf(dk);     // the row the point lands in decides (exact in fp32)
+        ok = (fabsf(dts) <= (float)(N / 2)) && (rowf >= 0.f) && (rowf <= (float)(N / 2)) &&
              (col >= 0) && (col < a.F);
         if (!ok) { dtc = 0.f; dk = 0.f; }
     }

@@ -297,7 +297,10 @@ __device__ __forceinline__ void bin_tail(const StftArgs& a, const FrameCtx& fc, 
         dtc = dts * a.inv_hop;
         rc = rintf(dtc);
         wh = kf + dk;
-        ok = live && (fabsf(dts) <= (float)(N / 2)) && (wh >= -0.5f) && (wh <= (float)(N / 2) + 0.5f) &&
+        // the row the point lands in, k + rint(dk), decides (exact: two small integers in fp32); a test on
+        // wh = k + dk would round in fp32 and let a point at N/2 + 0.5 through to row N/2 + 1
+        const float rowf = kf + rintf(dk);
+        ok = live && (fabsf(dts) <= (float)(N / 2)) && (rowf >= 0.f) && (rowf <= (float)(N / 2)) &&
              (rc >= fc.lo) && (rc <= fc.hi);
         dtc = ok ? dtc : 0.f;
         dk = ok ? dk : 0.f;

@@ -28,8 +28,9 @@ Conventions (SURVEY.md §7 "Sign conventions", §8c):
   points are reported as displacements (dt/H columns, dk bins) from (m, k) so that
   fp32 keeps full precision on hour-long streams;
   a point is dropped (energy 0, zero displacement) when e <= gate, |dt| > N/2,
-  w^ outside [-0.5, N/2 + 0.5] (its nearest bin would leave the spectrum; the half-bin margin
-  keeps DC and Nyquist energy, whose w^ sits exactly on 0 and N/2, off a knife edge),
+  its nearest bin k + rint(dk) outside [0, N/2] (w^ within half a bin of the spectrum: DC and
+  Nyquist energy, whose w^ sits exactly on 0 and N/2, stay off a knife edge; the test is on the
+  rounded row itself so that it is exact in fp32 and a kept point can never leave the grid),
   or m + rint(dt/H) outside [0, F-1];
   nearest-cell deposit at (m + rint(dt/H), k + rint(dk)), round-half-even (np.rint / rintf).
 Display shaping (/root/reference/README.md:46-51): gain, low-end boost, smoothing,
@@ -124,6 +125,17 @@ def reassign_operators(Xh, Xth, Xdh, n_fft: int):
     return e, dt, dk
 
 
+def keep_mask(e, dt, dk, m, k, F: int, prm: Params):
+    """The drop rule (SURVEY.md §7 "Out-of-support points"; header of this file): a point of frame m,
+    bin k with energy e, dt [samples], dk [bins] is kept iff it clears the gate, stays inside the
+    window support and its nearest cell (m + rint(dt/H), k + rint(dk)) lies on the grid."""
+    N, H = prm.n_fft, prm.hop
+    col = m + np.rint(dt / H)
+    row = k + np.rint(dk)
+    return (e > prm.gate_lin) & (np.abs(dt) <= N / 2) & (row >= 0) & (row <= N / 2) \
+        & (col >= 0) & (col <= F - 1)
+
+
 def reassign_points(x: np.ndarray, prm: Params, chunk: int = 256, workers: int = 1,
                     return_raw: bool = False):
     """The a1..a3 path: fp64 points as [F][B] arrays (dt_cols, dk_bins, energy).
@@ -152,10 +164,7 @@ def reassign_points(x: np.ndarray, prm: Params, chunk: int = 256, workers: int =
             raw[m0:m1] = e
         if prm.flags & FLAG_REASSIGN:
             dc = dt / H
-            col = m + np.rint(dc)
-            wh = k + dk
-            ok = (e > gate) & (np.abs(dt) <= N / 2) & (wh >= -0.5) & (wh <= N / 2 + 0.5) \
-                 & (col >= 0) & (col <= F - 1)
+            ok = keep_mask(e, dt, dk, m, k, F, prm)
             dcol[m0:m1] = np.where(ok, dc, 0.0)
             dbin[m0:m1] = np.where(ok, dk, 0.0)
         else:

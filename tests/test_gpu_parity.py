@@ -546,3 +546,32 @@ def test_streaming_matches_offline(emspec, n_fft, hop, channels, smoothing):
             again[ci] = col.numpy().copy()
     assert all((again[k] == got[k]).all() for k in got)
     eng.close()
+
+
+def test_fused_deposit_never_leaves_the_grid_on_white_noise(emspec):
+    """on white noise a few points per 100k frames have k + dk within fp32 rounding of
+    N/2 + 0.5; the old test on wh let them through to row N/2 + 1, i.e. row 0 of the next column
+    (or past the end of the accumulator).  The fused deposit must equal the bounds-checked scatter of
+    the stored points bit for bit, every stored point must land on the grid, and the accumulator must
+    be clean afterwards (a second call gives the same image)."""
+    S = 4096 + 128 * 160000
+    g = torch.Generator(device="cuda").manual_seed(3)
+    x = 0.25 * torch.randn(S, device="cuda", generator=g)
+    eng = emspec.Engine(n_fft=4096, hop=128, noise_gate_db=-200.0,
+                        flags=emspec.FLAG_REASSIGN | emspec.FLAG_DETERMINISTIC | emspec.FLAG_SYNC)
+    _, idx = eng.process_grid(x, want_grid=False)
+    dt, dk, e = eng.process_points(x)
+    k = torch.arange(2049, device="cuda", dtype=torch.float32)[None, None, :]
+    row = k + torch.round(dk)                       # torch.round is half-to-even, like rintf
+    kept = e > 0
+    assert kept.float().mean() > 0.9
+    assert bool(((row >= 0) & (row <= 2048))[kept].all())
+    near = kept & ((k + dk) > 2048.25)
+    assert int(near.sum()) > 0                      # the edge really is exercised
+    del row, near, kept, k
+    _, idx2 = eng.scatter_points(dt, dk, e, want_grid=False)
+    assert torch.equal(idx, idx2)
+    del dt, dk, e, idx2
+    _, idx3 = eng.process_grid(x, want_grid=False)
+    assert torch.equal(idx, idx3)
+    eng.close()

@@ -218,3 +218,23 @@ def test_agc_level_recurrence():
     assert idx[0, 5] == 255 and idx[1, 7] == 255 and idx[2, 9] < 255
     off = orc.postpass(grid, orc.Params(**{**prm.__dict__, "agc_strength": 0.0}))
     assert off[1, 7] == int(np.rint(255 * 40 / 60))
+
+
+def test_drop_rule_is_decided_on_the_rounded_row():
+    """a point whose w^ = k + dk sits at N/2 + 0.5 (or -0.5) must not reach row N/2 + 1
+    (or -1) through round-half-even; the rule tests the rounded row itself."""
+    prm = orc.Params(n_fft=4096, hop=128, noise_gate_db=-200.0)
+    F = 100
+    e = np.ones(6)
+    dt = np.zeros(6)
+    k = np.array([2047.0, 2047.0, 2046.0, 1.0, 1.0, 0.0])
+    dk = np.array([1.5, 1.49, 2.5, -1.5, -1.49, -0.5])
+    ok = orc.keep_mask(e, dt, dk, np.full(6, 50.0), k, F, prm)
+    rows = k + np.rint(dk)
+    assert ((rows >= 0) & (rows <= 2048))[ok].all()
+    assert list(ok) == [False, True, True, False, True, True]      # 1.5 -> 2 (row 2049) and -1.5 -> -2 (row -1) are dropped
+    # kept points always land on the grid, so the scatter never spills into a neighbouring column
+    en = np.zeros((F, prm.n_bins)); dc = np.zeros_like(en); db = np.zeros_like(en)
+    en[50, 2047] = 1.0; db[50, 2047] = 1.49
+    g = orc.scatter_grid(dc, db, en, prm)
+    assert g[50, 2048] == 1.0 and g.sum() == 1.0
