@@ -64,7 +64,8 @@ struct StftArgs {
     float         warp_c;     // (R-1)/log1p(a)  (mode 2)  or  (R-1)  (mode 1)
     float         inv_half;   // 2 / n_fft
     long long     samp_off;   // frame f starts at sample f*hop + samp_off of its channel
-    int           ring;       // > 0: the accumulator is a ring of `ring` columns per channel (streaming)
+    int           ring;       // > 0: accumulator and flags are rings of `ring` columns per channel (a power of two;
+                              //      streaming, and the O(chunk) host path); 0: linear, F columns per channel
     int           stream_M;   // streaming: pushes per ring lap = ceil(n_fft / hop)
     const long long* sstate;  // streaming: device counter of completed pushes (frame range decoded on device)
 };
@@ -87,14 +88,18 @@ constexpr int kFlagShift = 6;                              // one dirty flag per
 __host__ __device__ constexpr int flag_blocks(int B) { return (B + 63) >> kFlagShift; }
 // Flags are column-contiguous per bin block ([channels][NB][F]) so the post-pass reads the
 // flags of 16 consecutive columns from one cache line.
-__device__ __forceinline__ long long flag_index(int ch, long long F, int rows, long long col, int row) {
-    return ((long long)ch * flag_blocks(rows) + (row >> kFlagShift)) * F + col;
+// `ncols` columns per channel (F, or the ring size), `slot` = the column's place among them.
+__device__ __forceinline__ long long flag_index(int ch, long long ncols, int rows, long long slot, int row) {
+    return ((long long)ch * flag_blocks(rows) + (row >> kFlagShift)) * ncols + slot;
 }
 
-// Accumulator cell of (channel, column, row): linear [channels][F][R] or a column ring.
+// Accumulator cell of (channel, column, row): linear [channels][F][R] or a ring of 2^n columns.
 __device__ __forceinline__ long long acc_cell(const StftArgs& a, int ch, long long col, int row) {
-    return a.ring ? ((long long)ch * a.ring + (col % a.ring)) * a.rows + row
+    return a.ring ? ((long long)ch * a.ring + (col & (a.ring - 1))) * a.rows + row
                   : ((long long)ch * a.F + col) * a.rows + row;
+}
+__device__ __forceinline__ long long acc_flag(const StftArgs& a, int ch, long long col, int row) {
+    return a.ring ? flag_index(ch, a.ring, a.rows, col & (a.ring - 1), row) : flag_index(ch, a.F, a.rows, col, row);
 }
 
 // Output row of a point at reassigned frequency wh = k + dk [bins]
@@ -115,9 +120,13 @@ struct PostArgs {
     uint8_t*      index;      // u8   [channels][F][B] or null
     const float*  weight;     // [B] gain^2 * w_low(k)
     float*        carry;      // [channels][B] EMA state entering col_begin (updated)
-    long long     F;
+    long long     F;          // columns per channel of the stream (colscale is [channels][F])
     long long     col_begin;
     long long     col_end;
+    long long     acc_cols;   // columns per channel of acc / flags: F, or the ring size
+    long long     acc_mask;   // slot of column c = c & acc_mask (-1: linear)
+    long long     out_cols;   // columns per channel of grid / index: F, or the staging buffer's
+    long long     out_col0;   // stream column held by output column 0
     int           B;          // output rows per column R
     int           channels;
     float         smoothing;

@@ -42,7 +42,12 @@ struct ems_handle {
     float*  thw = nullptr;              // [N] th' window
     float2* tw = nullptr;               // [N]
     float*  weight = nullptr;           // [B]
-    ems::DevBuf acc, flags, carry, ema_local, ema_carry, host_pcm, host_i16, host_idx, host_grid, big_scratch, lut, colscale, agc_level;
+    ems::DevBuf acc, flags, carry, ema_local, ema_carry, big_scratch, lut, colscale, agc_level;
+    struct HostPipe {                   // ems_process_host*: two of everything, chunk c uses set c & 1
+        ems::DevBuf pcm[2], raw[2], idx[2], grid[2];   // fp32 planar chunk, raw int16/int24 chunk, staging images
+        cudaEvent_t ev_in[2]{}, ev_done[2]{}, ev_out[2]{}, ev_start{};
+        bool events = false;
+    } hp;
     bool acc_clean = false;             // accumulator and dirty flags are all zero (kept so by the post-pass)
     cudaEvent_t ev[EMS_STAGE_COUNT][2]{};
     bool ev_valid[EMS_STAGE_COUNT]{};
@@ -62,6 +67,7 @@ struct ems_handle {
         float* in_pin = nullptr;         // pinned staging
         uint8_t* out_pin = nullptr;
         int M = 0, Lr = 0, R = 0, ring_cols = 0;
+        int in_i16 = 0;                  // format of the hop the captured graph reads (0: fp32, 1: int16)
         long long pushes = 0;            // host mirror of the device counter
         size_t acc_bytes = 0;
     } st;
@@ -108,10 +114,16 @@ static bool valid_params(const ems_params& p) {
     if (p.display_rows < 0 || p.display_rows == 1 || p.display_rows > 65536) return false;
     if (!(p.freq_scale >= 0.f) || !(p.freq_scale <= 4.f)) return false;
     if (!(p.agc_strength >= 0.f) || !(p.agc_strength <= 1.f)) return false;
+    if (!(p.brightness > 0.f) || !(p.brightness <= 1.f)) return false;
     return true;
 }
 
 static int ilog2(int n) { int l = 0; while ((1 << l) < n) ++l; return l; }
+
+// "Brightness": the automatic gain draws the running level at T = 10^(-(1 - brightness) range / 10)
+static float agc_target(const ems_params& p) {
+    return (float)std::pow(10.0, -(1.0 - (double)p.brightness) * (double)p.db_range / 10.0);
+}
 
 static int rows_of(const ems_params& p);
 static double warp_a_of(const ems_params& p);
@@ -319,6 +331,7 @@ static PostArgs make_post(ems_handle* h, long long F, float* grid, uint8_t* inde
     p.grid = grid; p.index = index; p.weight = h->weight;
     p.carry = (float*)h->carry.p;
     p.F = F; p.col_begin = 0; p.col_end = F;
+    p.acc_cols = F; p.acc_mask = -1; p.out_cols = F; p.out_col0 = 0;
     p.B = rows_of(h->prm); p.channels = h->prm.channels;
     p.smoothing = h->prm.smoothing;
     p.db_floor = (float)(kTopDb - (double)h->prm.db_range);
@@ -327,17 +340,20 @@ static PostArgs make_post(ems_handle* h, long long F, float* grid, uint8_t* inde
     return p;
 }
 
-static ems_status clear_flags(ems_handle* h, long long F, long long c0, long long c1, int B);
+static ems_status clear_flags(ems_handle* h, const PostArgs& p);
 
 // Zero-fills columns [col_begin, col_end) of every channel of a [channels][F][col_bytes] array:
 // one memset when the range is the whole stream, one pitched memset otherwise (never one call
 // per channel: a batch maps clips to channels, up to 65535 of them).
-static cudaError_t zero_cols(ems_handle* h, void* base, size_t col_bytes, const PostArgs& p) {
+// `cols` = columns per channel of the array (p.F for colscale, p.out_cols for grid / index),
+// `col0` = the stream column its column 0 holds.
+static cudaError_t zero_cols(ems_handle* h, void* base, size_t col_bytes, const PostArgs& p, long long cols,
+                             long long col0) {
     const size_t ncols = (size_t)(p.col_end - p.col_begin);
-    char* b0 = (char*)base + (size_t)p.col_begin * col_bytes;
-    if (p.channels == 1 || ncols == (size_t)p.F)
-        return cudaMemsetAsync(b0, 0, (p.channels - 1) * (size_t)p.F * col_bytes + ncols * col_bytes, h->stream);
-    return cudaMemset2DAsync(b0, (size_t)p.F * col_bytes, 0, ncols * col_bytes, (size_t)p.channels, h->stream);
+    char* b0 = (char*)base + (size_t)(p.col_begin - col0) * col_bytes;
+    if (p.channels == 1 || ncols == (size_t)cols)
+        return cudaMemsetAsync(b0, 0, (p.channels - 1) * (size_t)cols * col_bytes + ncols * col_bytes, h->stream);
+    return cudaMemset2DAsync(b0, (size_t)cols * col_bytes, 0, ncols * col_bytes, (size_t)p.channels, h->stream);
 }
 
 // Post-pass over columns [col_begin, col_end) of every channel; h->carry holds the EMA
@@ -353,18 +369,18 @@ static ems_status run_post(ems_handle* h, PostArgs p) {
         ems_status s = ensure(h, h->colscale, (size_t)p.channels * p.F * sizeof(float));
         if (s != EMS_OK) return s;
         p.colscale = (float*)h->colscale.p;
-        EMS_CUDA(h, zero_cols(h, p.colscale, sizeof(float), p));
+        EMS_CUDA(h, zero_cols(h, p.colscale, sizeof(float), p, p.F, 0));
     }
     auto agc_scan = [&]() {
         agc_scan_kernel<<<p.channels, 1024, 0, h->stream>>>(p.colscale, (float*)h->agc_level.p, p.F,
                                                             p.col_begin, p.col_end, lambda,
-                                                            h->prm.agc_strength);
+                                                            h->prm.agc_strength, agc_target(h->prm));
         ++h->launches;
     };
     if (!ema) {
         // no recurrence along time: zero-fill the outputs, then visit only the dirty blocks
-        if (p.index) EMS_CUDA(h, zero_cols(h, p.index, (size_t)p.B, p));
-        if (p.grid) EMS_CUDA(h, zero_cols(h, p.grid, (size_t)p.B * sizeof(float), p));
+        if (p.index) EMS_CUDA(h, zero_cols(h, p.index, (size_t)p.B, p, p.out_cols, p.out_col0));
+        if (p.grid) EMS_CUDA(h, zero_cols(h, p.grid, (size_t)p.B * sizeof(float), p, p.out_cols, p.out_col0));
         const dim3 g((unsigned)((ncols + 255) / 256), p.channels * p.NB);
         if (agc) {
             post_sparse_kernel<<<g, 256, 0, h->stream>>>(p, 1);
@@ -402,7 +418,7 @@ static ems_status run_post(ems_handle* h, PostArgs p) {
     }
     post_emit_kernel<<<grd, blk, 0, h->stream>>>(p, carry_in, (int)n_chunks, chunk_cols, 0);
     ++h->launches;
-    if ((s = clear_flags(h, p.F, p.col_begin, p.col_end, p.B)) != EMS_OK) return s;
+    if ((s = clear_flags(h, p)) != EMS_OK) return s;
     EMS_CUDA(h, cudaGetLastError());
     return EMS_OK;
 }
@@ -411,7 +427,7 @@ static ems_status run_post(ems_handle* h, PostArgs p) {
 // between calls: deposits flag the 64-bin blocks they touch and the emit pass clears exactly
 // those, so no call pays a 22 GB memset.  A call that fails midway leaves acc_clean false
 // and the next one starts with a full clear.
-static ems_status prepare_acc(ems_handle* h, size_t cells, size_t rows, int B) {
+static ems_status prepare_acc(ems_handle* h, size_t cells, size_t rows, int B) {   // rows = channels * columns
     const bool det = h->prm.flags & EMS_FLAG_DETERMINISTIC;
     const size_t need = cells * (det ? 8 : 4), need_f = rows * flag_blocks(B);
     if (h->acc.bytes < need || h->flags.bytes < need_f) h->acc_clean = false;
@@ -427,15 +443,16 @@ static ems_status prepare_acc(ems_handle* h, size_t cells, size_t rows, int B) {
 }
 
 // Clears the dirty flags of columns [c0, c1) of every channel after their emit pass.
-static ems_status clear_flags(ems_handle* h, long long F, long long c0, long long c1, int B) {
-    const int rows = flag_blocks(B) * h->prm.channels;
-    if (c0 == 0 && c1 == F) {
-        EMS_CUDA(h, cudaMemsetAsync(h->flags.p, 0, (size_t)rows * F, h->stream));
+static ems_status clear_flags(ems_handle* h, const PostArgs& p) {
+    const int rows = p.NB * p.channels;
+    const long long c0 = p.col_begin, c1 = p.col_end;
+    if (c1 - c0 >= p.acc_cols) {       // every column (or every slot of the ring)
+        EMS_CUDA(h, cudaMemsetAsync(p.flags, 0, (size_t)rows * p.acc_cols, h->stream));
         return EMS_OK;
     }
     long long blocks = ((c1 - c0) * rows + 255) / 256;
     if (blocks > 4096) blocks = 4096;
-    clear_flags_kernel<<<(unsigned)blocks, 256, 0, h->stream>>>((unsigned char*)h->flags.p, F, c0, c1, rows);
+    clear_flags_kernel<<<(unsigned)blocks, 256, 0, h->stream>>>(p.flags, p.acc_cols, p.acc_mask, c0, c1, rows);
     ++h->launches;
     EMS_CUDA(h, cudaGetLastError());
     return EMS_OK;
@@ -502,7 +519,8 @@ static ems_status stream_init(ems_handle* h) {
     st.M = (N + H - 1) / H;
     st.Lr = st.M * H;
     st.R = (N / 2 + H - 1) / H;
-    st.ring_cols = 2 * st.R + 1;
+    st.ring_cols = 1;                       // >= 2 R + 1 columns, a power of two (deposits mask the column)
+    while (st.ring_cols < 2 * st.R + 1) st.ring_cols *= 2;
     st.acc_bytes = (size_t)C * st.ring_cols * B * (det ? 8 : 4);
     EMS_CUDA(h, cudaMalloc(&st.sstate, 2 * sizeof(long long)));
     EMS_CUDA(h, cudaMalloc(&st.ring, sizeof(float) * C * 2 * st.Lr));
@@ -539,7 +557,8 @@ static ems_status stream_capture(ems_handle* h) {
     sa.db_floor = (float)(kTopDb - (double)h->prm.db_range);
     sa.inv_range = 255.0f / h->prm.db_range;
     sa.gate_db = h->prm.noise_gate_db;
-    sa.etmp = st.etmp; sa.agc = st.agc; sa.agc_strength = h->prm.agc_strength;
+    sa.etmp = st.etmp; sa.agc = st.agc; sa.agc_strength = h->prm.agc_strength; sa.agc_target = agc_target(h->prm);
+    sa.in_i16 = st.in_i16;
     sa.agc_lambda = std::exp(-(float)H / (h->prm.sample_rate * kAgcReleaseSeconds));
     StftArgs a = make_args(h, st.ring, (size_t)2 * st.Lr, /*F=*/(long long)1 << 60);
     a.f_begin = 0; a.f_end = 1;                       // grid sizing; the kernel decodes the real frame
@@ -603,7 +622,7 @@ ems_status ems_default_params(ems_params* p) {
     p->db_range = 58.f; p->gain = 3.5f; p->low_end_boost = 3.9f; p->smoothing = 0.f;
     p->noise_gate_db = -65.f;
     p->flags = EMS_FLAG_REASSIGN | EMS_FLAG_DETERMINISTIC;
-    p->display_rows = 0; p->freq_scale = 1.0f; p->agc_strength = 0.0f;
+    p->display_rows = 0; p->freq_scale = 1.0f; p->agc_strength = 0.0f; p->brightness = 0.44f;
     return EMS_OK;
 }
 
@@ -657,9 +676,15 @@ ems_status ems_create(const ems_params* params, ems_handle** out) {
 ems_status ems_destroy(ems_handle* h) {
     if (!h) return EMS_ERR_INVALID_ARG;
     if (h->stream) cudaStreamSynchronize(h->stream);
-    for (DevBuf* b : {&h->acc, &h->flags, &h->carry, &h->ema_local, &h->ema_carry, &h->host_pcm, &h->host_i16, &h->lut, &h->colscale, &h->agc_level,
-                      &h->host_idx, &h->host_grid, &h->big_scratch})
+    for (DevBuf* b : {&h->acc, &h->flags, &h->carry, &h->ema_local, &h->ema_carry, &h->lut, &h->colscale, &h->agc_level,
+                      &h->big_scratch, &h->hp.pcm[0], &h->hp.pcm[1], &h->hp.raw[0], &h->hp.raw[1], &h->hp.idx[0], &h->hp.idx[1],
+                      &h->hp.grid[0], &h->hp.grid[1]})
         if (b->p) cudaFree(b->p);
+    if (h->hp.events) {
+        for (auto* evs : {h->hp.ev_in, h->hp.ev_done, h->hp.ev_out})
+            for (int b = 0; b < 2; ++b) if (evs[b]) cudaEventDestroy(evs[b]);
+        if (h->hp.ev_start) cudaEventDestroy(h->hp.ev_start);
+    }
     stream_free(h);
     if (h->thw) cudaFree(h->thw);
     if (h->tw) cudaFree(h->tw);
@@ -801,33 +826,26 @@ ems_status ems_process_grid(ems_handle* h, const float* pcm, size_t S, float* gr
     return finish(h);
 }
 
-// Shared body of ems_process_host (fp32 planar) and ems_process_host_i16 (int16 interleaved).
-static ems_status process_host_impl(ems_handle* h, const void* pcm_host_v, bool is_i16, size_t S,
+// ---- ems_process_host*: the HOST-buffer call, O(chunk) device memory.
+// The stream is cut into frame chunks.  Per chunk: its samples ((n-1) hop + n_fft per channel, the
+// n_fft - hop halo is uploaded again) go into one of two device PCM buffers, the fused kernel
+// deposits into an accumulator RING of 2^n >= chunk + 2R columns, the post-pass shapes the columns
+// no later frame can reach (col < f_end - R) into one of two staging images, and those go back to
+// the caller while the next chunk runs.  Nothing on the device grows with the stream length
+// except the AGC's per-column scale (4 bytes per column).
+enum HostFmt : int { kFmtF32Planar = 0, kFmtI16 = 1, kFmtI24 = 2 };
+static size_t fmt_bytes(int fmt) { return fmt == kFmtI16 ? 2 : fmt == kFmtI24 ? 3 : 4; }
+
+static ems_status process_host_impl(ems_handle* h, const void* pcm_host_v, int fmt, size_t S,
                                     float* grid_host, uint8_t* index_host, size_t* n_frames) {
     if (!h) return EMS_ERR_INVALID_ARG;
-    const float* pcm_host = (const float*)pcm_host_v;
-    const int16_t* pcm_i16 = (const int16_t*)pcm_host_v;
     const long long F = frames_of(h->prm, S);
     if (n_frames) *n_frames = (size_t)F;
     for (bool& v : h->ev_valid) v = false;
     if (F == 0) return EMS_OK;
-    if (!pcm_host || (!grid_host && !index_host)) return fail(h, EMS_ERR_INVALID_ARG, "null buffer");
+    if (!pcm_host_v || (!grid_host && !index_host)) return fail(h, EMS_ERR_INVALID_ARG, "null buffer");
     const int N = h->prm.n_fft, H = h->prm.hop, B = rows_of(h->prm), C = h->prm.channels;   // B: output rows
     const bool det = h->prm.flags & EMS_FLAG_DETERMINISTIC;
-    const size_t cells = (size_t)C * F * B;
-    ems_status s;
-    if ((s = ensure(h, h->host_pcm, (size_t)C * S * sizeof(float))) != EMS_OK) return s;
-    if (is_i16 && (s = ensure(h, h->host_i16, (size_t)C * S * sizeof(int16_t))) != EMS_OK) return s;
-    if ((s = prepare_acc(h, cells, (size_t)C * F, B)) != EMS_OK) return s;
-    if (index_host && (s = ensure(h, h->host_idx, cells)) != EMS_OK) return s;
-    if (grid_host && (s = ensure(h, h->host_grid, cells * sizeof(float))) != EMS_OK) return s;
-    if ((s = reset_carry(h)) != EMS_OK) return s;
-    float* pcm_dev = (float*)h->host_pcm.p;
-    uint8_t* idx_dev = index_host ? (uint8_t*)h->host_idx.p : nullptr;
-    float* grid_dev = grid_host ? (float*)h->host_grid.p : nullptr;
-
-    // Frame chunks: H2D of chunk c+1 overlaps the kernels of chunk c, whose finished
-    // columns (those no later frame can reach: col < f_end - R) go back while c+1 runs.
     const long long R = (N / 2 + H - 1) / H;
     // Chunk = about 64 MiB of output image: the pipeline's tail is the D2H of the last chunk
     // (~1.2 ms at PCIe Gen5 rates) whatever the row count, and launches stay large.
@@ -838,74 +856,119 @@ static ems_status process_host_impl(ems_handle* h, const void* pcm_host_v, bool 
     }
     if (chunk > 262144) chunk = 262144;
     if (chunk < 4 * R + 1024) chunk = 4 * R + 1024;
+    if (chunk > F) chunk = F;
     const int n_chunks = (int)((F + chunk - 1) / chunk);
-    std::vector<cudaEvent_t> ev_in(n_chunks), ev_done(n_chunks);
-    for (int c = 0; c < n_chunks; ++c) {
-        cudaEventCreateWithFlags(&ev_in[c], cudaEventDisableTiming);
-        cudaEventCreateWithFlags(&ev_done[c], cudaEventDisableTiming);
+    long long ring = 1;
+    while (ring < chunk + 2 * R + 2) ring *= 2;             // columns [cols_done, f_end + R) are live
+    const long long Lc = (chunk - 1) * H + N;               // samples per channel of one chunk
+    const long long out_cols = std::min(F, chunk + R);      // columns one chunk can finish
+    const bool is_int = fmt != kFmtF32Planar;
+    const size_t bps = fmt_bytes(fmt);
+
+    ems_status s;
+    auto& hp = h->hp;
+    if (!hp.events) {
+        for (auto* evs : {hp.ev_in, hp.ev_done, hp.ev_out})
+            for (int b = 0; b < 2; ++b) EMS_CUDA(h, cudaEventCreateWithFlags(&evs[b], cudaEventDisableTiming));
+        EMS_CUDA(h, cudaEventCreateWithFlags(&hp.ev_start, cudaEventDisableTiming));
+        hp.events = true;
     }
-    auto cleanup = [&]() {
-        for (int c = 0; c < n_chunks; ++c) { cudaEventDestroy(ev_in[c]); cudaEventDestroy(ev_done[c]); }
+    for (int b = 0; b < 2; ++b) {
+        if ((s = ensure(h, hp.pcm[b], (size_t)C * Lc * sizeof(float))) != EMS_OK) return s;
+        if (is_int && (s = ensure(h, hp.raw[b], (size_t)C * Lc * bps + 16)) != EMS_OK) return s;
+        if (index_host && (s = ensure(h, hp.idx[b], (size_t)C * out_cols * B)) != EMS_OK) return s;
+        if (grid_host && (s = ensure(h, hp.grid[b], (size_t)C * out_cols * B * sizeof(float))) != EMS_OK) return s;
+    }
+    if ((s = prepare_acc(h, (size_t)C * ring * B, (size_t)C * ring, B)) != EMS_OK) return s;
+    if ((s = reset_carry(h)) != EMS_OK) return s;
+
+    int max_pitch = 0;
+    EMS_CUDA(h, cudaDeviceGetAttribute(&max_pitch, cudaDevAttrMaxPitch, h->device));
+    // rows of a [channels][...] array: one pitched copy, or one copy per channel when the caller's
+    // row pitch is beyond what a pitched copy takes (an hour of image is 2.8 GB per channel)
+    auto copy_rows = [&](void* dst, size_t dpitch, const void* src, size_t spitch, size_t width,
+                         cudaMemcpyKind kind, cudaStream_t st) -> cudaError_t {
+        if (C == 1) return cudaMemcpyAsync(dst, src, width, kind, st);
+        if (dpitch <= (size_t)max_pitch && spitch <= (size_t)max_pitch)
+            return cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, (size_t)C, kind, st);
+        for (int ch = 0; ch < C; ++ch) {
+            cudaError_t e = cudaMemcpyAsync((char*)dst + ch * dpitch, (const char*)src + ch * spitch, width, kind, st);
+            if (e != cudaSuccess) return e;
+        }
+        return cudaSuccess;
     };
-    cudaEvent_t ev_start;
-    cudaEventCreateWithFlags(&ev_start, cudaEventDisableTiming);
-    cudaEventRecord(ev_start, h->stream);
-    cudaStreamWaitEvent(h->copy_in, ev_start, 0);     // the memset and earlier work come first
-    cudaStreamWaitEvent(h->copy_out, ev_start, 0);
-    cudaEventDestroy(ev_start);
-    long long sent = 0;        // samples per channel already on the device
-    long long cols_done = 0;   // columns already post-processed
+
     ems_status rs = EMS_OK;
+    cudaError_t ce = cudaSuccess;
+    const char* what = "";
+#define HP_CUDA(call)                                                        \
+    if ((ce = (call)) != cudaSuccess) { what = #call; rs = EMS_ERR_CUDA; break; }
+
+    long long cols_done = 0;   // columns already post-processed
+    do {
+        HP_CUDA(cudaEventRecord(hp.ev_start, h->stream));
+        HP_CUDA(cudaStreamWaitEvent(h->copy_in, hp.ev_start, 0));      // the memsets and earlier work come first
+        HP_CUDA(cudaStreamWaitEvent(h->copy_out, hp.ev_start, 0));
+    } while (0);
     for (int c = 0; c < n_chunks && rs == EMS_OK; ++c) {
+        const int b = c & 1;
         const long long f0 = (long long)c * chunk, f1 = std::min(F, f0 + chunk);
-        const long long need = (f1 == F) ? (long long)S : (f1 - 1) * H + N;   // samples needed
-        if (is_i16) {
-            int16_t* stage = (int16_t*)h->host_i16.p;
-            cudaMemcpyAsync(stage + (size_t)sent * C, pcm_i16 + (size_t)sent * C,
-                            (size_t)(need - sent) * C * sizeof(int16_t), cudaMemcpyHostToDevice, h->copy_in);
-        } else {
-            for (int ch = 0; ch < C; ++ch)
-                cudaMemcpyAsync(pcm_dev + (size_t)ch * S + sent, pcm_host + (size_t)ch * S + sent,
-                                (size_t)(need - sent) * sizeof(float), cudaMemcpyHostToDevice,
-                                h->copy_in);
+        const long long s0 = f0 * H, n = (f1 - 1) * H + N - s0;          // samples [s0, s0 + n) of every channel
+        float* pcm_dev = (float*)hp.pcm[b].p;
+        if (c >= 2) HP_CUDA(cudaStreamWaitEvent(h->copy_in, hp.ev_done[b], 0));   // chunk c-2 has read this buffer
+        if (!is_int) {
+            HP_CUDA(copy_rows(pcm_dev, (size_t)Lc * sizeof(float), (const float*)pcm_host_v + s0, S * sizeof(float),
+                              (size_t)n * sizeof(float), cudaMemcpyHostToDevice, h->copy_in));
+        } else {      // interleaved: one contiguous run of n * C samples
+            HP_CUDA(cudaMemcpyAsync(hp.raw[b].p, (const char*)pcm_host_v + (size_t)s0 * C * bps, (size_t)n * C * bps,
+                                    cudaMemcpyHostToDevice, h->copy_in));
         }
-        cudaEventRecord(ev_in[c], h->copy_in);
-        cudaStreamWaitEvent(h->stream, ev_in[c], 0);
-        if (is_i16) {
-            const long long n = (need - sent) * C;
-            long long blocks = (n + 255) / 256;
+        HP_CUDA(cudaEventRecord(hp.ev_in[b], h->copy_in));
+        HP_CUDA(cudaStreamWaitEvent(h->stream, hp.ev_in[b], 0));
+        if (is_int) {
+            const long long work = fmt == kFmtI24 ? (n * C + 3) / 4 : n * C;
+            long long blocks = (work + 255) / 256;
             if (blocks > 8192) blocks = 8192;
-            pcm_i16_to_planar_kernel<<<(unsigned)blocks, 256, 0, h->stream>>>(
-                (const int16_t*)h->host_i16.p, pcm_dev, (long long)S, C, sent, need);
+            if (fmt == kFmtI16)
+                pcm_i16_to_planar_kernel<<<(unsigned)blocks, 256, 0, h->stream>>>((const int16_t*)hp.raw[b].p, pcm_dev, Lc, C, n);
+            else
+                pcm_i24_to_planar_kernel<<<(unsigned)blocks, 256, 0, h->stream>>>((const uint32_t*)hp.raw[b].p, pcm_dev, Lc, C, n);
             ++h->launches;
+            HP_CUDA(cudaGetLastError());
         }
-        sent = need;
-        StftArgs a = make_args(h, pcm_dev, S, F);
+        StftArgs a = make_args(h, pcm_dev, (size_t)Lc, F);
+        a.samp_off = -s0;                                                 // frame f starts at sample f hop - s0 of the buffer
         a.f_begin = f0; a.f_end = f1;
         a.acc = h->acc.p; a.flags = (unsigned char*)h->flags.p; a.mode = det ? kDepositU64 : kDepositF32;
+        a.ring = (int)ring;
         if ((rs = launch_stft(h, a)) != EMS_OK) break;
         const long long col_end = (f1 == F) ? F : std::max(cols_done, f1 - R);
-        PostArgs p = make_post(h, F, grid_dev, idx_dev);
+        if (c >= 2) HP_CUDA(cudaStreamWaitEvent(h->stream, hp.ev_out[b], 0));    // staging image b has gone to the host
+        PostArgs p = make_post(h, F, grid_host ? (float*)hp.grid[b].p : nullptr, index_host ? (uint8_t*)hp.idx[b].p : nullptr);
         p.col_begin = cols_done; p.col_end = col_end;
+        p.acc_cols = ring; p.acc_mask = ring - 1; p.out_cols = out_cols; p.out_col0 = cols_done;
         if ((rs = run_post(h, p)) != EMS_OK) break;
-        cudaEventRecord(ev_done[c], h->stream);
-        cudaStreamWaitEvent(h->copy_out, ev_done[c], 0);
+        HP_CUDA(cudaEventRecord(hp.ev_done[b], h->stream));
+        HP_CUDA(cudaStreamWaitEvent(h->copy_out, hp.ev_done[b], 0));
         if (col_end > cols_done) {
-            for (int ch = 0; ch < C; ++ch) {
-                const size_t off = ((size_t)ch * F + cols_done) * B, cnt = (size_t)(col_end - cols_done) * B;
-                if (index_host)
-                    cudaMemcpyAsync(index_host + off, idx_dev + off, cnt, cudaMemcpyDeviceToHost, h->copy_out);
-                if (grid_host)
-                    cudaMemcpyAsync(grid_host + off, grid_dev + off, cnt * sizeof(float),
-                                    cudaMemcpyDeviceToHost, h->copy_out);
-            }
+            const size_t nc = (size_t)(col_end - cols_done);
+            if (index_host)
+                HP_CUDA(copy_rows(index_host + (size_t)cols_done * B, (size_t)F * B, hp.idx[b].p, (size_t)out_cols * B,
+                                  nc * B, cudaMemcpyDeviceToHost, h->copy_out));
+            if (grid_host)
+                HP_CUDA(copy_rows(grid_host + (size_t)cols_done * B, (size_t)F * B * sizeof(float), hp.grid[b].p,
+                                  (size_t)out_cols * B * sizeof(float), nc * B * sizeof(float), cudaMemcpyDeviceToHost,
+                                  h->copy_out));
         }
+        HP_CUDA(cudaEventRecord(hp.ev_out[b], h->copy_out));
         cols_done = col_end;
     }
-    cudaError_t e1 = cudaStreamSynchronize(h->copy_out);
-    cudaError_t e2 = cudaStreamSynchronize(h->stream);
-    cudaError_t e3 = cudaStreamSynchronize(h->copy_in);
-    cleanup();
+#undef HP_CUDA
+    // whatever happened, no copy may still be targeting the caller's buffers when this returns
+    const cudaError_t e1 = cudaStreamSynchronize(h->copy_out);
+    const cudaError_t e2 = cudaStreamSynchronize(h->stream);
+    const cudaError_t e3 = cudaStreamSynchronize(h->copy_in);
+    if (rs == EMS_ERR_CUDA && ce != cudaSuccess) return fail(h, EMS_ERR_CUDA, "process_host: %s: %s", what, cudaGetErrorString(ce));
     if (rs != EMS_OK) return rs;
     if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess)
         return fail(h, EMS_ERR_CUDA, "process_host: %s",
@@ -916,12 +979,28 @@ static ems_status process_host_impl(ems_handle* h, const void* pcm_host_v, bool 
 
 ems_status ems_process_host(ems_handle* h, const float* pcm_host, size_t S, float* grid_host,
                             uint8_t* index_host, size_t* n_frames) {
-    return process_host_impl(h, pcm_host, false, S, grid_host, index_host, n_frames);
+    return process_host_impl(h, pcm_host, kFmtF32Planar, S, grid_host, index_host, n_frames);
 }
 
 ems_status ems_process_host_i16(ems_handle* h, const int16_t* pcm_host, size_t S, float* grid_host,
                                 uint8_t* index_host, size_t* n_frames) {
-    return process_host_impl(h, pcm_host, true, S, grid_host, index_host, n_frames);
+    return process_host_impl(h, pcm_host, kFmtI16, S, grid_host, index_host, n_frames);
+}
+
+ems_status ems_process_host_i24(ems_handle* h, const uint8_t* pcm_host, size_t S, float* grid_host,
+                                uint8_t* index_host, size_t* n_frames) {
+    return process_host_impl(h, pcm_host, kFmtI24, S, grid_host, index_host, n_frames);
+}
+
+ems_status ems_scratch_bytes(const ems_handle* h, size_t* bytes) {
+    if (!h || !bytes) return EMS_ERR_INVALID_ARG;
+    size_t n = 0;
+    for (const DevBuf* b : {&h->acc, &h->flags, &h->carry, &h->ema_local, &h->ema_carry, &h->big_scratch, &h->lut,
+                            &h->colscale, &h->agc_level, &h->hp.pcm[0], &h->hp.pcm[1], &h->hp.raw[0], &h->hp.raw[1],
+                            &h->hp.idx[0], &h->hp.idx[1], &h->hp.grid[0], &h->hp.grid[1]})
+        n += b->bytes;
+    *bytes = n;
+    return EMS_OK;
 }
 
 ems_status ems_colorize(ems_handle* h, const uint8_t* index_dev, size_t n_cells,
@@ -955,15 +1034,21 @@ ems_status ems_launch_count(const ems_handle* h, uint64_t* n) {
     return EMS_OK;
 }
 
-ems_status ems_stream_push(ems_handle* h, const float* pcm_host, uint8_t* column_host,
-                           int* column_ready, int64_t* column_index) {
+static ems_status stream_push_impl(ems_handle* h, const void* pcm_host, int is_i16, uint8_t* column_host,
+                                   int* column_ready, int64_t* column_index) {
     if (!h || !pcm_host || !column_host || !column_ready) return EMS_ERR_INVALID_ARG;
     auto& st = h->st;
     ems_status s;
     if (!st.ready && (s = stream_init(h)) != EMS_OK) return s;
+    if (st.graph && st.in_i16 != is_i16) {          // the ingest kernel of the graph reads the other format
+        EMS_CUDA(h, cudaStreamSynchronize(h->stream));
+        cudaGraphExecDestroy(st.graph);
+        st.graph = nullptr;
+    }
+    st.in_i16 = is_i16;
     if (!st.graph && (s = stream_capture(h)) != EMS_OK) return s;
     const int H = h->prm.hop, C = h->prm.channels, B = rows_of(h->prm);
-    memcpy(st.in_pin, pcm_host, sizeof(float) * H * C);
+    memcpy(st.in_pin, pcm_host, (is_i16 ? sizeof(int16_t) : sizeof(float)) * H * C);
     EMS_CUDA(h, cudaGraphLaunch(st.graph, h->stream));
     h->launches += 3;
     EMS_CUDA(h, cudaStreamSynchronize(h->stream));
@@ -973,6 +1058,16 @@ ems_status ems_stream_push(ems_handle* h, const float* pcm_host, uint8_t* column
     if (column_index) *column_index = cf;
     if (cf >= 0) memcpy(column_host, st.out_pin, (size_t)C * B);
     return EMS_OK;
+}
+
+ems_status ems_stream_push(ems_handle* h, const float* pcm_host, uint8_t* column_host,
+                           int* column_ready, int64_t* column_index) {
+    return stream_push_impl(h, pcm_host, 0, column_host, column_ready, column_index);
+}
+
+ems_status ems_stream_push_i16(ems_handle* h, const int16_t* pcm_host, uint8_t* column_host,
+                               int* column_ready, int64_t* column_index) {
+    return stream_push_impl(h, pcm_host, 1, column_host, column_ready, column_index);
 }
 
 // ---- stream checkpoint: header + [pushes][ring][acc][carry][agc]

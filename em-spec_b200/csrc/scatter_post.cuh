@@ -87,6 +87,17 @@ __device__ __forceinline__ void acc_zero(void* acc, int is_u64, long long o) {
     else reinterpret_cast<float*>(acc)[o] = 0.f;
 }
 
+// Stream column c of channel ch: its accumulator row, its dirty flag (of bin block blk), its output row.
+__device__ __forceinline__ long long acc_row(const PostArgs& a, int ch, long long c) {
+    return ((long long)ch * a.acc_cols + (c & a.acc_mask)) * a.B;
+}
+__device__ __forceinline__ long long flag_at(const PostArgs& a, int ch, int blk, long long c) {
+    return ((long long)ch * a.NB + blk) * a.acc_cols + (c & a.acc_mask);
+}
+__device__ __forceinline__ long long out_row_of(const PostArgs& a, int ch, long long c) {
+    return ((long long)ch * a.out_cols + (c - a.out_col0)) * a.B;
+}
+
 constexpr int kPostChunk = 256;   // columns per thread in the EMA scan
 constexpr int kPostTile = 8;      // columns per thread when there is no recurrence along time
 
@@ -101,9 +112,9 @@ post_ema_local_kernel(const PostArgs a, float* __restrict__ local_end, int n_chu
     const long long c1 = min(c0 + (long long)kPostChunk, a.col_end);
     const float w = a.weight[k], s = a.smoothing, oms = 1.0f - a.smoothing;
     float y = 0.f;
-    const unsigned char* fl = a.flags + ((long long)ch * a.NB + (k >> kFlagShift)) * a.F;
+    const int blk = k >> kFlagShift;
     for (long long c = c0; c < c1; ++c) {
-        const float E = fl[c] ? acc_load(a.acc, a.acc_is_u64, ((long long)ch * a.F + c) * a.B + k) * w : 0.f;
+        const float E = a.flags[flag_at(a, ch, blk, c)] ? acc_load(a.acc, a.acc_is_u64, acc_row(a, ch, c) + k) * w : 0.f;
         y = s * y + oms * E;
     }
     local_end[((long long)ch * n_chunks + chunk) * a.B + k] = y;
@@ -141,25 +152,24 @@ post_emit_kernel(const PostArgs a, const float* __restrict__ carry_in, int n_chu
     const long long c1 = min(c0 + (long long)chunk_cols, a.col_end);
     const float w = a.weight[k], s = a.smoothing, oms = 1.0f - a.smoothing;
     float y = carry_in ? carry_in[((long long)ch * n_chunks + chunk) * a.B + k] : 0.f;
-    const unsigned char* fl = a.flags + ((long long)ch * a.NB + (k >> kFlagShift)) * a.F;
+    const int blk = k >> kFlagShift;
     constexpr int kTile = kPostTile;   // columns whose flags and cells are fetched together
     for (long long cb = c0; cb < c1; cb += kTile) {
         const int nt = (int)min((long long)kTile, c1 - cb);
-        const long long o0 = ((long long)ch * a.F + cb) * a.B + k;
         unsigned char f[kTile];
 #pragma unroll
-        for (int i = 0; i < kTile; ++i) f[i] = (i < nt) ? fl[cb + i] : 0;
+        for (int i = 0; i < kTile; ++i) f[i] = (i < nt) ? a.flags[flag_at(a, ch, blk, cb + i)] : 0;
         float G[kTile];
         // clean 64-bin blocks (no deposit since the last post-pass) are neither read nor cleared
 #pragma unroll
         for (int i = 0; i < kTile; ++i) {
-            const long long o = o0 + (long long)i * a.B;
+            const long long o = acc_row(a, ch, cb + i) + k;
             G[i] = !f[i] ? 0.f : measure ? acc_load(a.acc, a.acc_is_u64, o) : acc_take(a.acc, a.acc_is_u64, o);
         }
 #pragma unroll
         for (int i = 0; i < kTile; ++i) {
             if (i < nt) {
-                const long long o = o0 + (long long)i * a.B;
+                const long long o = out_row_of(a, ch, cb + i) + k;
                 float E = G[i] * w;
                 if (s > 0.f) { y = s * y + oms * E; E = y; }
                 if (measure) {
@@ -189,9 +199,8 @@ post_sparse_kernel(const PostArgs a, int measure) {
     const int ch = r / a.NB, blk = r - ch * a.NB;
     const long long cw = a.col_begin + ((long long)blockIdx.x * 8 + (threadIdx.x >> 5)) * 32;
     if (cw >= a.col_end) return;
-    unsigned char* fl = a.flags + (long long)r * a.F;
     const long long c = cw + lane;
-    unsigned mask = __ballot_sync(0xffffffffu, c < a.col_end && fl[c] != 0);
+    unsigned mask = __ballot_sync(0xffffffffu, c < a.col_end && a.flags[flag_at(a, ch, blk, c)] != 0);
     const int k0 = (blk << kFlagShift) + lane, k1 = k0 + 32;
     const float w0 = k0 < a.B ? a.weight[k0] : 0.f, w1 = k1 < a.B ? a.weight[k1] : 0.f;
     constexpr int kBatch = 4;     // flagged blocks in flight per warp: 8 independent loads per lane
@@ -205,7 +214,7 @@ post_sparse_kernel(const PostArgs a, int measure) {
         float G0[kBatch], G1[kBatch];
 #pragma unroll
         for (int b = 0; b < kBatch; ++b) {
-            const long long row = ((long long)ch * a.F + cw + max(js[b], 0)) * a.B;
+            const long long row = acc_row(a, ch, cw + max(js[b], 0));
             const bool on = js[b] >= 0;
             G0[b] = (on && k0 < a.B) ? acc_load(a.acc, a.acc_is_u64, row + k0) : 0.f;
             G1[b] = (on && k1 < a.B) ? acc_load(a.acc, a.acc_is_u64, row + k1) : 0.f;
@@ -222,44 +231,76 @@ post_sparse_kernel(const PostArgs a, int measure) {
 #pragma unroll
         for (int b = 0; b < kBatch; ++b) {
             if (js[b] < 0) continue;
-            const long long row = ((long long)ch * a.F + cw + js[b]) * a.B;
+            const long long row = acc_row(a, ch, cw + js[b]), orow = out_row_of(a, ch, cw + js[b]);
             const float sc = a.colscale ? a.colscale[(long long)ch * a.F + cw + js[b]] : 1.0f;
             if (k0 < a.B) {
                 acc_zero(a.acc, a.acc_is_u64, row + k0);
-                if (a.grid) a.grid[row + k0] = G0[b];
-                if (a.index) a.index[row + k0] = a.colscale ? colour_index(G0[b] * w0, sc, a) : colour_index(G0[b] * w0, a);
+                if (a.grid) a.grid[orow + k0] = G0[b];
+                if (a.index) a.index[orow + k0] = a.colscale ? colour_index(G0[b] * w0, sc, a) : colour_index(G0[b] * w0, a);
             }
             if (k1 < a.B) {
                 acc_zero(a.acc, a.acc_is_u64, row + k1);
-                if (a.grid) a.grid[row + k1] = G1[b];
-                if (a.index) a.index[row + k1] = a.colscale ? colour_index(G1[b] * w1, sc, a) : colour_index(G1[b] * w1, a);
+                if (a.grid) a.grid[orow + k1] = G1[b];
+                if (a.index) a.index[orow + k1] = a.colscale ? colour_index(G1[b] * w1, sc, a) : colour_index(G1[b] * w1, a);
             }
-            if (lane == 0) fl[cw + js[b]] = 0;
+            if (lane == 0) a.flags[flag_at(a, ch, blk, cw + js[b])] = 0;
         }
     }
 }
 
-// Capture-side format: int16 PCM, interleaved [S][channels] ->
-// fp32 planar [channels][S], full scale 32768, samples [s0, s1) of every channel.
+// Capture-side formats: integer PCM, interleaved [n][channels] (one chunk of the
+// stream, starting at the buffer's first byte) -> fp32 planar [channels][S] samples [0, n).
+// int16: full scale 32768.
 __global__ void pcm_i16_to_planar_kernel(const int16_t* __restrict__ in, float* __restrict__ out,
-                                         long long S, int channels, long long s0, long long s1) {
-    const long long n = (s1 - s0) * channels;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
-         i += (long long)gridDim.x * blockDim.x) {
-        const long long e = s0 * channels + i;
+                                         long long S, int channels, long long n) {
+    const long long total = n * channels;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+         e += (long long)gridDim.x * blockDim.x) {
         const long long smp = e / channels;
         const int ch = (int)(e - smp * channels);
         out[(long long)ch * S + smp] = (float)in[e] * (1.0f / 32768.0f);
     }
 }
+// int24: three bytes per sample, little-endian, packed; full scale 2^23 (exact in fp32).  A thread
+// unpacks four samples from three aligned 32-bit words.
+__global__ void pcm_i24_to_planar_kernel(const uint32_t* __restrict__ in, float* __restrict__ out,
+                                         long long S, int channels, long long n) {
+    const long long total = n * channels, quads = (total + 3) / 4;
+    const unsigned char* in8 = reinterpret_cast<const unsigned char*>(in);
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < quads;
+         q += (long long)gridDim.x * blockDim.x) {
+        int v[4];
+        if (4 * q + 4 <= total) {
+            const uint32_t w0 = in[3 * q], w1 = in[3 * q + 1], w2 = in[3 * q + 2];
+            v[0] = (int)(w0 << 8) >> 8;
+            v[1] = (int)(((w0 >> 24) | (w1 << 8)) << 8) >> 8;
+            v[2] = (int)(((w1 >> 16) | (w2 << 16)) << 8) >> 8;
+            v[3] = (int)w2 >> 8;
+        } else {       // the last, partial quad: byte loads
+            for (int i = 0; i < 4; ++i) {
+                const long long e = 4 * q + i;
+                v[i] = e < total ? (int)(((uint32_t)in8[3 * e] | ((uint32_t)in8[3 * e + 1] << 8) | ((uint32_t)in8[3 * e + 2] << 16)) << 8) >> 8 : 0;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const long long e = 4 * q + i;
+            if (e < total) {
+                const long long smp = e / channels;
+                const int ch = (int)(e - smp * channels);
+                out[(long long)ch * S + smp] = (float)v[i] * (1.0f / 8388608.0f);
+            }
+        }
+    }
+}
 
 // AGC level scan over columns [c0, c1) of one channel per block: colscale holds the column
-// peaks on entry and level^-strength on exit.  level[m] = max(peak[m], lambda * level[m-1]);
+// peaks on entry and target * level^-strength on exit (target: the "Brightness" control).  level[m] = max(peak[m], lambda * level[m-1]);
 // `level_carry[ch]` enters c0 and leaves with the level after c1 - 1.  The operator is
 // associative (max-plus with decay), so each thread scans a chunk and thread 0 chains them.
 __global__ void __launch_bounds__(1024)
 agc_scan_kernel(float* __restrict__ colscale, float* __restrict__ level_carry, long long F,
-                long long c0, long long c1, float lambda, float strength) {
+                long long c0, long long c1, float lambda, float strength, float target) {
     __shared__ float s_end[1024];
     __shared__ float s_in[1024];
     const int ch = blockIdx.x, t = threadIdx.x;
@@ -283,7 +324,7 @@ agc_scan_kernel(float* __restrict__ colscale, float* __restrict__ level_carry, l
     lv = s_in[t];
     for (long long m = a0; m < a1; ++m) {
         lv = fmaxf(cs[m], lambda * lv);
-        cs[m] = lv > 0.f ? powf(lv, -strength) : 1.0f;
+        cs[m] = lv > 0.f ? target * powf(lv, -strength) : 1.0f;
     }
 }
 
@@ -316,13 +357,14 @@ colorize_kernel(const uint8_t* __restrict__ index, uint32_t* __restrict__ rgba, 
 }
 
 // Clears the dirty flags of columns [c0, c1) of every (channel, bin block) row.
-__global__ void clear_flags_kernel(unsigned char* __restrict__ flags, long long F, long long c0,
-                                   long long c1, int rows) {
+// `ncols` columns per row (F, or the ring size), column c sits at slot c & mask.
+__global__ void clear_flags_kernel(unsigned char* __restrict__ flags, long long ncols, long long mask,
+                                   long long c0, long long c1, int rows) {
     const long long n = c1 - c0;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n * rows;
          i += (long long)gridDim.x * blockDim.x) {
         const long long r = i / n;
-        flags[r * F + c0 + (i - r * n)] = 0;
+        flags[r * ncols + ((c0 + (i - r * n)) & mask)] = 0;
     }
 }
 

@@ -115,7 +115,7 @@ __device__ __forceinline__ void reassign_emit(const StftArgs& a, int ch,
             red_add_u64(reinterpret_cast<unsigned long long*>(a.acc) + o, fix_energy(e));
         else
             red_add_f32(reinterpret_cast<float*>(a.acc) + o, e);
-        if (a.flags) flag_set(a.flags + flag_index(ch, a.F, a.rows, col, row));
+        if (a.flags) flag_set(a.flags + acc_flag(a, ch, col, row));
     }
 }
 

@@ -244,13 +244,13 @@ template <int MODE>
 __device__ __noinline__ void deposit_point(const DepositCtx d, int ch, long long col, int k, float dk,
                                            float wh, float e) {
     const int row = out_row(d.warp_mode, d.warp_a, d.warp_c, d.inv_half, k, dk, wh);
-    const long long o = d.ring ? ((long long)ch * d.ring + (col % d.ring)) * d.rows + row
-                               : ((long long)ch * d.F + col) * d.rows + row;
+    const long long ncols = d.ring ? d.ring : d.F, slot = d.ring ? (col & (d.ring - 1)) : col;
+    const long long o = ((long long)ch * ncols + slot) * d.rows + row;
     if (MODE == kDepositU64)
         red_add_u64(reinterpret_cast<unsigned long long*>(d.acc) + o, fix_energy(e));
     else
         red_add_f32(reinterpret_cast<float*>(d.acc) + o, e);
-    if (d.flags) flag_set(d.flags + flag_index(ch, d.F, d.rows, col, row));
+    if (d.flags) flag_set(d.flags + flag_index(ch, ncols, d.rows, slot, row));
 }
 
 // One bin of the epilogue: Hann / Hann-derivative stencils of the rectangular spectrum, the

@@ -20,7 +20,8 @@ struct StreamArgs {
     float*       etmp;       // [channels][B] shaped energy of the final column
     float*       agc;        // [2][channels]: (unused), running level
     int hop, channels, M, Lr, R, ring_cols, B, acc_is_u64;
-    float smoothing, db_floor, inv_range, gate_db, agc_strength, agc_lambda;
+    float smoothing, db_floor, inv_range, gate_db, agc_strength, agc_lambda, agc_target;
+    int in_i16;              // the hop is int16 (full scale 32768) instead of fp32
 };
 
 // De-interleaves the hop and writes it twice (pos and pos + Lr) so that any n_fft-long
@@ -31,7 +32,7 @@ __global__ void stream_ingest_kernel(const StreamArgs s) {
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < s.hop * s.channels;
          e += gridDim.x * blockDim.x) {
         const int smp = e / s.channels, ch = e - smp * s.channels;
-        const float v = s.in[e];
+        const float v = s.in_i16 ? (float)reinterpret_cast<const int16_t*>(s.in)[e] * (1.0f / 32768.0f) : s.in[e];
         float* r = s.ring + (long long)ch * 2 * s.Lr + wp + smp;
         r[0] = v;
         r[s.Lr] = v;
@@ -79,7 +80,7 @@ stream_finish_kernel(const StreamArgs s) {
                 if (t == 0) {
                     const float lv = fmaxf(v, s.agc_lambda * s.agc[s.channels + ch]);
                     s.agc[s.channels + ch] = lv;                       // level recurrence
-                    s_scale = lv > 0.f ? powf(lv, -s.agc_strength) : 1.0f;
+                    s_scale = lv > 0.f ? s.agc_target * powf(lv, -s.agc_strength) : 1.0f;
                 }
             }
             __syncthreads();

@@ -36,6 +36,7 @@ class Params(C.Structure):
         ("low_end_boost", C.c_float), ("smoothing", C.c_float),
         ("noise_gate_db", C.c_float), ("flags", C.c_uint32),
         ("display_rows", C.c_int32), ("freq_scale", C.c_float), ("agc_strength", C.c_float),
+        ("brightness", C.c_float),
     ]
 
 
@@ -59,10 +60,13 @@ _SIG = {
     "ems_scatter_points": (C.c_int, [_VP, _FP, _FP, _FP, C.c_size_t, _FP, _U8P]),
     "ems_process_host": (C.c_int, [_VP, _FP, C.c_size_t, _FP, _U8P, C.POINTER(C.c_size_t)]),
     "ems_process_host_i16": (C.c_int, [_VP, _FP, C.c_size_t, _FP, _U8P, C.POINTER(C.c_size_t)]),
+    "ems_process_host_i24": (C.c_int, [_VP, _U8P, C.c_size_t, _FP, _U8P, C.POINTER(C.c_size_t)]),
+    "ems_scratch_bytes": (C.c_int, [_VP, C.POINTER(C.c_size_t)]),
     "ems_colorize": (C.c_int, [_VP, _U8P, C.c_size_t, _VP, _VP]),
     "ems_stage_ms": (C.c_int, [_VP, C.c_int, C.POINTER(C.c_float)]),
     "ems_launch_count": (C.c_int, [_VP, C.POINTER(C.c_uint64)]),
     "ems_stream_push": (C.c_int, [_VP, _FP, _U8P, C.POINTER(C.c_int), C.POINTER(C.c_int64)]),
+    "ems_stream_push_i16": (C.c_int, [_VP, _VP, _U8P, C.POINTER(C.c_int), C.POINTER(C.c_int64)]),
     "ems_stream_reset": (C.c_int, [_VP]),
     "ems_stream_state_size": (C.c_int, [_VP, C.POINTER(C.c_size_t)]),
     "ems_stream_save": (C.c_int, [_VP, _VP, C.c_size_t]),
@@ -260,6 +264,30 @@ class Engine:
                                                   _ptr(index_out), C.byref(n)))
         return grid_out, index_out
 
+    def process_host_i24(self, pcm_i24, want_grid=False, index_out=None, grid_out=None):
+        """Host uint8 tensor [S][channels][3] (packed little-endian int24, interleaved) ->
+        (grid | None, index) CPU tensors."""
+        import torch
+        assert (not pcm_i24.is_cuda) and pcm_i24.dtype == torch.uint8 and pcm_i24.is_contiguous()
+        assert pcm_i24.dim() == 3 and pcm_i24.shape[1] == self.params.channels and pcm_i24.shape[2] == 3
+        S = pcm_i24.shape[0]
+        F = self.frame_count(S)
+        shape = (self.params.channels, F, self.n_rows)
+        pin = torch.cuda.is_available()
+        if index_out is None:
+            index_out = torch.empty(shape, dtype=torch.uint8, pin_memory=pin)
+        if want_grid and grid_out is None:
+            grid_out = torch.empty(shape, dtype=torch.float32, pin_memory=pin)
+        n = C.c_size_t()
+        self._check(self.lib.ems_process_host_i24(self.h, _ptr(pcm_i24), S, _ptr(grid_out),
+                                                  _ptr(index_out), C.byref(n)))
+        return grid_out, index_out
+
+    def scratch_bytes(self) -> int:
+        n = C.c_size_t()
+        self._check(self.lib.ems_scratch_bytes(self.h, C.byref(n)))
+        return n.value
+
     def colorize(self, index, lut_rgba):
         """index: CUDA u8 tensor (any shape); lut_rgba: 256 uint32 (numpy / CPU tensor, 0xAABBGGRR)
         -> CUDA int32 tensor of the same shape holding the packed pixels."""
@@ -288,9 +316,10 @@ class Engine:
         self._check(self.lib.ems_stream_load(self.h, blob, len(blob)))
 
     def stream_push(self, pcm_host, column_host):
-        """pcm_host: CPU fp32 [hop*channels] interleaved; column_host: CPU u8 [channels][n_rows].
+        """pcm_host: CPU fp32 (or int16, capture format) [hop*channels] interleaved; column_host: CPU u8 [channels][n_rows].
         -> (ready: bool, column_index: int)"""
+        import torch
         ready, idx = C.c_int(0), C.c_int64(-1)
-        self._check(self.lib.ems_stream_push(self.h, _ptr(pcm_host), _ptr(column_host),
-                                             C.byref(ready), C.byref(idx)))
+        fn = self.lib.ems_stream_push_i16 if pcm_host.dtype == torch.int16 else self.lib.ems_stream_push
+        self._check(fn(self.h, _ptr(pcm_host), _ptr(column_host), C.byref(ready), C.byref(idx)))
         return bool(ready.value), idx.value

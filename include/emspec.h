@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define EMS_ABI_VERSION 3
+#define EMS_ABI_VERSION 4
 
 typedef enum ems_status {
     EMS_OK = 0,
@@ -77,6 +77,11 @@ typedef struct ems_params {
                                level[m] = max(peak[m], lambda*level[m-1]), peak = loudest shaped
                                cell of column m, lambda = exp(-hop/(sample_rate * 1 s)); cells are
                                drawn at E / level^strength (the gate still sees E)      (0.0)  */
+    float    brightness;    /* "Brightness" (assets/settings.png, 44 %), used when agc_strength > 0:
+                               where on the colour scale the automatic gain places the running
+                               level — cells are drawn at E * T / level^strength with
+                               T = 10^(-(1 - brightness) * db_range / 10), so at full strength the
+                               loudest cell gets colour index 255 * brightness; in (0, 1]   (0.44) */
 } ems_params;
 
 typedef struct ems_handle ems_handle;
@@ -101,7 +106,7 @@ ems_status ems_create(const ems_params* params, ems_handle** out);
 ems_status ems_destroy(ems_handle* h);
 
 /* Live display controls (README.md:41 "changes are applied in real-time"): updates
- * db_range, gain, low_end_boost, smoothing, noise_gate_db, agc_strength and flags; n_fft / hop /
+ * db_range, gain, low_end_boost, smoothing, noise_gate_db, agc_strength, brightness and flags; n_fft / hop /
  * channels changes require a new handle (EMS_ERR_INVALID_ARG). */
 ems_status ems_update_display(ems_handle* h, const ems_params* params);
 
@@ -151,6 +156,15 @@ ems_status ems_process_host(ems_handle* h, const float* pcm_host, size_t n_sampl
 ems_status ems_process_host_i16(ems_handle* h, const int16_t* pcm_host, size_t n_samples_per_ch,
                                 float* grid_host, uint8_t* index_host, size_t* n_frames);
 
+/* int24 PCM, packed little-endian, interleaved [n_samples_per_ch][channels][3 bytes], full scale
+ * 2^23 (the other common capture / file format; 3/4 of the fp32 bytes); otherwise as above. */
+ems_status ems_process_host_i24(ems_handle* h, const uint8_t* pcm_host, size_t n_samples_per_ch,
+                                float* grid_host, uint8_t* index_host, size_t* n_frames);
+
+/* Device memory this handle holds for scratch right now (accumulator, flags, staging, tables of
+ * the smoothing / AGC scans) — ems_process_host* keep it independent of the stream length. */
+ems_status ems_scratch_bytes(const ems_handle* h, size_t* bytes);
+
 /* Colour map ("Color Map", /root/reference/README.md:15,45): applies a
  * 256-entry RGBA table (HOST pointer, packed 0xAABBGGRR like a byte-wise R,G,B,A store) to
  * n_cells colour indices on the device; rgba_dev receives n_cells 32-bit pixels in the same
@@ -171,6 +185,10 @@ ems_status ems_launch_count(const ems_handle* h, uint64_t* launches);
  * recommended) holds it and *column_index (nullable) its frame index.  Synchronous. */
 ems_status ems_stream_push(ems_handle* h, const float* pcm_host, uint8_t* column_host,
                            int* column_ready, int64_t* column_index);
+/* The same push with the hop in capture format: int16, interleaved [hop][channels], full scale
+ * 32768.  A stream may switch formats between pushes. */
+ems_status ems_stream_push_i16(ems_handle* h, const int16_t* pcm_host, uint8_t* column_host,
+                               int* column_ready, int64_t* column_index);
 /* Clears the ring, the rolling grid and the smoothing state. */
 ems_status ems_stream_reset(ems_handle* h);
 

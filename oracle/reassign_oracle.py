@@ -69,6 +69,7 @@ class Params:
     display_rows: int = 0        # 0: one row per bin; > 0: rows of the warped frequency axis
     freq_scale: float = 1.0      # README.md:48 "Frequency Scale" (used when display_rows > 0)
     agc_strength: float = 0.0    # README.md:14 "AGC" / settings.png "AGC Strength"; 0 = off
+    brightness: float = 0.44     # settings.png "Brightness 44 %": where the AGC draws the running level
 
     @property
     def n_bins(self) -> int:
@@ -234,15 +235,18 @@ def shaped_energy(grid: np.ndarray, prm: Params) -> np.ndarray:
 def agc_scale(E: np.ndarray, prm: Params) -> np.ndarray:
     """Automatic gain (README.md:14; SURVEY.md §8f-2, stand-in semantics): per column m
     level[m] = max(peak[m], lambda level[m-1]), peak[m] = max_r E[m, r], level[-1] = 0,
-    lambda = exp(-hop / (sample_rate * 1 s)); cells are drawn at E / level^strength."""
+    lambda = exp(-hop / (sample_rate * 1 s)); cells are drawn at E * T / level^strength, where the
+    "Brightness" control sets T = 10^(-(1 - brightness) db_range / 10): at full strength the loudest
+    cell of the running level gets colour index 255 * brightness."""
     lam = math.exp(-prm.hop / (prm.sample_rate * AGC_RELEASE_SECONDS))
     peak = E.max(axis=1) if E.shape[1] else np.zeros(E.shape[0])
     scale = np.ones(E.shape[0])
+    target = 10.0 ** (-(1.0 - prm.brightness) * prm.db_range / 10.0)
     lv = 0.0
     for m in range(E.shape[0]):
         lv = max(peak[m], lam * lv)
         if lv > 0.0:
-            scale[m] = lv ** (-prm.agc_strength)
+            scale[m] = target * lv ** (-prm.agc_strength)
     return scale
 
 
@@ -289,4 +293,28 @@ def synth_signal(n_samples: int, sample_rate: float = 48000.0, seed: int = 0,
     rng = np.random.default_rng(seed)
     x = 0.5 * np.sin(phase) + 0.25 * np.sin(2 * np.pi * fa * t) \
         + 0.125 * np.sin(2 * np.pi * fb * t) + 1e-3 * rng.standard_normal(n_samples)
+    return x.astype(np.float32)
+
+
+def synth_music(n_samples: int, sample_rate: float = 48000.0, seed: int = 0) -> np.ndarray:
+    """Dense, music-like test signal (stand-in for "system audio", README.md:36):
+    pink noise at about -26 dBFS rms, three notes with vibrato and 12 harmonics each (1/h roll-off,
+    repeating attack/decay envelopes, peaks near -20 dBFS) and a decaying noise burst every 0.25 s.
+    Unlike synth_signal almost every bin of every frame is above the default -65 dB gate."""
+    rng = np.random.default_rng(seed)
+    t = np.arange(n_samples, dtype=np.float64) / sample_rate
+    spec = np.fft.rfft(rng.standard_normal(n_samples))
+    f = np.fft.rfftfreq(n_samples, 1.0 / sample_rate)
+    spec[1:] /= np.sqrt(f[1:])
+    spec[0] = 0.0
+    pink = np.fft.irfft(spec, n_samples)
+    x = 0.05 * pink / np.sqrt(np.mean(pink * pink))
+    for i, f0 in enumerate((110.0, 196.0, 329.63)):
+        vib = 0.005 * f0 / 5.0 * np.sin(2 * np.pi * 5.0 * t + i)            # +-0.5 % at 5 Hz, as phase deviation / (2 pi)
+        env = np.exp(-3.0 * np.mod(t + 0.17 * i, 0.5)) * (1.0 - np.exp(-200.0 * np.mod(t + 0.17 * i, 0.5)))
+        for hn in range(1, 13):
+            if hn * f0 < 0.45 * sample_rate:
+                x += 0.1 / hn * env * np.sin(2 * np.pi * hn * (f0 * t + vib) + 0.3 * hn)
+    burst = np.exp(-60.0 * np.mod(t, 0.25)) * rng.standard_normal(n_samples)
+    x += 0.03 * burst
     return x.astype(np.float32)

@@ -112,32 +112,52 @@ def check_grid_rows(grid_gpu, x: np.ndarray, prm: orc.Params):
 
 
 def boundary_cells(x: np.ndarray, prm: orc.Params) -> np.ndarray:
-    """Cells a point may land in or leave because nearest-cell deposit is discontinuous: the
-    oracle's point sits within the coordinate tolerance of a rounding boundary (x.5 columns or
-    bins), so the fp32 coordinate may round to the neighbouring cell.  The tolerance is the
-    north_star 1e-3 plus the fp32 noise floor of the operators at that bin's level (same slack
-    as the validity flips in check_points).  Bin-per-row axis only."""
-    assert prm.display_rows == 0
+    """Cells [F][R] a point may land in or leave because nearest-cell deposit is discontinuous: the
+    oracle's point sits within the coordinate tolerance of a rounding boundary (x.5 columns, or a row
+    boundary of the bin-per-row or warped display axis), so the fp32 coordinate may round to the
+    neighbouring cell.  The tolerance is the north_star 1e-3 plus the fp32 noise floor of the operators
+    at that bin's level (same slack as the validity flips in check_points)."""
     dt_o, dk_o, e_o, raw = orc.reassign_points(x, prm, return_raw=True)
     F, B = e_o.shape
+    R = prm.n_rows
     valid = e_o > 0
     slack = 2e-6 * np.sqrt(raw.max() / np.maximum(raw, 1e-300))
     tol_t = COORD_TOL + slack * (prm.n_fft / 2) / prm.hop
     tol_k = COORD_TOL + slack
-    near_t = valid & (np.abs(dt_o - np.rint(dt_o)) > 0.5 - tol_t)
-    near_k = valid & (np.abs(dk_o - np.rint(dk_o)) > 0.5 - tol_k)
-    mask = np.zeros((F, B), bool)
-    for f, k in np.argwhere(near_t | near_k):
-        cols = {f + int(np.floor(dt_o[f, k])), f + int(np.ceil(dt_o[f, k]))} if near_t[f, k] else {f + int(np.rint(dt_o[f, k]))}
-        rows = {k + int(np.floor(dk_o[f, k])), k + int(np.ceil(dk_o[f, k]))} if near_k[f, k] else {k + int(np.rint(dk_o[f, k]))}
-        for c in cols:
-            for r in rows:
-                if 0 <= c < F and 0 <= r < B:
-                    mask[c, r] = True
+    k = np.arange(B)[None, :] + np.zeros((F, 1), np.int64)
+    f = np.arange(F)[:, None] + np.zeros((1, B), np.int64)
+    c_lo = f + np.rint(dt_o - tol_t).astype(np.int64)
+    c_hi = f + np.rint(dt_o + tol_t).astype(np.int64)
+    r_lo = orc.output_row(k, dk_o - tol_k, prm)
+    r_hi = orc.output_row(k, dk_o + tol_k, prm)
+    near = valid & ((c_lo != c_hi) | (r_lo != r_hi))
+    mask = np.zeros((F, R), bool)
+    for cc in (c_lo, c_hi):
+        for rr in (r_lo, r_hi):
+            c, r = cc[near], rr[near]
+            ok = (c >= 0) & (c < F) & (r >= 0) & (r < R)
+            mask[c[ok], r[ok]] = True
     return mask
 
 
-def check_index(idx_gpu, grid_o: np.ndarray, prm: orc.Params, x: np.ndarray | None = None):
+def check_grid_dense(grid_gpu, x: np.ndarray, prm: orc.Params, max_ambiguous: float = 0.25):
+    """Dense input (almost every bin kept): nearest-cell deposit moves the few points that sit within
+    fp32 error of a rounding boundary one cell over, which alone is ~1e-3 rel-L2 on the whole grid.
+    So: the total energy agrees to 1e-6, and the cells NOT fed by a boundary point agree to the
+    default 1e-4 rel-L2.  Returns (err, grid_o, ambiguous mask)."""
+    grid_o, _ = orc.process(x, prm)
+    g = np.asarray(grid_gpu, np.float64)
+    tot = grid_o.sum()
+    assert abs(g.sum() - tot) <= 1e-6 * tot, (g.sum(), tot)
+    amb = boundary_cells(x, prm)
+    assert amb.mean() <= max_ambiguous, f"{amb.mean()} of the cells are fed by a boundary point"
+    err = rel_l2(g[~amb], grid_o[~amb])
+    assert err <= ENERGY_TOL, f"grid rel-L2 {err} away from rounding boundaries"
+    return err, grid_o, amb
+
+
+def check_index(idx_gpu, grid_o: np.ndarray, prm: orc.Params, x: np.ndarray | None = None,
+                max_excused: float = 1e-4, max_off_by_one: float = 1e-3):
     """u8 colour index: a quantised float -> +-1 at rounding boundaries, flips allowed only
     for cells whose level sits on the gate.  With `x` given, cells fed by a point that sits on
     a deposit rounding boundary (boundary_cells) are exempt, at most 1e-4 of the image."""
@@ -151,9 +171,9 @@ def check_index(idx_gpu, grid_o: np.ndarray, prm: orc.Params, x: np.ndarray | No
     if x is not None and d.max() > 1:
         amb = boundary_cells(x, prm)
         excused = (d > 1) & amb
-        assert excused.mean() <= 1e-4, f"{excused.mean()} of cells moved across a deposit rounding boundary"
+        assert excused.mean() <= max_excused, f"{excused.mean()} of cells moved across a deposit rounding boundary"
         d = np.where(amb, 0, d)
     assert d.max() <= 1, f"colour index differs by {d.max()}"
     frac = float((d > 0).mean())
-    assert frac <= 1e-3, f"{frac} of cells off by one"
+    assert frac <= max_off_by_one, f"{frac} of cells off by one"
     return frac

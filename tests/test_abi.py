@@ -28,7 +28,7 @@ def test_header_symbols_all_exported(lib_built):
 def test_abi_version_and_status_strings(lib_built):
     import emspec
     lib = emspec.load()
-    assert lib.ems_abi_version() == 3
+    assert lib.ems_abi_version() == 4
     assert lib.ems_status_str(0) == b"ok"
     for s in range(1, 6):
         assert len(lib.ems_status_str(s)) > 0
@@ -42,6 +42,7 @@ def test_default_params_are_the_settings_png_preset(lib_built):
     assert abs(p.low_end_boost - 3.9) < 1e-6 and p.smoothing == 0 and p.noise_gate_db == -65
     assert p.flags & emspec.FLAG_REASSIGN and p.flags & emspec.FLAG_DETERMINISTIC
     assert p.display_rows == 0 and abs(p.freq_scale - 1.0) < 1e-6
+    assert p.agc_strength == 0 and abs(p.brightness - 0.44) < 1e-6        # settings.png "Brightness 44 %"
 
 
 def test_invalid_arguments_rejected_before_any_cuda_call(lib_built):
@@ -51,7 +52,8 @@ def test_invalid_arguments_rejected_before_any_cuda_call(lib_built):
     assert lib.ems_create(None, ctypes.byref(h)) == emspec.ERR_INVALID_ARG
     for bad in (dict(n_fft=1000), dict(n_fft=128), dict(n_fft=65536), dict(hop=0),
                 dict(hop=8192), dict(channels=0), dict(smoothing=1.0), dict(db_range=0.0),
-                dict(display_rows=1), dict(display_rows=-3), dict(freq_scale=-1.0), dict(agc_strength=1.5)):
+                dict(display_rows=1), dict(display_rows=-3), dict(freq_scale=-1.0), dict(agc_strength=1.5),
+                dict(brightness=0.0), dict(brightness=1.5)):
         p = emspec.default_params()
         for k, v in bad.items():
             setattr(p, k, v)
@@ -80,3 +82,43 @@ def test_product_never_imports_oracle():
                 txt = open(os.path.join(dp, f)).read()
                 assert "import reassign_oracle" not in txt and "from reassign_oracle" not in txt, f
                 assert "oracle/" not in txt.replace("oracle/reassign_oracle.py", "").replace("oracle/reassign_oracle.py::", ""), f
+
+
+def _build_abi_check(tmp_path):
+    """tests/c/abi_check.c compiled with gcc as plain C against include/emspec.h and linked to the library."""
+    import subprocess
+    import build_emspec
+    exe = str(tmp_path / "abi_check")
+    libdir = os.path.dirname(build_emspec.OUT)
+    cmd = ["gcc", "-std=c11", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+           os.path.join(ROOT, "tests", "c", "abi_check.c"), "-o", exe, "-L", libdir, "-l:libemspec.so",
+           f"-Wl,-rpath,{libdir}", "-lm"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    return exe
+
+
+def test_header_is_plain_c_and_layout_matches_the_ctypes_mirror(lib_built, tmp_path):
+    """the struct layout is checked by a C compiler (static asserts in abi_check.c), and
+    the offsets it prints equal those of the hand-written ctypes mirror."""
+    import subprocess
+    import emspec
+    exe = _build_abi_check(tmp_path)
+    out = subprocess.run([exe, "layout"], capture_output=True, text=True, check=True).stdout.split("\n")
+    got = dict(ln.split() for ln in out if ln.strip())
+    assert int(got.pop("sizeof")) == ctypes.sizeof(emspec.Params)
+    assert int(got.pop("abi")) == emspec.load().ems_abi_version()
+    names = [f[0] for f in emspec.Params._fields_]
+    assert sorted(got) == sorted(names)
+    for n in names:
+        assert int(got[n]) == getattr(emspec.Params, n).offset, n
+
+
+@pytest.mark.gpu
+def test_c_caller_end_to_end(lib_built, tmp_path):
+    """A C program (no Python, no torch) drives ems_create / ems_process_host / ems_destroy."""
+    import subprocess
+    exe = _build_abi_check(tmp_path)
+    res = subprocess.run([exe, "run"], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert "bad_columns 0" in res.stdout

@@ -205,7 +205,7 @@ def test_agc_level_recurrence():
     """AGC: peak hold with exponential release; strength 1 pins the loudest
     recent cell at 0 dB; strength 0 is the identity."""
     prm = orc.Params(n_fft=512, hop=128, gain=1.0, low_end_boost=1.0, agc_strength=1.0, db_range=60.0,
-                     noise_gate_db=-90.0)
+                     noise_gate_db=-90.0, brightness=1.0)
     grid = np.zeros((6, 257))
     grid[0, 5] = 1e-3
     grid[1, 7] = 1e-2
@@ -218,6 +218,12 @@ def test_agc_level_recurrence():
     assert idx[0, 5] == 255 and idx[1, 7] == 255 and idx[2, 9] < 255
     off = orc.postpass(grid, orc.Params(**{**prm.__dict__, "agc_strength": 0.0}))
     assert off[1, 7] == int(np.rint(255 * 40 / 60))
+    # "Brightness" (settings.png): the running level is drawn at index 255 * brightness
+    half = orc.Params(**{**prm.__dict__, "brightness": 0.44})
+    assert np.allclose(orc.agc_scale(grid, half), sc * 10 ** (-0.56 * 6.0))
+    idx = orc.postpass(grid, half)
+    assert idx[0, 5] == int(np.rint(255 * 0.44)) and idx[1, 7] == int(np.rint(255 * 0.44))
+    assert (orc.postpass(grid, orc.Params(**{**half.__dict__, "agc_strength": 0.0})) == off).all()   # only with the AGC on
 
 
 def test_drop_rule_is_decided_on_the_rounded_row():
