@@ -12,6 +12,14 @@ per GPU (clip-sharded, weak scaling, NCCL only for the final gather of per-rank 
                  out to pinned HOST memory (the whole a1-a5 path, copies inside the region).
   cpu_baseline : the float64 NumPy stand-in oracle (whole a1-a5 path) on the host cores.
 
+  batch        : configs[3] — 4096 clips x 60 s, n_fft=4096 hop=256, clip-sharded over the ranks
+                 (strong scaling: the same 4096 clips at every N), clips fed to the engine as planar
+                 channels in groups, per-clip checksums all_gathered at the end; the u8 images can
+                 also be gathered to rank 0 over NCCL (timed separately).
+  value_dense / pipeline_u8_dense / *_broadband : the same calls with every bin kept (gate -200 dB)
+                 and on a broadband signal (pink noise + harmonic stacks) — the worst cases of the
+                 epilogue and of the scatter.
+
 --impl reference times the oracle port (the only CPU implementation that exists: EM-Spec
 ships no source, /root/reference/README.md:73) on rank 0 with all host cores.
 """
@@ -162,9 +170,117 @@ def synth_device(S: int, seed: int, device):
     return x
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of stft_reassign_r16<store>, one `ncu --set full`
-# capture of a 224,969-frame launch (profiles/r01_ncu_stft_reassign_r16.txt): 5.6072 GB
-NCU_DRAM_BYTES_PER_FRAME = (129.329152e6 + 5.481495e9) / 224969
+def synth_broadband_device(S: int, seed: int, device):
+    """Dense, music-like signal generated on the device (the worst case of the epilogue and the
+    scatter): pink noise at -26 dBFS rms (spectral shaping per 2^22-sample block) + three notes
+    with 12 harmonics each (1/h roll-off, peaks near -20 dBFS, 5 Hz vibrato).  Almost every bin
+    of every frame clears the default -65 dB gate."""
+    import math
+    import torch
+    x = torch.empty(S, dtype=torch.float32, device=device)
+    g = torch.Generator(device=device).manual_seed(1000 + seed)
+    blk = 1 << 22
+    f = torch.fft.rfftfreq(blk, 1.0 / SR).to(device)
+    shape = torch.zeros_like(f)
+    shape[1:] = f[1:].rsqrt()
+    for s0 in range(0, S, blk):
+        s1 = min(S, s0 + blk)
+        pink = torch.fft.irfft(torch.fft.rfft(torch.randn(blk, device=device, generator=g)) * shape, blk)
+        pink = 0.05 * pink / pink.square().mean().sqrt()
+        t = torch.arange(s0, s1, device=device, dtype=torch.float64) / SR
+        v = torch.zeros(s1 - s0, dtype=torch.float64, device=device)
+        for i, f0 in enumerate((110.0, 196.0, 329.63)):
+            ph = f0 * t + 0.005 * f0 / 5.0 * torch.sin(2 * math.pi * 5.0 * t + i)
+            for hn in range(1, 13):
+                v += (0.1 / hn) * torch.sin(2 * math.pi * hn * ph + 0.3 * hn)
+        x[s0:s1] = v.float() + pink[: s1 - s0]
+    return x
+
+
+def gpu_numa_cpus(local: int):
+    """CPUs local to GPU `local` (sysfs local_cpulist of its PCI function), or None."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        txt = open(f"/sys/bus/pci/devices/{bdf}/local_cpulist").read().strip()
+        node = open(f"/sys/bus/pci/devices/{bdf}/numa_node").read().strip()
+        cpus = set()
+        for part in txt.split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        return sorted(cpus), int(node), bdf
+    except Exception:
+        return None
+
+
+def numa_bind(local: int, world: int):
+    """Pins this rank to its share of the CPUs local to its GPU, so that the pinned host buffers it
+    allocates afterwards are first-touched on that NUMA node.  Returns what was done (for the line)."""
+    info = gpu_numa_cpus(local)
+    if not info:
+        return {"bound": False, "why": "no sysfs topology for this GPU"}
+    cpus, node, bdf = info
+    allowed = sorted(os.sched_getaffinity(0))
+    cpus = [c for c in cpus if c in allowed] or allowed
+    # ranks whose GPUs share a node split its CPUs
+    per = max(1, len(cpus) // max(1, world))
+    mine = cpus[(local % max(1, len(cpus) // per)) * per:][:per] or cpus
+    try:
+        os.sched_setaffinity(0, mine)
+    except OSError as e:
+        return {"bound": False, "why": str(e), "numa_node": node}
+    return {"bound": True, "numa_node": node, "pci": bdf, "cpus": f"{mine[0]}-{mine[-1]}", "n_cpus": len(mine)}
+
+
+def pcie_ceiling(dev, world, barrier, nbytes_d2h: int, nbytes_h2d: int, dist=None):
+    """Bare copies, all ranks at once: D2H of nbytes_d2h into pinned memory while H2D of nbytes_h2d runs
+    on a second stream (what one e2e step moves, with no kernels).  -> aggregate GB/s over all ranks
+    (bytes of all ranks / slowest rank's time): the ceiling the e2e number is compared with."""
+    import torch
+    d = torch.empty(nbytes_d2h, dtype=torch.uint8, device=dev)
+    h = torch.empty(nbytes_d2h, dtype=torch.uint8, pin_memory=True)
+    xd = torch.empty(nbytes_h2d, dtype=torch.uint8, device=dev)
+    xh = torch.empty(nbytes_h2d, dtype=torch.uint8, pin_memory=True)
+    h.zero_(); xh.zero_()                      # first touch on this rank's NUMA node
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    def once():
+        with torch.cuda.stream(s1):
+            h.copy_(d, non_blocking=True)
+        with torch.cuda.stream(s2):
+            xd.copy_(xh, non_blocking=True)
+    once(); torch.cuda.synchronize()
+    barrier()
+    t0 = time.perf_counter()
+    reps = 3
+    for _ in range(reps):
+        once()
+    torch.cuda.synchronize()
+    dt = torch.tensor([(time.perf_counter() - t0) / reps], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    del d, h, xd, xh
+    torch.cuda.empty_cache()
+    return {"d2h_GBs": world * nbytes_d2h / dt.item() / 1e9, "h2d_GBs": world * nbytes_h2d / dt.item() / 1e9,
+            "step_ms": 1e3 * dt.item(),
+            "what": "bare concurrent cudaMemcpyAsync D2H + H2D of one e2e step's bytes per rank, all ranks at once, no kernels"}
+
+
+def kernel_profile():
+    """The committed ncu capture of the dominant kernel (profiles/r02_kernel_profile.json, written by
+    tools/ncu_summary.py --json): DRAM bytes and executed flops per frame, with the hash of the kernel
+    sources it was taken from.  bench.py recomputes the hash: a stale capture is reported as such."""
+    import hashlib
+    try:
+        prof = json.load(open(os.path.join(ROOT, "profiles", "r02_kernel_profile.json")))
+    except Exception:
+        return None
+    hsh = hashlib.sha256()
+    csrc = os.path.join(ROOT, "em-spec_b200", "csrc")
+    for fn in sorted(os.listdir(csrc)):
+        hsh.update(open(os.path.join(csrc, fn), "rb").read())
+    prof["stale"] = prof.get("csrc_sha16") != hsh.hexdigest()[:16]
+    return prof
 
 
 def peaks():
@@ -228,6 +344,125 @@ def run_reference(args):
     return 0
 
 
+def time_calls(fn, steps, warmup, barrier=None):
+    """CUDA-event time of `steps` calls of fn on the current stream after `warmup` calls -> ms per call."""
+    import torch
+    for _ in range(warmup):
+        fn()
+    if barrier:
+        barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def run_batch(args, emspec, rank, world, dev, dist, barrier):
+    """configs[3]: `batch_clips` clips x 60 s at 48 kHz, n_fft=4096 hop=256, clip-sharded (strong
+    scaling: the same clips at every N).  A rank holds its clips' PCM in HBM and feeds them to the engine
+    as planar channels, `batch_group` clips per call; each group's u8 image is reduced to two per-clip
+    checksums; one all_gather of the checksums ends the step (the job's only collective).  With
+    --batch-gather (default when N > 1) one more step also ships every image to rank 0 over NCCL
+    (isend / irecv per group, overlapped with the next group's kernels), timed separately."""
+    import hashlib
+    import torch
+    from emspec.batch import shard_clips
+    C, hop = args.batch_clips, 256
+    S = 60 * SR
+    F, B = frame_count(S, N_FFT, hop), N_FFT // 2 + 1
+    lo, hi = shard_clips(C, rank, world)
+    n = hi - lo
+    G = min(args.batch_group, n)
+    while n % G:
+        G -= 1
+    pcm_all = torch.empty((n, S), dtype=torch.float32, device=dev)
+    for c in range(n):
+        pcm_all[c] = synth_device(S, lo + c, dev)
+    eng = emspec.Engine(n_fft=N_FFT, hop=hop, channels=G)
+    eng.use_torch_stream()
+    idx = [torch.empty((G, F, B), dtype=torch.uint8, device=dev) for _ in range(2)]
+    sums = torch.zeros((n, 2), dtype=torch.int64, device=dev)
+    all_sums = [torch.empty_like(sums) for _ in range(world)] if world > 1 else None
+    images = None
+
+    def step(gather=False):
+        pend = [None, None]
+        reqs = []
+        for gi, c0 in enumerate(range(0, n, G)):
+            buf = idx[gi & 1]
+            if pend[gi & 1] is not None:
+                pend[gi & 1].wait()                      # the image this buffer held has been sent
+            eng.process_grid(pcm_all[c0:c0 + G], out=(None, buf))
+            sums[c0:c0 + G, 0] = buf.view(G, -1).sum(dim=1, dtype=torch.int64)
+            sums[c0:c0 + G, 1] = buf[:, 3::7, :].sum(dim=(1, 2), dtype=torch.int64)
+            if gather:
+                if rank == 0:
+                    images[c0:c0 + G].copy_(buf)
+                    ops = [dist.P2POp(dist.irecv, images[shard_clips(C, p_, world)[0] + c0:][:G], p_) for p_ in range(1, world)]
+                    reqs += dist.batch_isend_irecv(ops)
+                else:
+                    pend[gi & 1] = dist.isend(buf, 0)
+        for r in reqs + [q for q in pend if q is not None]:
+            r.wait()
+        if world > 1:
+            dist.all_gather(all_sums, sums)
+
+    for _ in range(args.batch_warmup):
+        step()
+    barrier()
+    l0 = eng.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.batch_steps):
+        step()
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    launches = eng.launch_count() - l0
+    every = torch.cat(all_sums) if world > 1 else sums
+    digest = hashlib.sha256(every.cpu().numpy().tobytes()).hexdigest()[:16]
+    res = {"workload": f"configs[3] batch: {C} clips x 60 s 48 kHz, n_fft=4096 hop=256, clip-sharded x{world} "
+                       f"({n} clips per rank, {G} per call as planar channels), PCM resident in HBM -> u8 image -> per-clip checksums",
+           "value": C * F * args.batch_steps / (ms.item() * 1e-3), "unit": UNIT, "scaling": "strong",
+           "steps": args.batch_steps, "warmup": args.batch_warmup, "ms_per_step": ms.item() / args.batch_steps,
+           "clips": C, "frames_per_clip": F, "clip_range_rank0": [lo, hi], "clips_per_call": G,
+           "gpu_launches": int(launches), "clip_checksums_sha16": digest,
+           "checksum_of": "per-clip (sum of all index bytes, sum over columns f % 7 == 3), all clips in clip order: identical at every N",
+           "pcm_bytes_per_rank": int(pcm_all.numel() * 4), "scratch_bytes_per_rank": int(eng.scratch_bytes())}
+    if world > 1 and not args.no_batch_gather:
+        if rank == 0:
+            images = torch.empty((C, F, B), dtype=torch.uint8, device=dev)
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        step(gather=True)
+        g1.record()
+        barrier()
+        gms = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device=dev)
+        dist.all_reduce(gms, op=dist.ReduceOp.MAX)
+        ok = None
+        if rank == 0:      # the gathered images carry the checksums their owners computed
+            every = torch.cat(all_sums)
+            probe = [shard_clips(C, p_, world)[0] for p_ in range(world)] + [C - 1]
+            ok = all(int(images[c].sum(dtype=torch.int64)) == int(every[c, 0]) for c in probe)
+        recv = (C - n) * F * B
+        res["image_gather"] = {"ms_step_with_gather": gms.item(), "ms_step_without": ms.item() / args.batch_steps,
+                               "bytes_to_rank0": recv, "GBs_if_exposed": recv / max(gms.item() - ms.item() / args.batch_steps, 1e-3) / 1e6,
+                               "verified": ok,
+                               "what": "one more step in which every group's u8 image also goes to rank 0 (NCCL isend / batched irecv, "
+                                       "double-buffered, overlapped with the next group's kernels)"}
+        images = None
+    eng.close()
+    del pcm_all, idx
+    torch.cuda.empty_cache()
+    return res
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -240,6 +475,7 @@ def run_ours(args):
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    bind = {"bound": False, "why": "--no-bind"} if args.no_bind else numa_bind(local, world)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -247,6 +483,12 @@ def run_ours(args):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def allmax(ms):
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item()
 
     S = int(args.seconds * SR)
     F = frame_count(S, N_FFT, HOP)
@@ -269,20 +511,13 @@ def run_ours(args):
     e0.record()
     for _ in range(args.steps):
         eng.process_points(pcm, out=out)      # one kernel launch per step, nothing else on the stream
-    summary = torch.tensor([F], dtype=torch.int64, device=dev)
-    if world > 1:   # the final gather of the batch job: per-rank frame counts
-        gathered = [torch.empty_like(summary) for _ in range(world)]
-        dist.all_gather(gathered, summary)
     e1.record()
     barrier()
     launches = eng.launch_count() - l0
     my_ms = e0.elapsed_time(e1)
     kern_last_ms = eng.stage_ms(emspec.STAGE_POINTS)   # library's own events, last step (cross-check)
-    ms = torch.tensor([my_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    total_ms = allmax(my_ms)
     clocks = sampler.stop(t_region0, time.perf_counter()) if rank == 0 else None
-    total_ms = ms.item()
     frames_all = F * world
     value = frames_all * args.steps / (total_ms * 1e-3)
 
@@ -291,42 +526,59 @@ def run_ours(args):
     kern_ms = my_ms / args.steps
     peak, peak_src = peaks()
     achieved = b_points(N_FFT, HOP) * F / (kern_ms * 1e-3) / 1e9
+    prof = kernel_profile()
+
+    # ---- the worst cases of the same call: every bin kept, and a broadband signal
+    worst = {}
+    pcm_bb = None
+    if not args.no_dense:
+        dense = emspec.Engine(n_fft=N_FFT, hop=HOP, noise_gate_db=-200.0)
+        dense.use_torch_stream()
+        ms = allmax(time_calls(lambda: dense.process_points(pcm, out=out), max(3, args.steps // 4), 2, barrier))
+        worst["value_dense"] = {"value": frames_all / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms,
+                                "what": "ems_process_points, same stream, noise gate -200 dB: every bin runs the "
+                                        "reassignment arithmetic and is stored"}
+        dense.close()
+        pcm_bb = synth_broadband_device(S, seed=rank, device=dev)
+        ms = allmax(time_calls(lambda: eng.process_points(pcm_bb, out=out), max(3, args.steps // 4), 2, barrier))
+        worst["value_broadband"] = {"value": frames_all / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms,
+                                    "kept_fraction": float(torch.count_nonzero(out[2])) / out[2].numel(),
+                                    "what": "ems_process_points at the default -65 dB gate on a broadband signal: pink noise "
+                                            "(-26 dBFS rms) + three 12-harmonic notes with vibrato (peaks near -20 dBFS)"}
 
     # ---- whole pipeline device-resident (extra, not the headline): ems_process_grid -> u8
     pipe = None
     if not args.no_pipeline:
+        del out
+        torch.cuda.empty_cache()
         idx = torch.empty((1, F, B), dtype=torch.uint8, device=dev)
-        for _ in range(2):
-            eng.process_grid(pcm, out=(None, idx))
-        barrier()
-        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        p0.record()
-        for _ in range(args.steps):
-            eng.process_grid(pcm, out=(None, idx))
-        p1.record()
-        barrier()
-        pms = torch.tensor([p0.elapsed_time(p1)], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(pms, op=dist.ReduceOp.MAX)
-        pipe = {"value": frames_all * args.steps / (pms.item() * 1e-3), "unit": UNIT,
+        ms = allmax(time_calls(lambda: eng.process_grid(pcm, out=(None, idx)), args.steps, 2, barrier))
+        pipe = {"value": frames_all / (ms * 1e-3), "unit": UNIT,
                 "what": "ems_process_grid: PCM in HBM -> u8 colour-index image in HBM (a1-a5, fused deposit)"}
-        # batch bookkeeping (outside any timed region): every rank learns every clip's summary
-        from emspec.batch import ClipSummary, gather_summaries, image_checksum, shard_clips
-        lo, hi = shard_clips(world, rank, world)          # one 1 h clip per GPU
-        mine = [ClipSummary(c, F, 0.0, image_checksum(idx)) for c in range(lo, hi)]
-        allc = gather_summaries(mine, world, device=dev)
-        pipe["clips_gathered"] = len(allc)
-        pipe["clip_checksums"] = [c.checksum for c in allc]
+        if not args.no_dense:
+            dense = emspec.Engine(n_fft=N_FFT, hop=HOP, noise_gate_db=-200.0)
+            dense.use_torch_stream()
+            ms = allmax(time_calls(lambda: dense.process_grid(pcm, out=(None, idx)), max(3, args.steps // 4), 2, barrier))
+            worst["pipeline_u8_dense"] = {"value": frames_all / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms,
+                                          "what": "ems_process_grid with the gate at -200 dB: 2,049 deposits per frame, every "
+                                                  "64-row block of the image dirty"}
+            dense.close()
+            ms = allmax(time_calls(lambda: eng.process_grid(pcm_bb, out=(None, idx)), max(3, args.steps // 4), 2, barrier))
+            worst["pipeline_u8_broadband"] = {"value": frames_all / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms,
+                                              "what": "ems_process_grid at the default gate on the broadband signal"}
         del idx
+    pcm_bb = None
+    out = None
+    torch.cuda.empty_cache()
 
     # ---- end to end: pinned host PCM -> pinned host u8 image through ems_process_host
     e2e = None
     if not args.no_e2e:
-        del out
-        torch.cuda.empty_cache()
+        ceiling = pcie_ceiling(dev, world, barrier, F * B, S * 4, dist)
         pcm_host = torch.empty((1, S), dtype=torch.float32, pin_memory=True)
         pcm_host.copy_(pcm[None, :])
         idx_host = torch.empty((1, F, B), dtype=torch.uint8, pin_memory=True)
+        idx_host.zero_()
         heng = emspec.Engine(n_fft=N_FFT, hop=HOP, noise_gate_db=args.gate_db)   # on its own stream, as an application would
         for _ in range(max(1, min(args.warmup, 2))):
             heng.process_host(pcm_host, index_out=idx_host)
@@ -338,17 +590,22 @@ def run_ours(args):
             heng.process_host(pcm_host, index_out=idx_host)      # returns with the image in host memory
             step_s.append(time.perf_counter() - ts)
         torch.cuda.synchronize()
-        wall_s = time.perf_counter() - t0        # the K steps, not the teardown (freeing 26 GB can take a second)
+        wall_s = time.perf_counter() - t0
+        scratch = heng.scratch_bytes()
         heng.close()
-        wall = torch.tensor([wall_s], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(wall, op=dist.ReduceOp.MAX)
-        e2e = {"value": frames_all * args.steps / wall.item(), "unit": UNIT,
+        wall = allmax(wall_s)
+        e2e = {"value": frames_all * args.steps / wall, "unit": UNIT,
                "h2d_bytes_per_step": S * 4 * world, "d2h_bytes_per_step": F * B * world,
                "step_ms": {"min": 1e3 * min(step_s), "median": 1e3 * sorted(step_s)[len(step_s) // 2],
                            "max": 1e3 * max(step_s), "first": 1e3 * step_s[0]},
+               "achieved_d2h_gbs": F * B * world * args.steps / wall / 1e9,
+               "pcie_ceiling_gbs": ceiling["d2h_GBs"], "pcie_ceiling": ceiling,
+               "frac_of_pcie_ceiling": (F * B * world * args.steps / wall / 1e9) / ceiling["d2h_GBs"],
+               "engine_scratch_bytes": int(scratch), "numa": bind,
                "what": "ems_process_host: pinned host fp32 PCM -> pinned host u8 colour-index "
-                       "image [F][B] (a1-a5), chunked copies overlapped with compute"}
+                       "image [F][B] (a1-a5), chunked copies overlapped with compute, O(chunk) device memory; "
+                       "bound by the D2H of the image (2,049 bytes per frame)"}
+        del pcm_host, idx_host
 
     # ---- streaming latency (configs[1]): wall time of ems_stream_push, host hop in -> final
     # column in pinned host memory, one frame per launch
@@ -387,15 +644,7 @@ def run_ours(args):
             e4.use_torch_stream()
             F4 = frame_count(S4, n4, h4)
             o4 = tuple(torch.empty((1, F4, n4 // 2 + 1), dtype=torch.float32, device=dev) for _ in range(3))
-            for _ in range(3):
-                e4.process_points(pcm[:S4], out=o4)
-            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            s0.record()
-            for _ in range(5):
-                e4.process_points(pcm[:S4], out=o4)
-            s1.record()
-            torch.cuda.synchronize()
-            ms4 = s0.elapsed_time(s1) / 5
+            ms4 = time_calls(lambda: e4.process_points(pcm[:S4], out=o4), 5, 3)
             gbs = b_points(n4, h4) * F4 / (ms4 * 1e-3) / 1e9
             sweep.append({"n_fft": n4, "hop": h4, "frames": F4, "frames_per_s": F4 / (ms4 * 1e-3),
                           "algorithmic_GBs": gbs, "frac_of_peak": gbs / peak})
@@ -419,15 +668,20 @@ def run_ours(args):
         for _ in range(args.steps):
             deng.process_host_i16(q_host, index_out=didx)
         torch.cuda.synchronize()
-        wall = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(wall, op=dist.ReduceOp.MAX)
-        e2e_display = {"value": frames_all * args.steps / wall.item(), "unit": UNIT,
+        wall = allmax(time.perf_counter() - t0)
+        e2e_display = {"value": frames_all * args.steps / wall, "unit": UNIT,
                        "h2d_bytes_per_step": S * 2 * world, "d2h_bytes_per_step": F * rows * world,
                        "what": "ems_process_host_i16: pinned host int16 PCM -> pinned host u8 image "
                                "[F][546] on the warped frequency axis (display_rows=546, freq_scale=1)"}
         deng.close()
         del q_host, didx
+    del pcm
+    torch.cuda.empty_cache()
+
+    # ---- configs[3]: the batch, clip-sharded (the multi-GPU workload north_star names)
+    batch = None
+    if not args.no_batch:
+        batch = run_batch(args, emspec, rank, world, dev, dist, barrier)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -438,6 +692,26 @@ def run_ours(args):
                          "NumPy/SciPy stand-in oracle a1-a5, one process per core, best of 2"}
 
     if rank == 0:
+        roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None,
+                "algorithmic_bytes_per_launch": b_points(N_FFT, HOP) * F,
+                "peak_source": peak_src,
+                "kernel": "stft_reassign (fused frame gather + 3-window STFT + reassignment)",
+                "kernel_ms": kern_ms, "kernel_ms_last_step_lib_events": kern_last_ms,
+                "bytes_per_frame": b_points(N_FFT, HOP),
+                "frac_of_nominal_8TBs": achieved / 8000.0}
+        if prof:
+            fps = F / (kern_ms * 1e-3)
+            if not prof["stale"] and args.gate_db == -65.0:
+                roof["traffic"] = prof["dram_bytes_per_frame"] * F
+            roof["traffic_source"] = {"file": "profiles/r02_kernel_profile.json", "kernel": prof.get("kernel"),
+                                      "frames_in_capture": prof.get("frames"), "csrc_sha16": prof.get("csrc_sha16"),
+                                      "stale": prof["stale"],
+                                      "unit": "bytes per launch = ncu dram bytes per frame of the capture x frames of this launch"}
+            roof["fp32_executed"] = {"flops_per_frame": prof.get("flops_per_frame"),
+                                     "frac_of_74.45TF": fps * prof.get("flops_per_frame", 0) / 74.45e12,
+                                     "how": "2 x FFMA + FADD + FMUL thread-level counts (packed x2) of the SASS mix of the ncu capture / frames",
+                                     "survey_count_483378_frac": fps * 483378 / 74.45e12}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
@@ -446,20 +720,11 @@ def run_ours(args):
                                    "n_fft=4096 hop=128 fused STFT+reassignment -> points, one stream per GPU",
                        "n_fft": N_FFT, "hop": HOP, "frames_per_gpu": F, "samples_per_gpu": S,
                        "l2_policy": "inputs (0.69 GB) and outputs (33 GB) larger than L2, no flush needed",
-                       "parallelism": f"clip-sharded x{world}, NCCL all_gather of per-rank summaries only"},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak,
-                         "traffic": NCU_DRAM_BYTES_PER_FRAME * F if args.gate_db == -65.0 else None,
-                         "traffic_unit": "bytes per launch (ncu dram bytes per frame of a 224,969-frame "
-                                         "launch x frames of this launch; algorithmic = bytes_per_frame x frames)",
-                         "algorithmic_bytes_per_launch": b_points(N_FFT, HOP) * F,
-                         "peak_source": peak_src,
-                         "kernel": "stft_reassign (fused frame gather + 3-window STFT + reassignment)",
-                         "kernel_ms": kern_ms, "kernel_ms_last_step_lib_events": kern_last_ms,
-                         "bytes_per_frame": b_points(N_FFT, HOP),
-                         "frac_of_nominal_8TBs": achieved / 8000.0,
-                         "fp32_frac_of_74.45TF": (F / (kern_ms * 1e-3)) * 483378 / 74.45e12},
-            "cpu_baseline": cpu, "e2e": e2e, "pipeline_u8": pipe, "e2e_display_rows": e2e_display, "stream_latency": stream, "nfft_sweep": sweep, "gpu_launches": int(launches),
+                       "parallelism": f"one stream per GPU x{world} (replicas, no data-path collective); the clip-sharded "
+                                      "multi-GPU workload is the `batch` key"},
+            "roofline": roof,
+            "cpu_baseline": cpu, "e2e": e2e, "pipeline_u8": pipe, "worst_case": worst or None, "batch": batch,
+            "e2e_display_rows": e2e_display, "stream_latency": stream, "nfft_sweep": sweep, "gpu_launches": int(launches),
             "clocks": clocks,
         }
         emit_json(line)
@@ -486,6 +751,14 @@ def main():
     ap.add_argument("--no-display", action="store_true")
     ap.add_argument("--no-sweep", action="store_true")
     ap.add_argument("--stream-pushes", type=int, default=5000)
+    ap.add_argument("--no-dense", action="store_true", help="skip the worst-case (dense / broadband) measurements")
+    ap.add_argument("--no-batch", action="store_true", help="skip configs[3]")
+    ap.add_argument("--no-batch-gather", action="store_true", help="skip the NCCL image gather of the batch (N > 1)")
+    ap.add_argument("--no-bind", action="store_true", help="do not pin the rank to its GPU's NUMA node")
+    ap.add_argument("--batch-clips", type=int, default=4096)
+    ap.add_argument("--batch-group", type=int, default=64, help="clips per engine call (planar channels)")
+    ap.add_argument("--batch-steps", type=int, default=3)
+    ap.add_argument("--batch-warmup", type=int, default=1)
     args = ap.parse_args()
     claim_stdout()
     return run_reference(args) if args.impl == "reference" else run_ours(args)

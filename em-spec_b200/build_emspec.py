@@ -34,20 +34,24 @@ def _stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not _stale():
+def build(force: bool = False, verbose: bool = False, out: str | None = None, defines=()) -> str:
+    """`out` / `defines`: experimental builds for A/B runs (tools/variant_check.py), e.g.
+    build(out="gpurun_out/libx.so", defines=["EMS_R64_BASES=6"]); the product build takes neither."""
+    if out is None and not force and not _stale():
         return OUT
-    cmd = [_nvcc(), *NVCC_FLAGS]
+    cmd = [_nvcc(), *NVCC_FLAGS, *[f"-D{d}" for d in defines]]
     if verbose:
         cmd += ["-Xptxas", "-v"]
-    cmd += ["-o", OUT, *[os.path.join(CSRC, s) for s in SOURCES]]
+    cmd += ["-o", out or OUT, *[os.path.join(CSRC, s) for s in SOURCES]]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed building libemspec.so")
-    return OUT
+    return out or OUT
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    defs = [a[2:] for a in sys.argv[1:] if a.startswith("-D")]
+    outs = [a[2:] for a in sys.argv[1:] if a.startswith("-o")]
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, out=outs[0] if outs else None, defines=defs))

@@ -17,6 +17,7 @@
 #include "scatter_post.cuh"
 #include "stft_generic.cuh"
 #include "stft_r16.cuh"
+#include "stft_r64.cuh"
 #include "stream.cuh"
 
 namespace ems {
@@ -72,6 +73,7 @@ struct ems_handle {
         size_t acc_bytes = 0;
     } st;
     bool force_generic = false;         // EMS_FORCE_GENERIC=1: bypass the tuned kernels (A/B tests)
+    int kernel_variant = 0;             // EMS_KERNEL_VARIANT: experimental kernel selection (A/B runs); 0 = default
     char err[256] = "";
 };
 
@@ -230,6 +232,30 @@ static ems_status launch_r16(ems_handle* h, const StftArgs& a) {
     return EMS_OK;
 }
 
+// n_fft = 4096, single-exchange variant (64 x 64 in two passes, 4 workers x 64 threads).
+static ems_status launch_r64(ems_handle* h, const StftArgs& a) {
+    int tile_T = r64::tile_frames(a.hop);
+    if (tile_T < 1) return EMS_ERR_UNSUPPORTED;
+    const long long per_ch = a.f_end - a.f_begin;
+    const long long want = (per_ch * a.channels + h->sm_count - 1) / h->sm_count;
+    const long long t = ((want + r64::kWorkers - 1) / r64::kWorkers) * r64::kWorkers;
+    if (t < tile_T) tile_T = (int)std::max<long long>(t, 1);
+    const size_t smem = (size_t)r64::kFixedBytes + 2 * (size_t)r64::kTileFloats * sizeof(float) + r16::kSyncBytes;
+    void (*kern)(const StftArgs, const int) =
+        a.mode == kStorePoints ? r64::stft_reassign_r64<kStorePoints>
+        : a.mode == kDepositU64 ? r64::stft_reassign_r64<kDepositU64>
+                                : r64::stft_reassign_r64<kDepositF32>;
+    EMS_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, r16::kMaxSmem));
+    const long long n_tiles = ((per_ch + tile_T - 1) / tile_T) * a.channels;
+    long long grid = h->sm_count;
+    if (grid > n_tiles) grid = n_tiles;
+    if (grid < 1) return EMS_OK;
+    kern<<<(unsigned)grid, r64::kThreads64, smem, h->stream>>>(a, tile_T);
+    ++h->launches;
+    EMS_CUDA(h, cudaGetLastError());
+    return EMS_OK;
+}
+
 // Tuned kernels for n_fft = 4096 R0 (R0 = 2, 4): frames read straight from global memory.
 template <int R0>
 static ems_status launch_r16_large(ems_handle* h, const StftArgs& a) {
@@ -281,7 +307,7 @@ static ems_status launch_stft(ems_handle* h, const StftArgs& a) {
             case 512: s = launch_r16<2>(h, a); break;
             case 1024: s = launch_r16<4>(h, a); break;
             case 2048: s = launch_r16<8>(h, a); break;
-            case 4096: s = launch_r16<16>(h, a); break;
+            case 4096: s = h->kernel_variant == 64 ? launch_r64(h, a) : launch_r16<16>(h, a); break;
             case 8192: s = launch_r16_large<2>(h, a); break;
             case 16384: s = launch_r16_large<4>(h, a); break;
             case 32768: s = launch_r16_32k(h, a); break;
@@ -636,6 +662,7 @@ ems_status ems_create(const ems_params* params, ems_handle** out) {
     if (!h) return EMS_ERR_NOMEM;
     h->prm = *params;
     { const char* fg = getenv("EMS_FORCE_GENERIC"); h->force_generic = fg && fg[0] == '1'; }
+    { const char* kv = getenv("EMS_KERNEL_VARIANT"); h->kernel_variant = kv ? atoi(kv) : 0; }
     auto bail = [&](ems_status s) { ems_destroy(h); return s; };
     if (cudaGetDevice(&h->device) != cudaSuccess) return bail(EMS_ERR_CUDA);
     cudaDeviceProp prop{};
