@@ -396,15 +396,14 @@ def run_batch(args, emspec, rank, world, dev, dist, barrier):
             if pend[gi & 1] is not None:
                 pend[gi & 1].wait()                      # the image this buffer held has been sent
             eng.process_grid(pcm_all[c0:c0 + G], out=(None, buf))
-            sums[c0:c0 + G, 0] = buf.view(G, -1).sum(dim=1, dtype=torch.int64)
-            sums[c0:c0 + G, 1] = buf[:, 3::7, :].sum(dim=(1, 2), dtype=torch.int64)
+            eng.image_summary(buf, out=sums[c0:c0 + G])
             if gather:
                 if rank == 0:
                     images[c0:c0 + G].copy_(buf)
                     ops = [dist.P2POp(dist.irecv, images[shard_clips(C, p_, world)[0] + c0:][:G], p_) for p_ in range(1, world)]
                     reqs += dist.batch_isend_irecv(ops)
                 else:
-                    pend[gi & 1] = dist.isend(buf, 0)
+                    pend[gi & 1] = dist.batch_isend_irecv([dist.P2POp(dist.isend, buf, 0)])[0]
         for r in reqs + [q for q in pend if q is not None]:
             r.wait()
         if world > 1:
@@ -432,11 +431,12 @@ def run_batch(args, emspec, rank, world, dev, dist, barrier):
            "steps": args.batch_steps, "warmup": args.batch_warmup, "ms_per_step": ms.item() / args.batch_steps,
            "clips": C, "frames_per_clip": F, "clip_range_rank0": [lo, hi], "clips_per_call": G,
            "gpu_launches": int(launches), "clip_checksums_sha16": digest,
-           "checksum_of": "per-clip (sum of all index bytes, sum over columns f % 7 == 3), all clips in clip order: identical at every N",
+           "checksum_of": "ems_image_summary per clip (sum of the index bytes, position-weighted sum), all clips in clip order: identical at every N",
            "pcm_bytes_per_rank": int(pcm_all.numel() * 4), "scratch_bytes_per_rank": int(eng.scratch_bytes())}
     if world > 1 and not args.no_batch_gather:
         if rank == 0:
             images = torch.empty((C, F, B), dtype=torch.uint8, device=dev)
+        step(gather=True)        # warm-up: NCCL sets its peer-to-peer channels up on first use
         barrier()
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         g0.record()

@@ -1047,6 +1047,21 @@ ems_status ems_colorize(ems_handle* h, const uint8_t* index_dev, size_t n_cells,
     return finish(h);
 }
 
+ems_status ems_image_summary(ems_handle* h, const uint8_t* index_dev, size_t n_frames, uint64_t* summary_dev) {
+    if (!h) return EMS_ERR_INVALID_ARG;
+    if (!index_dev || !summary_dev) return fail(h, EMS_ERR_INVALID_ARG, "null buffer");
+    const int C = h->prm.channels;
+    EMS_CUDA(h, cudaMemsetAsync(summary_dev, 0, (size_t)C * 2 * sizeof(uint64_t), h->stream));
+    const size_t n = n_frames * (size_t)rows_of(h->prm);
+    if (n == 0) return finish(h);
+    unsigned bx = (unsigned)std::min<size_t>((n / 16 + 255) / 256 + 1, (size_t)std::max(1, h->sm_count * 8 / C));
+    if (bx < 1) bx = 1;
+    image_summary_kernel<<<dim3(bx, C), 256, 0, h->stream>>>(index_dev, n, (unsigned long long*)summary_dev);
+    ++h->launches;
+    EMS_CUDA(h, cudaGetLastError());
+    return finish(h);
+}
+
 ems_status ems_stage_ms(ems_handle* h, int stage, float* ms) {
     if (!h || !ms || stage < 0 || stage >= EMS_STAGE_COUNT) return EMS_ERR_INVALID_ARG;
     if (!h->ev_valid[stage]) return fail(h, EMS_ERR_STATE, "stage %d did not run", stage);

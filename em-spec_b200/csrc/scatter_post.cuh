@@ -356,6 +356,44 @@ colorize_kernel(const uint8_t* __restrict__ index, uint32_t* __restrict__ rgba, 
     for (size_t i = head + nvec * 16 + tid; i < n; i += nth) rgba[i] = lut[index[i]];
 }
 
+// Per-channel summary of a u8 image of `n` bytes per channel: out[ch] = (sum of bytes, sum of
+// byte * (1 + pos mod 65521)), 64-bit wrapping.  grid (blocks, channels); 16-byte loads on the aligned
+// body, byte loads at the ends; one 64-bit red pair per block.
+__global__ void __launch_bounds__(256)
+image_summary_kernel(const uint8_t* __restrict__ img, size_t n, unsigned long long* __restrict__ out) {
+    const uint8_t* p = img + (size_t)blockIdx.y * n;
+    const size_t head = min(n, (size_t)((16 - ((uintptr_t)p & 15)) & 15));
+    const size_t nvec = (n - head) / 16;
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
+    unsigned long long s0 = 0, s1 = 0;
+    auto add = [&](size_t pos, unsigned b) { s0 += b; s1 += (unsigned long long)b * (1ull + pos % 65521ull); };
+    for (size_t i = tid; i < head; i += nth) add(i, p[i]);
+    const uint4* v = reinterpret_cast<const uint4*>(p + head);
+    for (size_t j = tid; j < nvec; j += nth) {
+        const uint4 q = __ldg(v + j);
+        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+        const size_t pos0 = head + 16 * j;
+        unsigned m = (unsigned)(pos0 % 65521ull);            // position modulus, advanced incrementally
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+            const unsigned b = (w[e >> 2] >> (8 * (e & 3))) & 255u;
+            s0 += b;
+            s1 += (unsigned long long)(b * (m + 1u));
+            m = m + 1u == 65521u ? 0u : m + 1u;
+        }
+    }
+    for (size_t i = head + 16 * nvec + tid; i < n; i += nth) add(i, p[i]);
+#pragma unroll
+    for (int d = 16; d; d >>= 1) {
+        s0 += __shfl_xor_sync(0xffffffffu, s0, d);
+        s1 += __shfl_xor_sync(0xffffffffu, s1, d);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        red_add_u64(out + 2 * blockIdx.y, s0);
+        red_add_u64(out + 2 * blockIdx.y + 1, s1);
+    }
+}
+
 // Clears the dirty flags of columns [c0, c1) of every (channel, bin block) row.
 // `ncols` columns per row (F, or the ring size), column c sits at slot c & mask.
 __global__ void clear_flags_kernel(unsigned char* __restrict__ flags, long long ncols, long long mask,

@@ -62,6 +62,7 @@ _SIG = {
     "ems_process_host_i16": (C.c_int, [_VP, _FP, C.c_size_t, _FP, _U8P, C.POINTER(C.c_size_t)]),
     "ems_process_host_i24": (C.c_int, [_VP, _U8P, C.c_size_t, _FP, _U8P, C.POINTER(C.c_size_t)]),
     "ems_scratch_bytes": (C.c_int, [_VP, C.POINTER(C.c_size_t)]),
+    "ems_image_summary": (C.c_int, [_VP, _U8P, C.c_size_t, _VP]),
     "ems_colorize": (C.c_int, [_VP, _U8P, C.c_size_t, _VP, _VP]),
     "ems_stage_ms": (C.c_int, [_VP, C.c_int, C.POINTER(C.c_float)]),
     "ems_launch_count": (C.c_int, [_VP, C.POINTER(C.c_uint64)]),
@@ -282,6 +283,15 @@ class Engine:
         self._check(self.lib.ems_process_host_i24(self.h, _ptr(pcm_i24), S, _ptr(grid_out),
                                                   _ptr(index_out), C.byref(n)))
         return grid_out, index_out
+
+    def image_summary(self, index, out=None):
+        """index: CUDA u8 [channels][F][R] -> CUDA int64 [channels][2]: (sum of bytes, position-weighted sum)."""
+        import torch
+        assert index.is_cuda and index.dtype == torch.uint8 and index.is_contiguous() and index.shape[0] == self.params.channels
+        if out is None:
+            out = torch.empty((self.params.channels, 2), dtype=torch.int64, device=index.device)
+        self._check(self.lib.ems_image_summary(self.h, _ptr(index), index.shape[1], _ptr(out)))
+        return out
 
     def scratch_bytes(self) -> int:
         n = C.c_size_t()

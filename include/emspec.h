@@ -165,6 +165,13 @@ ems_status ems_process_host_i24(ems_handle* h, const uint8_t* pcm_host, size_t n
  * the smoothing / AGC scans) — ems_process_host* keep it independent of the stream length. */
 ems_status ems_scratch_bytes(const ems_handle* h, size_t* bytes);
 
+/* Per-clip summary of a colour-index image for batch jobs (clips are independent, the
+ * only exchange is a final gather of per-clip descriptors).  index_dev: u8 [channels][n_frames][R];
+ * summary_dev: uint64 [channels][2] (device): [0] = sum of the bytes, [1] = sum of byte * (1 + position
+ * mod 65521) in wrapping 64-bit arithmetic (order-dependent).  Integer work: exact, any alignment. */
+ems_status ems_image_summary(ems_handle* h, const uint8_t* index_dev, size_t n_frames,
+                             uint64_t* summary_dev);
+
 /* Colour map ("Color Map", /root/reference/README.md:15,45): applies a
  * 256-entry RGBA table (HOST pointer, packed 0xAABBGGRR like a byte-wise R,G,B,A store) to
  * n_cells colour indices on the device; rgba_dev receives n_cells 32-bit pixels in the same

@@ -672,3 +672,18 @@ def test_process_host_scratch_is_bounded(emspec):
             assert torch.equal(i_host, i_dev.cpu())
         eng.close()
     assert sizes[0] == sizes[1], sizes
+
+
+def test_image_summary_is_exact(emspec):
+    """Batch bookkeeping: per-clip (byte sum, position-weighted sum) of the u8 image —
+    integer work, bit-exact against NumPy for channel bases at any alignment, short and long images."""
+    rng = np.random.default_rng(9)
+    for C_, F_, R_ in ((3, 7, 257), (2, 1000, 2049), (5, 1, 129), (1, 40000, 2049)):
+        eng = emspec.Engine(n_fft=2 * (R_ - 1), hop=64, channels=C_, flags=emspec.FLAG_REASSIGN | emspec.FLAG_DETERMINISTIC | emspec.FLAG_SYNC)
+        img = rng.integers(0, 256, (C_, F_, R_), dtype=np.uint8)
+        got = eng.image_summary(torch.from_numpy(img).cuda()).cpu().numpy().astype(np.uint64)
+        flat = img.reshape(C_, -1).astype(np.uint64)
+        w = (np.arange(flat.shape[1], dtype=np.uint64) % np.uint64(65521)) + np.uint64(1)
+        assert (got[:, 0] == flat.sum(1)).all()
+        assert (got[:, 1] == (flat * w[None, :]).sum(1)).all()
+        eng.close()
