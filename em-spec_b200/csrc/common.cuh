@@ -38,6 +38,25 @@ enum DepositMode : int {
     kDepositF32  = 2    // red.global.add.f32 fast mode
 };
 
+// In-kernel post-pass ("fused" mode of the deposit kernels, stft_r16.cuh): the accumulator is one ring
+// of `vring` columns shared by all channels (virtual column = ch * F + col), small enough to stay in
+// L2; a CTA that completes the last tile a column block was waiting for shapes that block straight
+// from L2 into the colour-index image and clears it.  Nothing the size of the stream exists besides
+// the outputs.
+struct FusedPost {
+    int*           ready;     // [n_tiles] finished tiles among the 2 nb + 1 a block waits for (the finisher resets it)
+    int*           done;      // [n_tiles] = epoch once the block has been shaped and cleared
+    uint8_t*       index;     // [channels][F][rows] or null
+    float*         grid;      // [channels][F][rows] or null
+    const float*   weight;    // [rows]
+    float          db_floor, inv_range, gate_db;
+    int            epoch;     // this launch's stamp for done[]
+    int            nb;        // tiles on each side whose deposits can reach a block: ceil(R / tile_T)
+    int            vring;     // columns of the ring (a power of two); 0: fused mode off
+    int            NB;        // flag_blocks(rows)
+    int            debug;     // EMS_FUSED_DEBUG (timing experiments only): 1 = skip the shaping, 2 = skip the ring wait
+};
+
 // Arguments of the fused frame-gather + 3-window STFT + reassignment kernels.
 struct StftArgs {
     const float*  pcm;        // planar [channels][S]
@@ -68,6 +87,7 @@ struct StftArgs {
                               //      streaming, and the O(chunk) host path); 0: linear, F columns per channel
     int           stream_M;   // streaming: pushes per ring lap = ceil(n_fft / hop)
     const long long* sstate;  // streaming: device counter of completed pushes (frame range decoded on device)
+    FusedPost     fp;         // in-kernel post-pass (fp.vring > 0)
 };
 
 // Streaming launches sit in a CUDA graph, so the frame they analyse is derived on the device

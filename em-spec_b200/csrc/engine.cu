@@ -72,6 +72,13 @@ struct ems_handle {
         long long pushes = 0;            // host mirror of the device counter
         size_t acc_bytes = 0;
     } st;
+    struct FusedState {                 // in-kernel post-pass of ems_process_grid (common.cuh FusedPost)
+        ems::DevBuf ready, done;        // per-tile arrival counters (self-resetting) and epoch stamps
+        int epoch = 0;
+        bool counters_clean = false;    // ready[] is all zero (a failed launch leaves it unknown)
+        int mode = 0;                   // EMS_FUSED_POST=1 switches it on (experiment: measured 5x slower)
+        int ring = 8192;                // EMS_FUSED_RING: columns of the accumulator ring
+    } fz;
     bool force_generic = false;         // EMS_FORCE_GENERIC=1: bypass the tuned kernels (A/B tests)
     int kernel_variant = 0;             // EMS_KERNEL_VARIANT: experimental kernel selection (A/B runs); 0 = default
     char err[256] = "";
@@ -226,6 +233,34 @@ static ems_status launch_r16(ems_handle* h, const StftArgs& a) {
     long long grid = h->sm_count;
     if (grid > n_tiles) grid = n_tiles;
     if (grid < 1) return EMS_OK;
+    if (a.fp.vring > 0) {
+        // in-kernel post-pass: blocks of tile_T columns, shaped by the CTA that completes the last of the
+        // 2 nb + 1 tiles whose deposits can reach them.  CTAs may wait for one another (ring space), so the
+        // launch is cooperative: every CTA is resident or the launch fails.
+        StftArgs af = a;
+        const long long Rc = (C::N / 2 + a.hop - 1) / a.hop;
+        af.fp.nb = (int)((Rc + tile_T - 1) / tile_T);
+        if ((long long)af.fp.vring < 4 * ((2LL * af.fp.nb + 1) * tile_T + 2 * Rc))
+            return fail(h, EMS_ERR_STATE, "accumulator ring of %d columns is too short for hop %d", af.fp.vring, a.hop);
+        const size_t need = (size_t)n_tiles * sizeof(int);
+        if (h->fz.ready.bytes < need || h->fz.done.bytes < need) h->fz.counters_clean = false;
+        ems_status s;
+        if ((s = ensure(h, h->fz.ready, need)) != EMS_OK || (s = ensure(h, h->fz.done, need)) != EMS_OK) return s;
+        if (!h->fz.counters_clean) {
+            EMS_CUDA(h, cudaMemsetAsync(h->fz.ready.p, 0, h->fz.ready.bytes, h->stream));
+            EMS_CUDA(h, cudaMemsetAsync(h->fz.done.p, 0, h->fz.done.bytes, h->stream));
+            h->fz.epoch = 0;
+        }
+        h->fz.counters_clean = false;                  // until the caller has seen the launch succeed
+        af.fp.ready = (int*)h->fz.ready.p;
+        af.fp.done = (int*)h->fz.done.p;
+        af.fp.epoch = ++h->fz.epoch;
+        int tt = tile_T;
+        void* args[] = {(void*)&af, (void*)&tt};
+        EMS_CUDA(h, cudaLaunchCooperativeKernel((const void*)kern, dim3((unsigned)grid), dim3(r16::kThreads), args, smem, h->stream));
+        ++h->launches;
+        return EMS_OK;
+    }
     kern<<<(unsigned)grid, r16::kThreads, smem, h->stream>>>(a, tile_T);
     ++h->launches;
     EMS_CUDA(h, cudaGetLastError());
@@ -663,6 +698,8 @@ ems_status ems_create(const ems_params* params, ems_handle** out) {
     h->prm = *params;
     { const char* fg = getenv("EMS_FORCE_GENERIC"); h->force_generic = fg && fg[0] == '1'; }
     { const char* kv = getenv("EMS_KERNEL_VARIANT"); h->kernel_variant = kv ? atoi(kv) : 0; }
+    { const char* fv = getenv("EMS_FUSED_POST"); if (fv) h->fz.mode = atoi(fv); }
+    { const char* fr = getenv("EMS_FUSED_RING"); if (fr && atoi(fr) >= 256) { int r = 256; while (r < atoi(fr)) r *= 2; h->fz.ring = r; } }
     auto bail = [&](ems_status s) { ems_destroy(h); return s; };
     if (cudaGetDevice(&h->device) != cudaSuccess) return bail(EMS_ERR_CUDA);
     cudaDeviceProp prop{};
@@ -704,7 +741,7 @@ ems_status ems_destroy(ems_handle* h) {
     if (!h) return EMS_ERR_INVALID_ARG;
     if (h->stream) cudaStreamSynchronize(h->stream);
     for (DevBuf* b : {&h->acc, &h->flags, &h->carry, &h->ema_local, &h->ema_carry, &h->lut, &h->colscale, &h->agc_level,
-                      &h->big_scratch, &h->hp.pcm[0], &h->hp.pcm[1], &h->hp.raw[0], &h->hp.raw[1], &h->hp.idx[0], &h->hp.idx[1],
+                      &h->big_scratch, &h->fz.ready, &h->fz.done, &h->hp.pcm[0], &h->hp.pcm[1], &h->hp.raw[0], &h->hp.raw[1], &h->hp.idx[0], &h->hp.idx[1],
                       &h->hp.grid[0], &h->hp.grid[1]})
         if (b->p) cudaFree(b->p);
     if (h->hp.events) {
@@ -837,6 +874,39 @@ ems_status ems_process_grid(ems_handle* h, const float* pcm, size_t S, float* gr
     if (!pcm || (!grid && !index)) return fail(h, EMS_ERR_INVALID_ARG, "null buffer");
     const int C = h->prm.channels, R = rows_of(h->prm);
     const bool det = h->prm.flags & EMS_FLAG_DETERMINISTIC;
+    // Without smoothing and AGC a column depends on nothing but its own cells: the deposit kernel shapes
+    // finished column blocks itself, out of an accumulator ring that stays in L2 (tiled kernels only).
+    const bool fused = h->fz.mode && h->prm.smoothing == 0.f && h->prm.agc_strength == 0.f && !h->force_generic &&
+                       h->kernel_variant == 0 && h->prm.n_fft <= 4096 && flag_blocks(R) <= 64 &&
+                       (size_t)C * (size_t)F > (size_t)0;
+    if (fused) {
+        const size_t ring = (size_t)h->fz.ring;
+        ems_status s = prepare_acc(h, ring * R, ring, R);
+        if (s != EMS_OK) return s;
+        StftArgs a = make_args(h, pcm, S, F);
+        a.acc = h->acc.p; a.flags = (unsigned char*)h->flags.p; a.mode = det ? kDepositU64 : kDepositF32;
+        a.fp.vring = (int)ring; a.fp.NB = flag_blocks(R);
+        a.fp.index = index; a.fp.grid = grid; a.fp.weight = h->weight;
+        a.fp.db_floor = (float)(kTopDb - (double)h->prm.db_range);
+        a.fp.inv_range = 255.0f / h->prm.db_range;
+        a.fp.gate_db = h->prm.noise_gate_db;
+        { const char* dv = getenv("EMS_FUSED_DEBUG"); a.fp.debug = dv ? atoi(dv) : 0; }
+        stage_begin(h, EMS_STAGE_POINTS);
+        s = launch_stft(h, a);
+        if (s == EMS_ERR_STATE) {                      // ring too short for this geometry: the two-kernel path below
+            stage_abort();
+            h->acc_clean = true;                       // nothing was launched
+        } else {
+            if (s != EMS_OK) { stage_abort(); return s; }
+            stage_end(h, EMS_STAGE_POINTS);
+            // the post-pass ran inside the kernel: report it as a zero-length stage
+            stage_begin(h, EMS_STAGE_POST);
+            stage_end(h, EMS_STAGE_POST);
+            h->acc_clean = true;
+            h->fz.counters_clean = true;
+            return finish(h);
+        }
+    }
     const size_t cells = (size_t)C * F * R;
     ems_status s = prepare_acc(h, cells, (size_t)C * F, R);
     if (s != EMS_OK) return s;

@@ -41,7 +41,7 @@ namespace ems {
 namespace r16 {
 
 constexpr int kMaxSmem = 232448;       // 227 KB
-constexpr int kSyncBytes = 128;        // 2 mbarriers, 2 release counters, kWorkers refill flags
+constexpr int kSyncBytes = 192;        // 2 mbarriers, 2 release counters, kWorkers refill flags; fused mode: 4 finish counters, kWorkers go flags
 constexpr int kT2 = 16 * 16;           // W_256^{p2 i} as [p2][i]: a butterfly's 16 twiddles are contiguous
 constexpr int kScratch = 20;           // 2 X_th' of bin N/2 (and padding: the slot size stays 8 mod 16)
 constexpr int kThreads = 384;
@@ -86,7 +86,7 @@ struct Cfg {
     static_assert(kFixedBytes % 16 == 0, "tile buffers (TMA / cp.async destinations) start on a 16-byte boundary");
     static_assert(kFixedBytes + 2 * kTileFloats * 4 + kSyncBytes <= kMaxSmem, "shared memory");
     static_assert(kG == 1 || kSlot % 16 == 8, "frames of one half-warp sit in different banks");
-    static_assert(16 + 8 + 4 * kWorkers <= kSyncBytes, "mbarriers, release counters and refill flags fit their block");
+    static_assert(16 + 8 + 4 * kWorkers + 16 + 4 * kWorkers <= kSyncBytes, "mbarriers, release counters, refill flags, finish counters and go flags fit their block");
 };
 
 template <int... Is, class Fn>
@@ -239,11 +239,21 @@ struct DepositCtx {      // passed by value (registers): taking the address of S
     long long F;
     int ring, rows, warp_mode;
     float warp_a, warp_c, inv_half;
+    int vring, NB;       // fused mode: one ring of vring virtual columns (ch * F + col), flags [vring][NB]
 };
 template <int MODE>
 __device__ __noinline__ void deposit_point(const DepositCtx d, int ch, long long col, int k, float dk,
                                            float wh, float e) {
     const int row = out_row(d.warp_mode, d.warp_a, d.warp_c, d.inv_half, k, dk, wh);
+    if (d.vring) {
+        const long long slot = ((long long)ch * d.F + col) & (long long)(d.vring - 1);
+        if (MODE == kDepositU64)
+            red_add_u64(reinterpret_cast<unsigned long long*>(d.acc) + slot * d.rows + row, fix_energy(e));
+        else
+            red_add_f32(reinterpret_cast<float*>(d.acc) + slot * d.rows + row, e);
+        flag_set(d.flags + slot * d.NB + (row >> kFlagShift));
+        return;
+    }
     const long long ncols = d.ring ? d.ring : d.F, slot = d.ring ? (col & (d.ring - 1)) : col;
     const long long o = ((long long)ch * ncols + slot) * d.rows + row;
     if (MODE == kDepositU64)
@@ -308,7 +318,7 @@ __device__ __forceinline__ void bin_tail(const StftArgs& a, const FrameCtx& fc, 
     if (MODE == kStorePoints) {
         if (owner) { __stwb(fc.pd + off, dtc); __stwb(fc.pk + off, dk); __stwb(fc.pe + off, ok ? e : 0.f); }
     } else if (ok && owner) {
-        const DepositCtx d{a.acc, a.flags, a.F, a.ring, a.rows, a.warp_mode, a.warp_a, a.warp_c, a.inv_half};
+        const DepositCtx d{a.acc, a.flags, a.F, a.ring, a.rows, a.warp_mode, a.warp_a, a.warp_c, a.inv_half, a.fp.vring, a.fp.NB};
         deposit_point<MODE>(d, fc.ch, fc.f + (long long)rc, k, dk, wh, e);
     }
 }
@@ -550,6 +560,99 @@ __device__ __forceinline__ void epilogue(const StftArgs& a, int ch, long long f,
         bin_emit<N, MODE>(a, fc, owner && g.p == 0, N / 2, (float)(N / 2), Xs[N / 2 + 1], Xs[N / 2], Xs[N / 2 + 2], Sc[0]);
 }
 
+// ---------------------------------------------------------------- in-kernel post-pass (fused mode)
+__device__ __forceinline__ int ld_acquire(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint8_t colour_index_of(float E, float db_floor, float inv_range, float gate_db) {
+    if (!(E > 0.f)) return 0;                                     // same arithmetic as scatter_post.cuh::colour_index
+    const float db = 10.0f * log10f(E);
+    if (db < gate_db) return 0;
+    const float v = rintf((db - db_floor) * inv_range);
+    return (uint8_t)fminf(fmaxf(v, 0.f), 255.f);
+}
+
+// Shapes columns [c0, c1) of channel ch from the ring into index / grid and clears them.  Called by
+// all `nth` threads of one worker (whole warps); a warp takes a column at a time.  Cells are read
+// past L1 (other SMs deposited them with reds at L2).  Clean 64-row blocks are neither read nor
+// cleared; their outputs are zeros.  Lanes own four consecutive rows, shifted so that the four
+// index bytes of a lane are one aligned 32-bit store.
+template <int MODE>
+__device__ __noinline__ void fused_post_block(void* acc, unsigned char* flags, const FusedPost fp, long long F,
+                                              int rows, int ch, long long c0, long long c1, int t, int nth) {
+    const int lane = t & 31, wp = t >> 5, nwp = nth >> 5;
+    if (fp.debug & 4) {          // timing experiment: zero-fill only, the smallest possible loop
+        for (long long c = c0 + wp; c < c1; c += nwp) {
+            uint8_t* ix = fp.index + ((long long)ch * F + c) * rows;
+            for (int r = lane; r < rows; r += 32) ix[r] = 0;
+        }
+        return;
+    }
+    for (long long c = c0 + wp; c < c1; c += nwp) {
+        const long long slot = ((long long)ch * F + c) & (long long)(fp.vring - 1);
+        unsigned char* fl = flags + slot * fp.NB;
+        // dirty mask of the column's (<= 64) row blocks
+        const unsigned m0 = __ballot_sync(0xffffffffu, lane < fp.NB && __ldcg(fl + lane) != 0);
+        const unsigned m1 = __ballot_sync(0xffffffffu, lane + 32 < fp.NB && __ldcg(fl + lane + 32) != 0);
+        const unsigned long long dirty = (unsigned long long)m0 | ((unsigned long long)m1 << 32);
+        const long long orow = ((long long)ch * F + c) * rows;
+        uint8_t* ix = fp.index ? fp.index + orow : nullptr;
+        float* gr = fp.grid ? fp.grid + orow : nullptr;
+        const int a0 = ix ? (int)((4 - ((unsigned long long)ix & 3ull)) & 3ull) : 0;      // rows before the first aligned word
+        for (int r0 = a0 + 4 * lane - 128; r0 < rows; r0 += 128) {
+            // first iteration: the lanes whose word would start below row 0 take the a0 head rows one byte each
+            float G[4];
+            bool in[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                int r = r0 + q;
+                if (r0 < 0) r = (r0 + 128 == a0 + 4 * lane && q == 0 && lane < a0) ? lane : -1;   // head rows 0 .. a0-1
+                in[q] = r >= 0 && r < rows;
+                G[q] = 0.f;
+                if (in[q] && ((dirty >> (r >> kFlagShift)) & 1ull)) {
+                    if (MODE == kDepositU64) {
+                        unsigned long long* p = reinterpret_cast<unsigned long long*>(acc) + slot * rows + r;
+                        const unsigned long long v = __ldcg(p);
+                        if (v) { __stcg(p, 0ull); G[q] = __double2float_rn(__ull2double_rn(v) * kFixScaleInv); }
+                    } else {
+                        float* p = reinterpret_cast<float*>(acc) + slot * rows + r;
+                        const float v = __ldcg(p);
+                        if (v != 0.f) { __stcg(p, 0.f); G[q] = v; }
+                    }
+                }
+            }
+            if (r0 < 0) {
+                if (in[0]) {
+                    if (ix) ix[lane] = colour_index_of(G[0] * __ldg(fp.weight + lane), fp.db_floor, fp.inv_range, fp.gate_db);
+                    if (gr) gr[lane] = G[0];
+                }
+                continue;
+            }
+            if (ix) {
+                unsigned word = 0;
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (in[q] && G[q] > 0.f)
+                        word |= (unsigned)colour_index_of(G[q] * __ldg(fp.weight + r0 + q), fp.db_floor, fp.inv_range, fp.gate_db) << (8 * q);
+                if (in[3]) *reinterpret_cast<unsigned*>(ix + r0) = word;
+                else {
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) if (in[q]) ix[r0 + q] = (uint8_t)(word >> (8 * q));
+                }
+            }
+            if (gr) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) if (in[q]) gr[r0 + q] = G[q];
+            }
+        }
+        __syncwarp();
+        if (lane < fp.NB && ((dirty >> lane) & 1ull)) __stcg(fl + lane, (unsigned char)0);
+        if (lane + 32 < fp.NB && ((dirty >> (lane + 32)) & 1ull)) __stcg(fl + lane + 32, (unsigned char)0);
+    }
+}
+
 // ---------------------------------------------------------------- n_fft = 256 .. 4096
 template <int R, int MODE>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -607,6 +710,8 @@ stft_reassign_r16(const StftArgs a_in, const int tile_T) {
     unsigned long long* full = reinterpret_cast<unsigned long long*>(tile0 + 2 * kTileFloats);   // [2]
     unsigned* done = reinterpret_cast<unsigned*>(full + 2);                                     // [2]
     int* refill = reinterpret_cast<int*>(done + 2);                                             // [kWorkers]
+    unsigned* fin = reinterpret_cast<unsigned*>(refill + kWorkers);                             // [4] fused mode: workers done with tile ti & 3
+    int* go = reinterpret_cast<int*>(fin + 4);                                                  // [kWorkers] fused mode: this worker shapes a block
     const unsigned full_sm = (unsigned)__cvta_generic_to_shared(full);
     auto tile_geom = [&](long long tl, int& ch, long long& f0, int& nf) {
         ch = (int)(tl / tiles_per_ch);
@@ -631,10 +736,68 @@ stft_reassign_r16(const StftArgs a_in, const int tile_T) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(full_sm), "r"(kWTh));
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(full_sm + 8), "r"(kWTh));
         done[0] = 0; done[1] = 0;
+        fin[0] = 0; fin[1] = 0; fin[2] = 0; fin[3] = 0;
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
     // (no initial stagger: measured, it makes no difference)
+
+    // ---- fused mode (a.fp.vring > 0, deposit modes): ring space before a tile, completion after it
+    const bool fused = MODE != kStorePoints && a.fp.vring > 0;
+    const long long Rcols = (N / 2 + a.hop - 1) / a.hop;            // a deposit lands within +-Rcols columns of its frame
+    // the ring slots tile tl is about to deposit into were last used Rg columns earlier: wait until the
+    // blocks that owned them have been shaped and cleared (rare: the ring is several rounds of tiles long)
+    auto ring_wait = [&](long long tl, int ch, long long f0, int nf) {
+        if (wl == 0 && !(a.fp.debug & 2)) {
+            const long long lo = max(f0 - Rcols, 0LL), hi = min(f0 + nf - 1 + Rcols, a.F - 1);
+            const long long vlo = (long long)ch * a.F + lo - a.fp.vring, vhi = (long long)ch * a.F + hi - a.fp.vring;
+            if (vhi >= 0) {
+                const long long v0 = max(vlo, 0LL);
+                const long long b0 = (v0 / a.F) * tiles_per_ch + (v0 % a.F) / tile_T;
+                const long long b1 = (vhi / a.F) * tiles_per_ch + (vhi % a.F) / tile_T;
+                for (long long b = b0; b <= b1; ++b)
+                    while (ld_acquire(a.fp.done + b) != a.fp.epoch) __nanosleep(200);
+            }
+        }
+        worker_bar<kWT>(w);
+    };
+    // this worker has deposited its last point of tile tl (tile number ti of this CTA).  The last worker
+    // of the CTA to get here tells the blocks the tile can reach, and shapes those that were waiting
+    // for this tile only.
+    auto tile_done = [&](long long tl, long long ti, int ch) {
+        __threadfence();                              // this thread's reds are performed
+        worker_bar<kWT>(w);
+        if (wl == 0) {
+            const unsigned old = atomicAdd(&fin[ti & 3], 1u);
+            const bool last = old == kWorkers - 1;
+            if (last) fin[ti & 3] = 0;
+            go[w] = last ? 1 : 0;
+        }
+        worker_bar<kWT>(w);
+        if (!go[w]) return;
+        const long long j = tl - (long long)ch * tiles_per_ch;           // tile of its channel
+        const long long jlo = max(j - a.fp.nb, 0LL), jhi = min(j + a.fp.nb, tiles_per_ch - 1);
+        for (long long b = jlo; b <= jhi; ++b) {
+            worker_bar<kWT>(w);                       // go[w] of the previous round has been read
+            if (wl == 0) {
+                const int need = (int)(min(b + a.fp.nb, tiles_per_ch - 1) - max(b - a.fp.nb, 0LL) + 1);
+                int* rp = a.fp.ready + (long long)ch * tiles_per_ch + b;
+                const int got = atomicAdd(rp, 1) + 1;
+                if (got == need) *rp = 0;
+                go[w] = got == need ? 1 : 0;
+            }
+            worker_bar<kWT>(w);
+            if (go[w]) {
+                __threadfence();                      // acquire: the other tiles' reds, fenced before their arrival
+                const long long c0 = a.f_begin + b * tile_T, c1 = min(c0 + tile_T, a.f_end);
+                if (!(a.fp.debug & 1)) fused_post_block<MODE>(a.acc, a.flags, a.fp, a.F, a.rows, ch, c0, c1, wl, kWTh);
+                __threadfence();
+                worker_bar<kWT>(w);
+                if (wl == 0)
+                    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(a.fp.done + (long long)ch * tiles_per_ch + b), "r"(a.fp.epoch) : "memory");
+            }
+        }
+    };
 
     // this worker is done reading buffer b (tile number ti of this CTA): called by its thread
     // p == 0 after a worker barrier; tells the worker whether it has to refill the buffer
@@ -698,8 +861,10 @@ stft_reassign_r16(const StftArgs a_in, const int tile_T) {
             worker_bar<kWT>(w);
             if (refill[w]) refill_tile(buf, ti + 2);
             worker_bar<kWT>(w);
+            if (fused) tile_done(tl, ti, ch);
             continue;
         }
+        if (fused) ring_wait(tl, ch, f0, nf);
 
         for (int fi0 = w * kG; fi0 < nf; fi0 += kWorkers * kG) {
             // sub-warp workers: slots past the end of the tile redo its last frame and emit nothing
@@ -750,6 +915,7 @@ stft_reassign_r16(const StftArgs a_in, const int tile_T) {
             epilogue<R, MODE>(a, ch, f, Xs, Sc, g, xa, xb, ta, tb, active);
             }
         }
+        if (fused) tile_done(tl, ti, ch);
     }
 }
 
