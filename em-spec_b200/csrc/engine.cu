@@ -43,7 +43,8 @@ struct ems_handle {
     float*  thw = nullptr;              // [N] th' window
     float2* tw = nullptr;               // [N]
     float*  weight = nullptr;           // [B]
-    ems::DevBuf acc, flags, carry, ema_local, ema_carry, big_scratch, lut, colscale, agc_level;
+    ems::DevBuf acc, flags, carry, ema_local, ema_carry, big_scratch, lut, colscale, agc_level, post_mode;
+    bool post_mode_init = false;
     struct HostPipe {                   // ems_process_host*: two of everything, chunk c uses set c & 1
         ems::DevBuf pcm[2], raw[2], idx[2], grid[2];   // fp32 planar chunk, raw int16/int24 chunk, staging images
         cudaEvent_t ev_in[2]{}, ev_done[2]{}, ev_out[2]{}, ev_start{};
@@ -444,12 +445,37 @@ static ems_status run_post(ems_handle* h, PostArgs p) {
         if (p.grid) EMS_CUDA(h, zero_cols(h, p.grid, (size_t)p.B * sizeof(float), p, p.out_cols, p.out_col0));
         const dim3 g((unsigned)((ncols + 255) / 256), p.channels * p.NB);
         if (agc) {
-            post_sparse_kernel<<<g, 256, 0, h->stream>>>(p, 1);
+            post_sparse_kernel<<<g, 256, 0, h->stream>>>(p, 1, nullptr);
             ++h->launches;
             agc_scan();
+            post_sparse_kernel<<<g, 256, 0, h->stream>>>(p, 0, nullptr);
+            ++h->launches;
+            EMS_CUDA(h, cudaGetLastError());
+            return EMS_OK;
         }
-        post_sparse_kernel<<<g, 256, 0, h->stream>>>(p, 0);
-        ++h->launches;
+        // a mostly empty image is visited block by block; a mostly full one is streamed column by column.
+        // The choice is made on the device from the dirty flags; the kernel not chosen exits at once.
+        ems_status s = ensure(h, h->post_mode, 16);
+        if (s != EMS_OK) return s;
+        if (!h->post_mode_init) {
+            EMS_CUDA(h, cudaMemsetAsync(h->post_mode.p, 0, 16, h->stream));
+            h->post_mode_init = true;
+        }
+        unsigned long long* cnt = (unsigned long long*)h->post_mode.p;
+        int* mode = (int*)(cnt + 1);
+        const long long nflags = ncols * p.channels * p.NB;
+        const unsigned gb = (unsigned)std::min<long long>((nflags / 4 + 255) / 256 + 1, (long long)h->sm_count * 8);
+        post_density_kernel<<<gb, 256, 0, h->stream>>>(p, cnt, mode, 0);
+        post_density_kernel<<<1, 32, 0, h->stream>>>(p, cnt, mode, 1);
+        post_sparse_kernel<<<g, 256, 0, h->stream>>>(p, 0, mode);
+        if (p.B <= 4096) {
+            const unsigned gd = (unsigned)std::min<long long>(ncols * p.channels, (long long)h->sm_count * 16);
+            if (p.acc_is_u64) post_dense_kernel<8><<<gd, 128, 0, h->stream>>>(p, mode);
+            else post_dense_kernel<16><<<gd, 128, 0, h->stream>>>(p, mode);     // 4-byte cells: twice the loads in flight
+        }
+        clear_flags_if_kernel<<<(unsigned)std::min<long long>((nflags + 255) / 256, 4096LL), 256, 0, h->stream>>>(
+            p.flags, p.acc_cols, p.acc_mask, p.col_begin, p.col_end, p.channels * p.NB, mode);
+        h->launches += 5;
         EMS_CUDA(h, cudaGetLastError());
         return EMS_OK;
     }
@@ -741,7 +767,7 @@ ems_status ems_destroy(ems_handle* h) {
     if (!h) return EMS_ERR_INVALID_ARG;
     if (h->stream) cudaStreamSynchronize(h->stream);
     for (DevBuf* b : {&h->acc, &h->flags, &h->carry, &h->ema_local, &h->ema_carry, &h->lut, &h->colscale, &h->agc_level,
-                      &h->big_scratch, &h->fz.ready, &h->fz.done, &h->hp.pcm[0], &h->hp.pcm[1], &h->hp.raw[0], &h->hp.raw[1], &h->hp.idx[0], &h->hp.idx[1],
+                      &h->big_scratch, &h->post_mode, &h->fz.ready, &h->fz.done, &h->hp.pcm[0], &h->hp.pcm[1], &h->hp.raw[0], &h->hp.raw[1], &h->hp.idx[0], &h->hp.idx[1],
                       &h->hp.grid[0], &h->hp.grid[1]})
         if (b->p) cudaFree(b->p);
     if (h->hp.events) {

@@ -193,7 +193,8 @@ post_emit_kernel(const PostArgs a, const float* __restrict__ carry_in, int n_chu
 // and its flag are cleared.  grid: (ceil(ncols/256), channels*NB), 256 threads.
 // measure = 1 (AGC first pass): only the per-column peak of the shaped energy is produced.
 __global__ void __launch_bounds__(256)
-post_sparse_kernel(const PostArgs a, int measure) {
+post_sparse_kernel(const PostArgs a, int measure, const int* __restrict__ mode) {
+    if (mode && mode[0] == 1) return;                       // the dense kernel takes this range
     const int lane = threadIdx.x & 31;
     const int r = blockIdx.y;                               // ch * NB + blk
     const int ch = r / a.NB, blk = r - ch * a.NB;
@@ -245,6 +246,82 @@ post_sparse_kernel(const PostArgs a, int measure) {
             }
             if (lane == 0) a.flags[flag_at(a, ch, blk, cw + js[b])] = 0;
         }
+    }
+}
+
+// How dirty is the image?  Counts the set flags of columns [col_begin, col_end) and leaves
+// mode[0] = 1 when more than half of the 64-row blocks hold energy: the post-pass then streams whole
+// columns (post_dense_kernel) instead of visiting flagged blocks one by one (post_sparse_kernel).
+// Both kernels are launched; the one that is not selected exits at once.
+__global__ void __launch_bounds__(256)
+post_density_kernel(const PostArgs a, unsigned long long* __restrict__ count, int* __restrict__ mode, int pass) {
+    const long long n = a.col_end - a.col_begin, rows = (long long)a.channels * a.NB;
+    if (pass == 1) {                 // single thread: decide, reset the counter for the next call
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            // (every fourth flag was counted; the dense kernel stages a column of at most 4096 rows)
+            mode[0] = (a.B <= 4096 && 8 * count[0] > (unsigned long long)(n * rows)) ? 1 : 0;
+            count[0] = 0;
+        }
+        return;
+    }
+    unsigned c = 0;
+    for (long long i = 4 * ((long long)blockIdx.x * blockDim.x + threadIdx.x); i < n * rows; i += 4 * (long long)gridDim.x * blockDim.x) {
+        const long long r = i / n;
+        c += a.flags[r * a.acc_cols + ((a.col_begin + (i - r * n)) & a.acc_mask)] != 0;
+    }
+#pragma unroll
+    for (int d = 16; d; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(count, (unsigned long long)c);
+}
+
+// Dense post-pass (no smoothing, no AGC): one block per column, every cell of the column is read,
+// shaped and cleared, clean or not — 16 KB of contiguous accumulator per column, so the whole column
+// is in flight at once.  A thread owns four consecutive rows, shifted so that its four index bytes are
+// one aligned 32-bit store.  The caller clears the flags of the range afterwards.
+template <int kIter>                                      // kIter x 128 cells in flight per block: lanes read consecutive cells
+__global__ void __launch_bounds__(128)
+post_dense_kernel(const PostArgs a, const int* __restrict__ mode) {
+    if (mode[0] != 1) return;
+    __shared__ __align__(16) uint8_t col[4352];              // the column's index bytes (rows <= 4096 in this mode), 4 bytes of slack each end
+    const long long ncols = a.col_end - a.col_begin;
+    const int t = threadIdx.x;
+    for (long long job = blockIdx.x; job < ncols * a.channels; job += gridDim.x) {
+    const int ch = (int)(job / ncols);
+    const long long c = a.col_begin + (job - (long long)ch * ncols);
+    __syncthreads();                                          // the previous column's bytes have been written out
+    const long long arow = acc_row(a, ch, c), orow = out_row_of(a, ch, c);
+    uint8_t* ix = a.index ? a.index + orow : nullptr;
+    float* gr = a.grid ? a.grid + orow : nullptr;
+    for (int base = 0; base < a.B; base += 128 * kIter) {
+        float G[kIter];
+#pragma unroll
+        for (int i = 0; i < kIter; ++i) {
+            const int r = base + 128 * i + t;
+            G[i] = r < a.B ? acc_load(a.acc, a.acc_is_u64, arow + r) : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < kIter; ++i) {
+            const int r = base + 128 * i + t;
+            if (r < a.B) {
+                acc_zero(a.acc, a.acc_is_u64, arow + r);
+                if (gr) gr[r] = G[i];
+                if (ix) col[4 + r] = G[i] > 0.f ? colour_index(G[i] * a.weight[r], a) : (uint8_t)0;
+            }
+        }
+    }
+    if (!ix) continue;
+    __syncthreads();
+    // aligned 32-bit words of the output row from the staged bytes; the ragged ends byte by byte
+    const int a0 = (int)((4 - ((unsigned long long)ix & 3ull)) & 3ull);
+    const int nw = (a.B - a0) >> 2;
+    for (int w = t; w < nw; w += 128) {
+        const int r = a0 + 4 * w;
+        const unsigned v = (unsigned)col[4 + r] | ((unsigned)col[5 + r] << 8) | ((unsigned)col[6 + r] << 16) | ((unsigned)col[7 + r] << 24);
+        *reinterpret_cast<unsigned*>(ix + r) = v;
+    }
+    if (t < a0) ix[t] = col[4 + t];
+    const int tail0 = a0 + 4 * nw;
+    if (tail0 + t < a.B && t < 4) ix[tail0 + t] = col[4 + tail0 + t];
     }
 }
 
@@ -398,6 +475,18 @@ image_summary_kernel(const uint8_t* __restrict__ img, size_t n, unsigned long lo
 // `ncols` columns per row (F, or the ring size), column c sits at slot c & mask.
 __global__ void clear_flags_kernel(unsigned char* __restrict__ flags, long long ncols, long long mask,
                                    long long c0, long long c1, int rows) {
+    const long long n = c1 - c0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n * rows;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / n;
+        flags[r * ncols + ((c0 + (i - r * n)) & mask)] = 0;
+    }
+}
+
+// The same, only when the dense post-pass ran (it does not clear flags block by block).
+__global__ void clear_flags_if_kernel(unsigned char* __restrict__ flags, long long ncols, long long mask,
+                                      long long c0, long long c1, int rows, const int* __restrict__ mode) {
+    if (mode[0] != 1) return;
     const long long n = c1 - c0;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n * rows;
          i += (long long)gridDim.x * blockDim.x) {

@@ -37,6 +37,10 @@
 #include <type_traits>
 #include <utility>
 
+#ifndef EMS_DEPOSIT_AGG
+#define EMS_DEPOSIT_AGG 0       // experiment: warp-aggregated deposits (match.any + segmented shuffle sum)
+#endif
+
 namespace ems {
 namespace r16 {
 
@@ -317,9 +321,48 @@ __device__ __forceinline__ void bin_tail(const StftArgs& a, const FrameCtx& fc, 
     }
     if (MODE == kStorePoints) {
         if (owner) { __stwb(fc.pd + off, dtc); __stwb(fc.pk + off, dk); __stwb(fc.pe + off, ok ? e : 0.f); }
-    } else if (ok && owner) {
-        const DepositCtx d{a.acc, a.flags, a.F, a.ring, a.rows, a.warp_mode, a.warp_a, a.warp_c, a.inv_half, a.fp.vring, a.fp.NB};
-        deposit_point<MODE>(d, fc.ch, fc.f + (long long)rc, k, dk, wh, e);
+    } else {
+#if EMS_DEPOSIT_AGG
+        // Experiment: warp-level pre-aggregation.  Lanes hold adjacent bins of one frame, so
+        // the bins of a main lobe land in the same cell: lanes with equal (column, row) that sit next to
+        // each other sum their (fixed-point) energies with a segmented shuffle reduction and the head of
+        // each run issues one reduction.  Integer sums: the grid stays bit-exact.  All 32 lanes are here.
+        if (a.warp_mode == 0 && !a.fp.vring) {
+            const bool mine = ok && owner;
+            const int row = k + (int)rintf(dk);
+            const unsigned key = mine ? (((unsigned)((int)rc + 32768) << 16) | (unsigned)row) : (0xffffff00u | (threadIdx.x & 31u));
+            const unsigned peers = __match_any_sync(0xffffffffu, key);
+            const unsigned lane = threadIdx.x & 31u;
+            const int n = __ffs(~(peers >> lane)) - 1;                        // lanes of my run from me upwards
+            const bool head = lane == 0 || !((peers >> (lane - 1)) & 1u);
+            const long long col = fc.f + (long long)rc;
+            const long long ncols = a.ring ? a.ring : a.F, slot = a.ring ? (col & (a.ring - 1)) : col;
+            const long long o = ((long long)fc.ch * ncols + slot) * a.rows + row;
+            if (MODE == kDepositU64) {
+                unsigned long long v = mine ? fix_energy(e) : 0ull;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const unsigned long long t = __shfl_down_sync(0xffffffffu, v, d);
+                    if (d < n) v += t;
+                }
+                if (mine && head) red_add_u64(reinterpret_cast<unsigned long long*>(a.acc) + o, v);
+            } else {
+                float v = mine ? e : 0.f;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const float t = __shfl_down_sync(0xffffffffu, v, d);
+                    if (d < n) v += t;
+                }
+                if (mine && head) red_add_f32(reinterpret_cast<float*>(a.acc) + o, v);
+            }
+            if (mine && head && a.flags) flag_set(a.flags + flag_index(fc.ch, ncols, a.rows, slot, row));
+            return;
+        }
+#endif
+        if (ok && owner) {
+            const DepositCtx d{a.acc, a.flags, a.F, a.ring, a.rows, a.warp_mode, a.warp_a, a.warp_c, a.inv_half, a.fp.vring, a.fp.NB};
+            deposit_point<MODE>(d, fc.ch, fc.f + (long long)rc, k, dk, wh, e);
+        }
     }
 }
 // One bin start to end.  A whole warp under the gate leaves after the stencil.  Must be reached by

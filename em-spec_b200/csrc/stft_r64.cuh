@@ -30,6 +30,15 @@
 #ifndef EMS_R64_LOOP
 #define EMS_R64_LOOP 0          // one copy of the radix-64 butterfly code, looped over the two passes
 #endif
+#ifndef EMS_R64_WORKERS
+#define EMS_R64_WORKERS 4       // frames in flight per CTA (64 threads each): 4 at <= 255 registers, 5 at <= 204
+#endif
+#ifndef EMS_R64_PARK
+#define EMS_R64_PARK 0          // (with EMS_R64_TMEM) 2 X_th' of the 32 bins waits in tensor memory between untangle and epilogue
+#endif
+#ifndef EMS_R64_TMEM
+#define EMS_R64_TMEM 0          // th' of a thread's 64 samples lives in tensor memory (tcgen05.ld) instead of a shared-memory table
+#endif
 
 namespace ems {
 namespace r64 {
@@ -37,13 +46,13 @@ namespace r64 {
 using namespace r16;
 
 constexpr int kN = 4096;
-constexpr int kWorkers = 4;
+constexpr int kWorkers = EMS_R64_WORKERS;
 constexpr int kWT = 64;                      // threads per worker = per frame
 constexpr int kThreads64 = kWorkers * kWT;
 constexpr int kRow = 65;                     // Z[n2][k1] at n2 * 65 + k1: both exchanges conflict-free
 constexpr int kZ = 64 * kRow;
 constexpr int kSlot = 2 + kZ + 6;            // 2 X[-1] (at Zb[-2]), Z, scratch: 2 X[2049], 2 X_th'[2048]
-constexpr int kThwBytes = kN * 4;
+constexpr int kThwBytes = EMS_R64_TMEM ? 0 : kN * 4;
 constexpr int kFixedBytes = kThwBytes + kWorkers * kSlot * 8;
 constexpr int kTileFloats = ((kMaxSmem - kFixedBytes - kSyncBytes) / 8) & ~3;
 constexpr int kMaxTile = 12 * kWorkers;
@@ -106,12 +115,41 @@ __device__ __forceinline__ void dft64(float2 (&v)[64]) {
     dft16_at<0>(v); dft16_at<16>(v); dft16_at<32>(v); dft16_at<48>(v);
 }
 
+// ---- tensor memory as per-thread storage: a warp owns the 32 lanes of its quarter (warp id % 4) and a
+// column range; tcgen05.st / tcgen05.ld 32x32b move 16 values per thread to / from the thread's own lane.
+// No shared-memory wavefronts (tools/microbench/tmem_regfile.cu).
+#define EMS_TMEM_LD16(r, addr)                                                                               \
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 "                                                   \
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"           \
+                 : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7]),       \
+                   "=f"(r[8]), "=f"(r[9]), "=f"(r[10]), "=f"(r[11]), "=f"(r[12]), "=f"(r[13]), "=f"(r[14]), "=f"(r[15]) \
+                 : "r"(addr))
+#define EMS_TMEM_LD8(r, addr)                                                                                \
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"            \
+                 : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7]) : "r"(addr))
+#define EMS_TMEM_ST8(r, addr)                                                                                \
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%8], {%0, %1, %2, %3, %4, %5, %6, %7};"            \
+                 :: "f"(r[0]), "f"(r[1]), "f"(r[2]), "f"(r[3]), "f"(r[4]), "f"(r[5]), "f"(r[6]), "f"(r[7]), "r"(addr) : "memory")
+#define EMS_TMEM_ST16(r, addr)                                                                               \
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%16], "                                            \
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15};"                  \
+                 :: "f"(r[0]), "f"(r[1]), "f"(r[2]), "f"(r[3]), "f"(r[4]), "f"(r[5]), "f"(r[6]), "f"(r[7]),            \
+                    "f"(r[8]), "f"(r[9]), "f"(r[10]), "f"(r[11]), "f"(r[12]), "f"(r[13]), "f"(r[14]), "f"(r[15]),      \
+                    "r"(addr) : "memory")
+
 __device__ __forceinline__ float2 shfl2(float2 a, int src) {
     return make_float2(__shfl_sync(0xffffffffu, a.x, src), __shfl_sync(0xffffffffu, a.y, src));
 }
 
+// (ptxas sizes the register budget of __launch_bounds__(320) as if the block had 384 threads: 168
+// registers; __maxnreg__ states the real budget of five workers)
 template <int MODE>
-__global__ void __launch_bounds__(kThreads64, 1)
+__global__ void
+#if EMS_R64_WORKERS == 5
+__maxnreg__(200)
+#else
+__launch_bounds__(kThreads64, 1)
+#endif
 stft_reassign_r64(const StftArgs a_in, const int tile_T) {
     constexpr int N = kN, B = N / 2 + 1;
     StftArgs a = a_in;
@@ -135,10 +173,33 @@ stft_reassign_r64(const StftArgs a_in, const int tile_T) {
     float2* Zb = wbuf + w * kSlot + 2;
     float2* Sc = Zb + kZ;                      // [0] 2 X[2049], [1] 2 X_th'[2048]
 
+#if EMS_R64_TMEM
+    // th'[tl + 64 n1], n1 = 0..63, into 64 columns of this thread's TMEM lane
+    unsigned* tmem_slot = reinterpret_cast<unsigned*>(tile0 + 2 * kTileFloats) + 40;      // spare word of the sync block
+    if (tid < 32) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"((unsigned)__cvta_generic_to_shared(tmem_slot)));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    const unsigned tmem_base = *tmem_slot;
+    const unsigned tmem_thw = tmem_base + ((unsigned)(32 * ((tid >> 5) & 3)) << 16) + 128u * (unsigned)(tid >> 7);
+    const unsigned tmem_T = tmem_thw + 64;       // 2 X_th' of the thread's 32 bins, parked between untangle and epilogue
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        float t16[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) t16[j] = __ldg(&a.thw[tl + 64 * (16 * q + j)]);
+        EMS_TMEM_ST16(t16, tmem_thw + 16 * q);
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+#else
     for (int e = tid; e < N; e += kThreads64) {
         const int t = e & 63, n1 = e >> 6;
         reinterpret_cast<float*>(thwT)[((n1 >> 2) * 64 + t) * 4 + (n1 & 3)] = __ldg(&a.thw[e]);
     }
+#endif
     // W_N^{n2 j}, W_N^{8 n2 j}, j = 1..7: exact, frame-independent, in registers
     float2 wlo[8], whi[8];
 #pragma unroll
@@ -254,6 +315,23 @@ stft_reassign_r64(const StftArgs a_in, const int tile_T) {
             float2 v[64];
             auto load_pass1 = [&]() {
                 // ================= pass 1: radix-64 over n1 of z[n] = x[n] (1 + j th'[n]), n = tl + 64 n1
+#if EMS_R64_TMEM
+                float ta_[16], tb_[16];
+                EMS_TMEM_LD16(ta_, tmem_thw);
+#pragma unroll
+                for (int n1 = 0; n1 < 64; ++n1) v[n1].x = xs[tl + 64 * n1];
+                static_for<4>([&](auto qc) {
+                    constexpr int q = decltype(qc)::value;
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    if constexpr (q + 1 < 4) {            // the next 16 fly while these are consumed
+                        if constexpr (q & 1) EMS_TMEM_LD16(ta_, tmem_thw + 16 * (q + 1));
+                        else EMS_TMEM_LD16(tb_, tmem_thw + 16 * (q + 1));
+                    }
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[16 * q + j].y = v[16 * q + j].x * ((q & 1) ? tb_[j] : ta_[j]);
+                });
+                return;
+#endif
                 // (quads in the order the first DFT-4 stage consumes them: n1 = b, b + 16, b + 32, b + 48)
 #pragma unroll
                 for (int qq = 0; qq < 16; ++qq) {
@@ -316,7 +394,26 @@ stft_reassign_r64(const StftArgs a_in, const int tile_T) {
             // ================= untangle: 2 X[k] = Z[k] + conj Z[N-k], 2 X_th'[k] = (Z[k] - conj Z[N-k]) / j
             // for k = k1 + 64 i, i < 32; Z[N-k] is output 63 - i of residue 64 - k1 (lane pl), or output
             // (64 - i) mod 64 of residue 0 itself
-            float2 X[32], T[32];
+            float2 X[32];
+#if EMS_R64_TMEM && EMS_R64_PARK
+            static_for<8>([&](auto gc) {
+                constexpr int g4 = 4 * decltype(gc)::value;
+                float t8[8];
+                static_for<4>([&](auto jc) {
+                    constexpr int i = g4 + decltype(jc)::value;
+                    const float2 got = shfl2(v[o64(63 - i)], pl);
+                    const float2 zn = cj(self0 ? v[o64((64 - i) & 63)] : got);
+                    const float2 zk = v[o64(i)];
+                    X[i] = zk + zn;
+                    const float2 tt = mulmj(zk - zn);
+                    t8[2 * (i - g4)] = tt.x; t8[2 * (i - g4) + 1] = tt.y;
+                    Zb[i * kRow + k1] = X[i];
+                });
+                EMS_TMEM_ST8(t8, tmem_T + 2 * g4);
+            });
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+#else
+            float2 T[32];
             static_for<32>([&](auto ic) {
                 constexpr int i = decltype(ic)::value;
                 const float2 got = shfl2(v[o64(63 - i)], pl);
@@ -326,6 +423,7 @@ stft_reassign_r64(const StftArgs a_in, const int tile_T) {
                 T[i] = mulmj(zk - zn);
                 Zb[i * kRow + k1] = X[i];
             });
+#endif
             if (k1 == 1) Zb[-2] = cj(X[0]);                     // X[-1] = conj X[1]
             if (k1 == 63) Sc[0] = cj(X[31]);                    // X[2049] = conj X[2047]
             if (self0) {                                        // bin N/2 pairs with itself
@@ -374,13 +472,23 @@ stft_reassign_r64(const StftArgs a_in, const int tile_T) {
 #pragma unroll
                     for (int j = 0; j < 4; ++j) bin_dead<MODE>(fk, true, 64 * (i0 + j));
                 } else {
+#if EMS_R64_TMEM && EMS_R64_PARK
+                    float t8[8];                       // only a group that keeps something fetches its 2 X_th'
+                    EMS_TMEM_LD8(t8, tmem_T + 2 * i0);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    const float2 T[4] = {make_float2(t8[0], t8[1]), make_float2(t8[2], t8[3]),
+                                         make_float2(t8[4], t8[5]), make_float2(t8[6], t8[7])};
+                    constexpr int tb0 = i0;
+#else
+                    constexpr int tb0 = 0;
+#endif
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         if (MODE == kStorePoints || __any_sync(0xffffffffu, lv[j]))
                             bin_tail<N, MODE>(a, fk, true, lv[j], k1 + 64 * (i0 + j), 64 * (i0 + j),
                                               k1f + (float)(64 * (i0 + j)), A4[j],
                                               kPrefetch ? Xm[(i0 + j) * kRow] : cm[j], kPrefetch ? Xp[(i0 + j) * kRow] : cp[j],
-                                              T[i0 + j]);
+                                              T[i0 + j - tb0]);
                         else
                             bin_dead<MODE>(fk, true, 64 * (i0 + j));
                     }
@@ -390,6 +498,11 @@ stft_reassign_r64(const StftArgs a_in, const int tile_T) {
                 bin_emit<N, MODE>(a, fc, self0, N / 2, (float)(N / 2), Zb[32 * kRow], Zb[31 * kRow + 63], Sc[0], Sc[1]);
         }
     }
+#if EMS_R64_TMEM
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    if (tid < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base));
+#endif
 }
 
 }  // namespace r64

@@ -17,7 +17,8 @@ secs = float(sys.argv[3]) if len(sys.argv) > 3 else 600.0
 mode = sys.argv[4] if len(sys.argv) > 4 else "points"
 S = int(secs * 48000)
 pcm = bench.synth_device(S, 0, torch.device("cuda"))
-eng = emspec.Engine(n_fft=n_fft, hop=hop, flags=emspec.FLAG_REASSIGN | emspec.FLAG_DETERMINISTIC | emspec.FLAG_SYNC)
+gate = float(os.environ.get("EMS_NCU_GATE", "-65"))
+eng = emspec.Engine(n_fft=n_fft, hop=hop, noise_gate_db=gate, flags=emspec.FLAG_REASSIGN | emspec.FLAG_DETERMINISTIC | emspec.FLAG_SYNC)
 if mode == "points":
     pts = eng.process_points(pcm)
     print("frames", pts[0].shape[1], "energy sum", float(pts[2].sum()))
