@@ -77,7 +77,7 @@ struct ems_handle {
         ems::DevBuf ready, done;        // per-tile arrival counters (self-resetting) and epoch stamps
         int epoch = 0;
         bool counters_clean = false;    // ready[] is all zero (a failed launch leaves it unknown)
-        int mode = 0;                   // EMS_FUSED_POST=1 switches it on (experiment: measured 5x slower)
+        int mode = 0;                   // env EMS_FUSED_POST=1 switches it on in a -DEMS_FUSED_POST=1 build (experiment: 5x slower)
         int ring = 8192;                // EMS_FUSED_RING: columns of the accumulator ring
     } fz;
     bool force_generic = false;         // EMS_FORCE_GENERIC=1: bypass the tuned kernels (A/B tests)
@@ -902,7 +902,7 @@ ems_status ems_process_grid(ems_handle* h, const float* pcm, size_t S, float* gr
     const bool det = h->prm.flags & EMS_FLAG_DETERMINISTIC;
     // Without smoothing and AGC a column depends on nothing but its own cells: the deposit kernel shapes
     // finished column blocks itself, out of an accumulator ring that stays in L2 (tiled kernels only).
-    const bool fused = h->fz.mode && h->prm.smoothing == 0.f && h->prm.agc_strength == 0.f && !h->force_generic &&
+    const bool fused = EMS_FUSED_POST && h->fz.mode && h->prm.smoothing == 0.f && h->prm.agc_strength == 0.f && !h->force_generic &&
                        h->kernel_variant == 0 && h->prm.n_fft <= 4096 && flag_blocks(R) <= 64 &&
                        (size_t)C * (size_t)F > (size_t)0;
     if (fused) {

@@ -37,6 +37,15 @@
 #include <type_traits>
 #include <utility>
 
+#ifndef EMS_LARGE_R32
+#define EMS_LARGE_R32 0         // experiment, n_fft = 8192: pass 1 as one radix-32 butterfly per thread (one exchange and one
+                                // barrier fewer than 2 x 16): correct, 30.9 against 33.2 M frames/s (32 loads and 64 live
+                                // registers per thread, spills at 128) — off
+#endif
+#ifndef EMS_FUSED_POST
+#define EMS_FUSED_POST 0        // experiment: in-kernel post-pass of the deposit kernels (see fused_post_block): correct, 5 x
+                                // slower, and its mere presence costs the deposit kernels 5 % — compiled out by default
+#endif
 #ifndef EMS_DEPOSIT_AGG
 #define EMS_DEPOSIT_AGG 0       // experiment: warp-aggregated deposits (match.any + segmented shuffle sum)
 #endif
@@ -249,7 +258,7 @@ template <int MODE>
 __device__ __noinline__ void deposit_point(const DepositCtx d, int ch, long long col, int k, float dk,
                                            float wh, float e) {
     const int row = out_row(d.warp_mode, d.warp_a, d.warp_c, d.inv_half, k, dk, wh);
-    if (d.vring) {
+    if (EMS_FUSED_POST && d.vring) {
         const long long slot = ((long long)ch * d.F + col) & (long long)(d.vring - 1);
         if (MODE == kDepositU64)
             red_add_u64(reinterpret_cast<unsigned long long*>(d.acc) + slot * d.rows + row, fix_energy(e));
@@ -786,7 +795,7 @@ stft_reassign_r16(const StftArgs a_in, const int tile_T) {
     // (no initial stagger: measured, it makes no difference)
 
     // ---- fused mode (a.fp.vring > 0, deposit modes): ring space before a tile, completion after it
-    const bool fused = MODE != kStorePoints && a.fp.vring > 0;
+    const bool fused = EMS_FUSED_POST && MODE != kStorePoints && a.fp.vring > 0;
     const long long Rcols = (N / 2 + a.hop - 1) / a.hop;            // a deposit lands within +-Rcols columns of its frame
     // the ring slots tile tl is about to deposit into were last used Rg columns earlier: wait until the
     // blocks that owned them have been shaped and cleared (rare: the ring is several rounds of tiles long)
@@ -1012,6 +1021,13 @@ stft_reassign_r16_large(const StftArgs a_in) {
     for (int e = tid; e < kT2; e += kThreads) { const int q = e / 16, i = e % 16; T2[e] = __ldg(&a.tw[R * q * i]); }
     __syncthreads();
     const Geom g = make_geom<R, kSI, kS16>(p);
+    constexpr bool kR32 = R0 == 2 && EMS_LARGE_R32;
+    // radix-32 pass 1 (n_fft = 8192): W_N^{p 2^l}, l = 0..4, exact and frame-independent, in registers
+    float2 wb[5];
+    if constexpr (kR32) {
+#pragma unroll
+        for (int l = 0; l < 5; ++l) wb[l] = __ldg(&a.tw[(p << l) & (C::N - 1)]);
+    }
 
     const long long per_ch = a.f_end - a.f_begin;
     const long long total = per_ch * a.channels;
@@ -1020,6 +1036,49 @@ stft_reassign_r16_large(const StftArgs a_in) {
         const long long f = a.f_begin + (it - (long long)ch * per_ch);
         const float* xs = a.pcm + (long long)ch * a.S + f * a.hop + a.samp_off;
 
+        if constexpr (kR32) {
+            // ================= pass 1, n_fft = 8192 = 32 x 256: thread b = p takes z[n], n = b + 256 j, j = 0..31,
+            // does the radix-32 butterfly in registers (even / odd j: two DFT-16, W_32 twiddles, radix 2),
+            // multiplies output i by W_N^{b i} and stores it as element b of sub-FFT i: Zb[kSI i + b].
+            // One exchange and one barrier fewer than radix 2 followed by radix 16.
+            constexpr int N = C::N;
+            float xr[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) xr[j] = __ldg(xs + p + 256 * j);
+            float2 ev[16], od[16];
+            {   // th'[n] = (n - N/2)(2/N)(0.5 - 0.5 cos(theta_b + j pi/16)): angle addition with constants
+                const float cb = wb[0].x, sb = -wb[0].y, rb = (float)(p - N / 2) * (2.0f / N);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const float cs = fmaf(cb, c32(j), -(sb * s32(j)));
+                    const float th = (rb + (float)j * (256.0f * 2.0f / N)) * fmaf(-0.5f, cs, 0.5f);
+                    const float2 z = make_float2(xr[j], xr[j] * th);
+                    if (j & 1) od[j >> 1] = z; else ev[j >> 1] = z;
+                }
+            }
+            dft16(ev); dft16(od);
+            float2 lo[8], hi[4];
+            lo[1] = wb[0]; lo[2] = wb[1]; lo[4] = wb[2];
+            lo[3] = cmul2(lo[1], lo[2]); lo[5] = cmul2(lo[1], lo[4]); lo[6] = cmul2(lo[2], lo[4]); lo[7] = cmul2(lo[3], lo[4]);
+            hi[1] = wb[3]; hi[2] = wb[4]; hi[3] = cmul2(hi[1], hi[2]);
+            float2* zo = Zb + p;
+            static_for<16>([&](auto ic) {
+                constexpr int i = decltype(ic)::value;
+                const float2 e = ev[o16(i)];
+                const float2 o = i == 0 ? od[o16(0)] : cmul2(od[o16(i)], make_float2(c32(i), -s32(i)));   // W_32^i
+                const float2 x0 = e + o, x1 = e - o;                     // outputs i and i + 16
+                auto tw = [&](auto kc) {
+                    constexpr int k = decltype(kc)::value, l = k & 7, h = k >> 3;
+                    if constexpr (l == 0) return hi[h];
+                    else if constexpr (h == 0) return lo[l];
+                    else return cmul2(lo[l], hi[h]);
+                };
+                if constexpr (i == 0) zo[0] = x0;
+                else zo[kSI * i] = cmul2(x0, tw(std::integral_constant<int, i>{}));
+                zo[kSI * (i + 16)] = cmul2(x1, tw(std::integral_constant<int, i + 16>{}));
+            });
+            worker_bar<kWT>(w);
+        } else {
         // ================= pass A: radix-R0 butterflies b = p + kWT u over n = b + 4096 j0,
         // z[n] = x[n] (1 + j th'[n]); output i0 of butterfly b = b1 + 256 j1 goes to the slot
         // pass B reads it from: Zb[kSI (i0 + R0 j1) + b1]
@@ -1077,6 +1136,7 @@ stft_reassign_r16_large(const StftArgs a_in) {
             twiddle_store_rows<16, kSI * R0>(v, Ztab, b1, zb);
         }
         worker_bar<kWT>(w);
+        }
 
         pass2<kSI, kS16>(Zb, T2, g);
         worker_bar<kWT>(w);

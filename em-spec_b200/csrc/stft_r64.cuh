@@ -141,15 +141,10 @@ __device__ __forceinline__ float2 shfl2(float2 a, int src) {
     return make_float2(__shfl_sync(0xffffffffu, a.x, src), __shfl_sync(0xffffffffu, a.y, src));
 }
 
-// (ptxas sizes the register budget of __launch_bounds__(320) as if the block had 384 threads: 168
-// registers; __maxnreg__ states the real budget of five workers)
+// (five workers: registers are handed out per four warps, so 320 threads get the budget of 384 — 168
+// registers; a 200-register build, __maxnreg__(200), fails to launch: "too many resources requested")
 template <int MODE>
-__global__ void
-#if EMS_R64_WORKERS == 5
-__maxnreg__(200)
-#else
-__launch_bounds__(kThreads64, 1)
-#endif
+__global__ void __launch_bounds__(kThreads64, 1)
 stft_reassign_r64(const StftArgs a_in, const int tile_T) {
     constexpr int N = kN, B = N / 2 + 1;
     StftArgs a = a_in;
