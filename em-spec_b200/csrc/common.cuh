@@ -38,6 +38,9 @@ enum DepositMode : int {
     kDepositF32  = 2    // red.global.add.f32 fast mode
 };
 
+// EXPERIMENT, compiled in only with -DEMS_FUSED_POST=1 (measured 5 x slower than the two-kernel path:
+// a worker that runs the shaping code next to workers running the FFT thrashes the instruction cache;
+// profiles/r02_fused_post_*.txt).
 // In-kernel post-pass ("fused" mode of the deposit kernels, stft_r16.cuh): the accumulator is one ring
 // of `vring` columns shared by all channels (virtual column = ch * F + col), small enough to stay in
 // L2; a CTA that completes the last tile a column block was waiting for shapes that block straight

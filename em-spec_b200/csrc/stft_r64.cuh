@@ -16,7 +16,16 @@
 //     that column), so there is no separate X buffer; the epilogue reads its two neighbours from the
 //     adjacent columns.  3 worker barriers per frame (2 warps each).
 // Shared-memory wavefronts per frame: 128 tile + 128 th' + 256 + 256 exchange + 128 shuffles +
-// 128 X + 256 neighbours = 1,280 against 1,931 of the three-pass kernel.
+// 128 X + 256 neighbours = 1,280 by design, 1,424 measured (ncu), against 1,931 of the three-pass kernel.
+//
+// RESULT (B200, profiles/r02_ncu_r64_v2.txt, r02_r64_*_times.txt): parity green, 5,018 warp instructions per
+// frame (three-pass: 5,560), but 64 values per thread means 255 registers and 8 warps per SM: the kernel
+// is latency-bound (issue slots 39 %, FMA pipe 47 %, l1tex 49 %) and runs at 94-99 M frames/s against 103-105 M
+// for the three-pass kernel.  More warps are not to be had: five workers get the register budget of six (168,
+// registers are handed out per four warps) and spill, and tensor memory as a register-file extension
+// (EMS_R64_TMEM / EMS_R64_PARK: th' and 2 X_th' parked in TMEM with tcgen05.st / tcgen05.ld) works but its
+// ~300-cycle loads cost more than the shared-memory table they replace.  Selected only with
+// EMS_KERNEL_VARIANT=64 (A/B runs, tools/variant_check.py); the product path stays stft_r16.cuh.
 #pragma once
 #include "stft_r16.cuh"
 
