@@ -706,8 +706,11 @@ __device__ __noinline__ void fused_post_block(void* acc, unsigned char* flags, c
 }
 
 // ---------------------------------------------------------------- n_fft = 256 .. 4096
+#ifndef EMS_R16_LB
+#define EMS_R16_LB kThreads      // (register-budget experiments compile with a larger bound)
+#endif
 template <int R, int MODE>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(EMS_R16_LB, 1)
 stft_reassign_r16(const StftArgs a_in, const int tile_T) {
     using C = Cfg<R>;
     constexpr int N = C::N, kWT = C::kWT, kWorkers = C::kWorkers, kZBuf = C::kZBuf,

@@ -687,3 +687,62 @@ def test_image_summary_is_exact(emspec):
         assert (got[:, 0] == flat.sum(1)).all()
         assert (got[:, 1] == (flat * w[None, :]).sum(1)).all()
         eng.close()
+
+
+def test_host_path_formats_chunked_and_tiny(emspec, monkeypatch):
+    """ems_process_host* with many small chunks (ring wrap, staging hand-over, ragged int24 quads at chunk
+    starts), three channels, fp32 grid output; and the smallest inputs (one frame, one column)."""
+    monkeypatch.setenv("EMS_HOST_CHUNK_FRAMES", "1100")
+    fl = emspec.FLAG_REASSIGN | emspec.FLAG_DETERMINISTIC | emspec.FLAG_SYNC
+    S = 5 * SR + 7
+    xs = [orc.synth_signal(S, SR, seed=50 + c) for c in range(3)]
+    q = np.clip(np.rint(np.stack(xs, 1).astype(np.float64) * 8388608.0), -8388608, 8388607).astype(np.int32)
+    xf = (q.astype(np.float32) / 8388608.0).T.copy()
+    b = q.astype("<i4").view(np.uint8).reshape(S, 3, 4)[:, :, :3].copy()
+    q16 = np.clip(np.rint(np.stack(xs, 1) * 32768.0), -32768, 32767).astype(np.int16)
+    eng = emspec.Engine(n_fft=1024, hop=100, channels=3, flags=fl)       # hop not a multiple of 4
+    g24, i24 = eng.process_host_i24(torch.from_numpy(b).pin_memory(), want_grid=True)
+    gf, i_f = eng.process_host(torch.from_numpy(xf).pin_memory(), want_grid=True)
+    gd, i_d = eng.process_grid(torch.from_numpy(xf).cuda())
+    assert i24.shape[1] > 2 * 1100                                       # really several chunks
+    assert torch.equal(g24, gf) and torch.equal(i24, i_f)
+    assert torch.equal(gf, gd.cpu()) and torch.equal(i_f, i_d.cpu())
+    g16, i16 = eng.process_host_i16(torch.from_numpy(q16).pin_memory(), want_grid=True)
+    x16 = (q16.astype(np.float32) / 32768.0).T.copy()
+    g16d, i16d = eng.process_grid(torch.from_numpy(x16).cuda())
+    assert torch.equal(g16, g16d.cpu()) and torch.equal(i16, i16d.cpu())
+    eng.close()
+    for S1 in (1024, 1024 + 99, 1024 + 100):                             # F = 1, 1, 2
+        eng = emspec.Engine(n_fft=1024, hop=100, flags=fl)
+        x1 = orc.synth_signal(S1, SR, seed=60)
+        g_h, i_h = eng.process_host(torch.from_numpy(x1).pin_memory(), want_grid=True)
+        g_d, i_d = eng.process_grid(torch.from_numpy(x1).cuda())
+        assert g_h.shape[1] == orc.frame_count(S1, 1024, 100) and torch.equal(g_h, g_d.cpu()) and torch.equal(i_h, i_d.cpu())
+        eng.close()
+
+
+def test_dense_and_sparse_post_pass_agree(emspec):
+    """The post-pass picks the sparse (flagged blocks) or the dense (whole columns) kernel on the device
+    from the dirty flags; both must give the same picture as the oracle, and a handle must be able to
+    alternate between them (flags and accumulator clean after either)."""
+    x_s = orc.synth_signal(SR, SR, seed=70)
+    x_d = orc.synth_music(SR, SR, seed=71)
+    for rows in (0, 300):
+        for det in (True, False):
+            fl = emspec.FLAG_REASSIGN | emspec.FLAG_SYNC | (emspec.FLAG_DETERMINISTIC if det else 0)
+            eng = emspec.Engine(n_fft=2048, hop=128, display_rows=rows, flags=fl)       # default gate: the music-like signal
+            prm = orc.Params(n_fft=2048, hop=128, display_rows=rows, flags=orc.FLAG_REASSIGN | orc.FLAG_DETERMINISTIC)   # dirties every block
+            seen = []
+            for x in (x_d, x_s, x_d):
+                g, idx = eng.process_grid(torch.from_numpy(x).cuda())
+                seen.append((g.cpu(), idx.cpu()))
+            assert torch.equal(seen[0][1], seen[2][1])
+            if det:
+                assert torch.equal(seen[0][0], seen[2][0])
+            for x, (g, idx) in zip((x_d, x_s), seen[:2]):
+                if rows == 0:
+                    err, grid_o, _ = check_grid_dense(g[0].numpy(), x, prm)
+                else:
+                    _, grid_o = check_grid_rows(g[0].numpy(), x, prm)
+                check_index(idx[0].numpy(), grid_o, prm, x, max_excused=5e-4)
+            eng.close()
