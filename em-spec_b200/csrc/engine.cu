@@ -443,7 +443,8 @@ static ems_status run_post(ems_handle* h, PostArgs p) {
         // no recurrence along time: zero-fill the outputs, then visit only the dirty blocks
         if (p.index) EMS_CUDA(h, zero_cols(h, p.index, (size_t)p.B, p, p.out_cols, p.out_col0));
         if (p.grid) EMS_CUDA(h, zero_cols(h, p.grid, (size_t)p.B * sizeof(float), p, p.out_cols, p.out_col0));
-        const dim3 g((unsigned)((ncols + 255) / 256), p.channels * p.NB);
+        if ((ncols + 255) / 256 > 65535) return fail(h, EMS_ERR_UNSUPPORTED, "more than 16.7 M columns in one post-pass");
+        const dim3 g((unsigned)(p.channels * p.NB), (unsigned)((ncols + 255) / 256));
         if (agc) {
             post_sparse_kernel<<<g, 256, 0, h->stream>>>(p, 1, nullptr);
             ++h->launches;
@@ -472,10 +473,11 @@ static ems_status run_post(ems_handle* h, PostArgs p) {
             const unsigned gd = (unsigned)std::min<long long>(ncols * p.channels, (long long)h->sm_count * 16);
             if (p.acc_is_u64) post_dense_kernel<8><<<gd, 128, 0, h->stream>>>(p, mode);
             else post_dense_kernel<16><<<gd, 128, 0, h->stream>>>(p, mode);     // 4-byte cells: twice the loads in flight
+            ++h->launches;
         }
         clear_flags_if_kernel<<<(unsigned)std::min<long long>((nflags + 255) / 256, 4096LL), 256, 0, h->stream>>>(
             p.flags, p.acc_cols, p.acc_mask, p.col_begin, p.col_end, p.channels * p.NB, mode);
-        h->launches += 5;
+        h->launches += 4;
         EMS_CUDA(h, cudaGetLastError());
         return EMS_OK;
     }

@@ -190,15 +190,15 @@ post_emit_kernel(const PostArgs a, const float* __restrict__ carry_in, int n_chu
 // the outputs are zero-filled by memset and this kernel visits only the dirty 64-bin blocks.
 // One warp reads 32 consecutive column flags of a (channel, bin block) row; each flagged
 // block is then shaped by the whole warp (2 bins per lane, coalesced), its accumulator cells
-// and its flag are cleared.  grid: (ceil(ncols/256), channels*NB), 256 threads.
+// and its flag are cleared.  grid: (channels*NB, ceil(ncols/256)), 256 threads.
 // measure = 1 (AGC first pass): only the per-column peak of the shaped energy is produced.
 __global__ void __launch_bounds__(256)
 post_sparse_kernel(const PostArgs a, int measure, const int* __restrict__ mode) {
     if (mode && mode[0] == 1) return;                       // the dense kernel takes this range
     const int lane = threadIdx.x & 31;
-    const int r = blockIdx.y;                               // ch * NB + blk
+    const int r = blockIdx.x;                               // ch * NB + blk (x: up to 65535 channels x NB blocks)
     const int ch = r / a.NB, blk = r - ch * a.NB;
-    const long long cw = a.col_begin + ((long long)blockIdx.x * 8 + (threadIdx.x >> 5)) * 32;
+    const long long cw = a.col_begin + ((long long)blockIdx.y * 8 + (threadIdx.x >> 5)) * 32;
     if (cw >= a.col_end) return;
     const long long c = cw + lane;
     unsigned mask = __ballot_sync(0xffffffffu, c < a.col_end && a.flags[flag_at(a, ch, blk, c)] != 0);

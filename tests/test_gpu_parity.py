@@ -746,3 +746,22 @@ def test_dense_and_sparse_post_pass_agree(emspec):
                     _, grid_o = check_grid_rows(g[0].numpy(), x, prm)
                 check_index(idx[0].numpy(), grid_o, prm, x, max_excused=5e-4)
             eng.close()
+
+
+def test_many_channels(emspec):
+    """A batch maps clips to channels: more than 65535 / NB channels used to overflow the post-pass grid."""
+    C_, S = 2500, 2048
+    rng = np.random.default_rng(11)
+    x = (0.2 * rng.standard_normal((C_, S))).astype(np.float32)
+    x[:, :] += 0.5 * np.sin(2 * np.pi * (np.arange(C_)[:, None] % 100 + 20) * np.arange(S)[None, :] / 256.0).astype(np.float32)
+    fl = emspec.FLAG_REASSIGN | emspec.FLAG_DETERMINISTIC | emspec.FLAG_SYNC
+    eng = emspec.Engine(n_fft=256, hop=64, channels=C_, flags=fl)
+    g, idx = eng.process_grid(torch.from_numpy(x).cuda())
+    summ = eng.image_summary(idx).cpu().numpy()
+    eng.close()
+    one = emspec.Engine(n_fft=256, hop=64, flags=fl)
+    for c in (0, 1, 1984, 1985, 1986, 2499):
+        g1, i1 = one.process_grid(torch.from_numpy(x[c]).cuda())
+        assert torch.equal(g1[0], g[c]) and torch.equal(i1[0], idx[c])
+        assert int(summ[c, 0]) == int(i1.sum(dtype=torch.int64))
+    one.close()
