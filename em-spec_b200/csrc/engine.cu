@@ -82,6 +82,7 @@ struct ems_handle {
     } fz;
     bool force_generic = false;         // EMS_FORCE_GENERIC=1: bypass the tuned kernels (A/B tests)
     int kernel_variant = 0;             // EMS_KERNEL_VARIANT: experimental kernel selection (A/B runs); 0 = default
+    int max_ctas = 0;                   // EMS_MAX_CTAS: cap on the persistent grids (schedule-perturbation tests); 0 = one per SM
     char err[256] = "";
 };
 
@@ -198,7 +199,7 @@ static ems_status launch_big(ems_handle* h, const StftArgs& a) {
     auto kern = stft_reassign_big<LOG2N, THREADS>;
     EMS_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const long long total = (a.f_end - a.f_begin) * a.channels;
-    long long grid = h->sm_count;
+    long long grid = h->max_ctas > 0 ? std::min(h->max_ctas, h->sm_count) : h->sm_count;
     if (grid > total) grid = total;
     if (grid < 1) return EMS_OK;
     const size_t need = (size_t)h->sm_count * (N / 2 + 3) * sizeof(float2);
@@ -231,7 +232,7 @@ static ems_status launch_r16(ems_handle* h, const StftArgs& a) {
                                 : r16::stft_reassign_r16<R, kDepositF32>;
     EMS_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, r16::kMaxSmem));
     const long long n_tiles = ((per_ch + tile_T - 1) / tile_T) * a.channels;
-    long long grid = h->sm_count;
+    long long grid = h->max_ctas > 0 ? std::min(h->max_ctas, h->sm_count) : h->sm_count;
     if (grid > n_tiles) grid = n_tiles;
     if (grid < 1) return EMS_OK;
     if (a.fp.vring > 0) {
@@ -283,7 +284,7 @@ static ems_status launch_r64(ems_handle* h, const StftArgs& a) {
                                 : r64::stft_reassign_r64<kDepositF32>;
     EMS_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, r16::kMaxSmem));
     const long long n_tiles = ((per_ch + tile_T - 1) / tile_T) * a.channels;
-    long long grid = h->sm_count;
+    long long grid = h->max_ctas > 0 ? std::min(h->max_ctas, h->sm_count) : h->sm_count;
     if (grid > n_tiles) grid = n_tiles;
     if (grid < 1) return EMS_OK;
     kern<<<(unsigned)grid, r64::kThreads64, smem, h->stream>>>(a, tile_T);
@@ -302,7 +303,7 @@ static ems_status launch_r16_large(ems_handle* h, const StftArgs& a) {
                                 : r16::stft_reassign_r16_large<R0, kDepositF32>;
     EMS_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
     const long long total = (a.f_end - a.f_begin) * a.channels;
-    long long grid = h->sm_count;
+    long long grid = h->max_ctas > 0 ? std::min(h->max_ctas, h->sm_count) : h->sm_count;
     if (grid > total) grid = total;
     if (grid < 1) return EMS_OK;
     kern<<<(unsigned)grid, C::kThreads, C::kSmemBytes, h->stream>>>(a);
@@ -321,7 +322,7 @@ static ems_status launch_r16_32k(ems_handle* h, const StftArgs& a) {
     constexpr int smem = (C::kZBuf + C::kZtab + r16::kT2) * 8;
     EMS_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     const long long total = (a.f_end - a.f_begin) * a.channels;
-    long long grid = h->sm_count;
+    long long grid = h->max_ctas > 0 ? std::min(h->max_ctas, h->sm_count) : h->sm_count;
     if (grid > total) grid = total;
     if (grid < 1) return EMS_OK;
     const size_t need = (size_t)h->sm_count * r16::k32kScratch * sizeof(float2);
@@ -726,6 +727,7 @@ ems_status ems_create(const ems_params* params, ems_handle** out) {
     h->prm = *params;
     { const char* fg = getenv("EMS_FORCE_GENERIC"); h->force_generic = fg && fg[0] == '1'; }
     { const char* kv = getenv("EMS_KERNEL_VARIANT"); h->kernel_variant = kv ? atoi(kv) : 0; }
+    { const char* mc = getenv("EMS_MAX_CTAS"); h->max_ctas = mc ? atoi(mc) : 0; }
     { const char* fv = getenv("EMS_FUSED_POST"); if (fv) h->fz.mode = atoi(fv); }
     { const char* fr = getenv("EMS_FUSED_RING"); if (fr && atoi(fr) >= 256) { int r = 256; while (r < atoi(fr)) r *= 2; h->fz.ring = r; } }
     auto bail = [&](ems_status s) { ems_destroy(h); return s; };

@@ -765,3 +765,37 @@ def test_many_channels(emspec):
         assert torch.equal(g1[0], g[c]) and torch.equal(i1[0], idx[c])
         assert int(summ[c, 0]) == int(i1.sum(dtype=torch.int64))
     one.close()
+
+
+@pytest.mark.parametrize("n_fft,hop", [(4096, 128), (4096, 333), (1024, 64), (256, 48), (8192, 512)])
+def test_schedule_perturbation_is_bit_exact(emspec, n_fft, hop, monkeypatch):
+    """Race proxy (compute-sanitizer is closed on this pool): the tile hand-over between workers (mbarrier +
+    release counters, no CTA-wide barrier) must give the same bits whatever the schedule.  The persistent
+    grid is capped at 1, 3, 17 and 148 CTAs — different tile-to-CTA maps, different numbers of tiles per
+    buffer, workers with no frame in short tiles — and points and image must not change by a bit."""
+    x = torch.from_numpy(orc.synth_signal(6 * SR + 11, SR, seed=80)).cuda()
+    fl = emspec.FLAG_REASSIGN | emspec.FLAG_DETERMINISTIC | emspec.FLAG_SYNC
+    ref = None
+    for ctas in ("148", "1", "3", "17"):
+        monkeypatch.setenv("EMS_MAX_CTAS", ctas)
+        eng = emspec.Engine(n_fft=n_fft, hop=hop, flags=fl)
+        for rep in range(2):
+            pts = eng.process_points(x)
+            g, idx = eng.process_grid(x)
+            cur = tuple(t.clone() for t in (*pts, g, idx))
+            if ref is None:
+                ref = cur
+            else:
+                assert all(torch.equal(a, b) for a, b in zip(cur, ref)), (ctas, rep)
+        eng.close()
+    monkeypatch.setenv("EMS_MAX_CTAS", "5")
+    monkeypatch.setenv("EMS_KERNEL_VARIANT", "64")
+    if n_fft == 4096:          # the single-exchange variant: its own arithmetic, the same determinism
+        eng = emspec.Engine(n_fft=n_fft, hop=hop, flags=fl)
+        a = tuple(t.clone() for t in eng.process_points(x))
+        eng.close()
+        monkeypatch.setenv("EMS_MAX_CTAS", "148")
+        eng = emspec.Engine(n_fft=n_fft, hop=hop, flags=fl)
+        b = eng.process_points(x)
+        assert all(torch.equal(u, v) for u, v in zip(a, b))
+        eng.close()
