@@ -259,11 +259,11 @@ static ems_status launch_r16(ems_handle* h, const StftArgs& a) {
         af.fp.epoch = ++h->fz.epoch;
         int tt = tile_T;
         void* args[] = {(void*)&af, (void*)&tt};
-        EMS_CUDA(h, cudaLaunchCooperativeKernel((const void*)kern, dim3((unsigned)grid), dim3(r16::kThreads), args, smem, h->stream));
+        EMS_CUDA(h, cudaLaunchCooperativeKernel((const void*)kern, dim3((unsigned)grid), dim3(C::kCta), args, smem, h->stream));
         ++h->launches;
         return EMS_OK;
     }
-    kern<<<(unsigned)grid, r16::kThreads, smem, h->stream>>>(a, tile_T);
+    kern<<<(unsigned)grid, C::kCta, smem, h->stream>>>(a, tile_T);
     ++h->launches;
     EMS_CUDA(h, cudaGetLastError());
     return EMS_OK;

@@ -42,6 +42,11 @@
                                 // barrier fewer than 2 x 16): correct, 30.9 against 33.2 M frames/s (32 loads and 64 live
                                 // registers per thread, spills at 128) — off
 #endif
+#ifndef EMS_R16_W4
+#define EMS_R16_W4 0            // experiment, n_fft = 4096: a fourth worker (16 warps at <= 128 registers):
+                                // 2 X written in place into the Z rows the thread read (no X buffer), th' from a shared-memory
+                                // table instead of 32 registers, one more worker barrier per frame
+#endif
 #ifndef EMS_FUSED_POST
 #define EMS_FUSED_POST 0        // experiment: in-kernel post-pass of the deposit kernels (see fused_post_block): correct, 5 x
                                 // slower, and its mere presence costs the deposit kernels 5 % — compiled out by default
@@ -69,7 +74,9 @@ struct Cfg {
     // a worker is kWT threads, or one warp analysing kG frames side by side when kWT < 32
     static constexpr int kG = kWT < 32 ? 32 / kWT : 1;
     static constexpr int kWorkerThreads = kWT * kG;
-    static constexpr int kWorkers = kThreads / kWorkerThreads;
+    static constexpr bool kW4 = EMS_R16_W4 && R == 16;           // four workers, X in place, th' table in shared memory
+    static constexpr int kCta = kW4 ? 512 : kThreads;            // threads per CTA
+    static constexpr int kWorkers = kCta / kWorkerThreads;
     static constexpr int kU = 32 / R;               // pass-1 butterflies per thread
     static constexpr int kRes = 16 * R;             // output residues of the last pass: k = t + kRes c
     // Z buffer: element b of sub-FFT i sits at kSI i + b + (b >> 4) (kS16 - 16).  With R = 16 the
@@ -79,11 +86,12 @@ struct Cfg {
     static constexpr int kSI = R >= 16 ? 257 : 272 + 16 / R;
     static constexpr int kZBuf = R >= 16 ? 4112 : R * kSI;    // (R = 1: 288 makes the slot size 8 mod 16, so the
                                                               //  frames of one half-warp sit in different banks)
-    static constexpr int kXBuf = N / 2 + 4;         // float2: 2 X[k] at index k + 1, mirrors at 0 and N/2 + 2
+    static constexpr int kXBuf = kW4 ? 0 : N / 2 + 4;   // float2: 2 X[k] at index k + 1, mirrors at 0 and N/2 + 2
     static constexpr int kZtab = kLogR * 256;       // W_N^{b i}, i = 1, 2, 4, .., b < 256 (the other powers are products)
     static constexpr int kTabFloat2 = kZtab + kT2;
     static constexpr int kSlot = kZBuf + kXBuf + kScratch;      // per frame in flight: Z, X, scratch
-    static constexpr int kFixedBytes = (kWorkers * kG * kSlot + kTabFloat2) * 8;
+    static constexpr int kThwBytes = kW4 ? N * 4 : 0;            // th'[n] table
+    static constexpr int kFixedBytes = (kWorkers * kG * kSlot + kTabFloat2) * 8 + kThwBytes;
     static constexpr int kTileFloats = ((kMaxSmem - kFixedBytes - kSyncBytes) / 8) & ~3;   // per buffer, two buffers
     static constexpr int kMaxTile = 12 * kWorkers * kG;
     // frames per tile: both tile buffers must hold (T-1)*hop + N samples
@@ -93,12 +101,15 @@ struct Cfg {
         return t > kMaxTile ? kMaxTile : t;
     }
     __host__ __device__ static constexpr int zpos(int i, int b) { return kSI * i + b + (b >> 4) * (kS16 - 16); }
-    static_assert(kThreads % kWorkerThreads == 0, "workers tile the CTA");
+    static_assert(kCta % kWorkerThreads == 0, "workers tile the CTA");
     static_assert(kZBuf >= zpos(R - 1, 255) + 1, "Z buffer holds every sub-FFT");
     static_assert(kTileFloats >= N && kTileFloats % 4 == 0, "each tile buffer holds at least one frame, 16-byte granular");
     static_assert(kFixedBytes % 16 == 0, "tile buffers (TMA / cp.async destinations) start on a 16-byte boundary");
     static_assert(kFixedBytes + 2 * kTileFloats * 4 + kSyncBytes <= kMaxSmem, "shared memory");
     static_assert(kG == 1 || kSlot % 16 == 8, "frames of one half-warp sit in different banks");
+    // X in place (kW4): 2 X[k], k = t + 256 c, sits at xslot(k) = zrow(t) + c, c <= 8 — slots of the row the owner
+    // of residue t read in pass 3; the mirrors 2 X[-1], 2 X[N/2+1] sit in the scratch (Sc[2], Sc[3])
+    __host__ __device__ static constexpr int zrow(int t) { return kSI * (t & (R - 1)) + kS16 * (t / R); }
     static_assert(16 + 8 + 4 * kWorkers + 16 + 4 * kWorkers <= kSyncBytes, "mbarriers, release counters, refill flags, finish counters and go flags fit their block");
 };
 
@@ -488,8 +499,8 @@ __device__ __forceinline__ void pass2(float2* Zb, const float2* T2, const Geom& 
 // selects inside the common instruction stream (a divergent branch here would put both paths
 // on the critical warp of the worker, and the other warps wait for it at the next barrier).
 // Residue 0 has a ninth bin, N/2: thread 0 untangles it on the side (Xs, Sc[0]).
-template <int R>
-__device__ __forceinline__ void pass3_untangle(const float2* Zb, float2* Xs, float2* Sc, const Geom& g,
+template <int R, bool XZ = false>
+__device__ __forceinline__ void pass3_untangle(float2* Zb, float2* Xs, float2* Sc, const Geom& g,
                                                float2 (&xa)[8], float2 (&xb)[8], float2 (&ta)[8], float2 (&tb)[8]) {
     constexpr int kRes = 16 * R, N = 256 * R;
     const int tA = g.tA, tB = g.tB;
@@ -506,16 +517,16 @@ __device__ __forceinline__ void pass3_untangle(const float2* Zb, float2* Xs, flo
         const float2 zb_n = cj(pa), za_n = cj(pb);
         xa[c] = za_c + zb_n; ta[c] = mulmj(za_c - zb_n);
         xb[c] = zb_c + za_n; tb[c] = mulmj(zb_c - za_n);
-        Xs[1 + tA + kRes * c] = xa[c];
-        Xs[1 + tB + kRes * c] = xb[c];
+        if constexpr (XZ) { Zb[g.zA + c] = xa[c]; Zb[g.zB + c] = xb[c]; }       // in place: rows this thread has just read
+        else { Xs[1 + tA + kRes * c] = xa[c]; Xs[1 + tB + kRes * c] = xb[c]; }
     });
     if (g.p == 1) {      // Hermitian mirrors: X[-1] = conj X[1], X[N/2+1] = conj X[N/2-1]
-        Xs[0] = cj(xa[0]);
-        Xs[N / 2 + 2] = cj(xb[7]);
+        if constexpr (XZ) { Sc[2] = cj(xa[0]); Sc[3] = cj(xb[7]); }       // (not in the Z rows: other threads still read them)
+        else { Xs[0] = cj(xa[0]); Xs[N / 2 + 2] = cj(xb[7]); }
     }
     if (self) {
         const float2 z = za[o16(8)], zn = cj(z);
-        Xs[1 + N / 2] = z + zn;
+        if constexpr (XZ) Zb[g.zA + 8] = z + zn; else Xs[1 + N / 2] = z + zn;
         Sc[0] = mulmj(z - zn);
     }
 }
@@ -526,11 +537,21 @@ __device__ __forceinline__ void pass3_untangle(const float2* Zb, float2* Xs, flo
 // per bin; gating all 16 first costs registers and is slower).
 // `active` is false for the lanes of a sub-warp worker whose frame slot is past the end of the tile:
 // they tag along (the warp votes) and emit nothing.
-template <int R, int MODE>
+template <int R, int MODE, bool XZ = false>
 __device__ __forceinline__ void epilogue(const StftArgs& a, int ch, long long f, const float2* Xs, const float2* Sc,
                                          const Geom& g, const float2 (&xa)[8], const float2 (&xb)[8],
                                          const float2 (&ta)[8], const float2 (&tb)[8], bool active = true) {
     constexpr int kRes = 16 * R, N = 256 * R, B = N / 2 + 1, kWT = 8 * R;
+    // XZ: Xs is the Z buffer; the neighbours of bin t + 256 c sit at zrow(t -+ 1) + c (residue 0's lower
+    // neighbour is residue 255 one c down, residue 255's upper neighbour is residue 0 one c up)
+    const float2* nAm = Xs; const float2* nAp = Xs; const float2* nBm = Xs; const float2* nBp = Xs;
+    if constexpr (XZ) {
+        using C = Cfg<R>;
+        nAm = Xs + (g.tA ? C::zrow(g.tA - 1) : C::zrow(kRes - 1) - 1);
+        nAp = Xs + C::zrow(g.tA + 1);
+        nBm = Xs + C::zrow(g.tB - 1);
+        nBp = Xs + (g.tB < kRes - 1 ? C::zrow(g.tB + 1) : C::zrow(0) + 1);
+    }
     const bool owner = active;
     FrameCtx fc;
     fc.lo = (float)max(-f, -1048576LL);
@@ -558,8 +579,13 @@ __device__ __forceinline__ void epilogue(const StftArgs& a, int ch, long long f,
 #pragma unroll
         for (int i = 0; i < GC; ++i) {
             const int kA = tA + kRes * (c0 + i), kB = tB + kRes * (c0 + i);
-            nm[2 * i] = Xs[kA]; np_[2 * i] = Xs[kA + 2];
-            nm[2 * i + 1] = Xs[kB]; np_[2 * i + 1] = Xs[kB + 2];
+            if constexpr (XZ) {
+                nm[2 * i] = (c0 + i == 0 && g.tA == 0) ? Sc[2] : nAm[c0 + i]; np_[2 * i] = nAp[c0 + i];
+                nm[2 * i + 1] = nBm[c0 + i]; np_[2 * i + 1] = nBp[c0 + i];
+            } else {
+                nm[2 * i] = Xs[kA]; np_[2 * i] = Xs[kA + 2];
+                nm[2 * i + 1] = Xs[kB]; np_[2 * i + 1] = Xs[kB + 2];
+            }
         }
     };
     if (kPrefetch) load_group(0);
@@ -596,20 +622,27 @@ __device__ __forceinline__ void epilogue(const StftArgs& a, int ch, long long f,
                 const int kA = tA + kRes * (c0 + i), kB = tB + kRes * (c0 + i);
                 if (MODE == kStorePoints || __any_sync(0xffffffffu, lv[2 * i]))
                     bin_tail<N, MODE>(a, fA, owner, lv[2 * i], kA, kRes * (c0 + i), g.tAf + (float)(kRes * (c0 + i)),
-                                      A2[2 * i], kPrefetch ? Xs[kA] : cm[2 * i], kPrefetch ? Xs[kA + 2] : cp[2 * i], ta[c0 + i]);
+                                      A2[2 * i], kPrefetch ? (XZ ? ((c0 + i == 0 && g.tA == 0) ? Sc[2] : nAm[c0 + i]) : Xs[kA]) : cm[2 * i],
+                                      kPrefetch ? (XZ ? nAp[c0 + i] : Xs[kA + 2]) : cp[2 * i], ta[c0 + i]);
                 else
                     bin_dead<MODE>(fA, owner, kRes * (c0 + i));
                 if (MODE == kStorePoints || __any_sync(0xffffffffu, lv[2 * i + 1]))
                     bin_tail<N, MODE>(a, fB, owner, lv[2 * i + 1], kB, kRes * (c0 + i), g.tBf + (float)(kRes * (c0 + i)),
-                                      A2[2 * i + 1], kPrefetch ? Xs[kB] : cm[2 * i + 1], kPrefetch ? Xs[kB + 2] : cp[2 * i + 1], tb[c0 + i]);
+                                      A2[2 * i + 1], kPrefetch ? (XZ ? nBm[c0 + i] : Xs[kB]) : cm[2 * i + 1],
+                                      kPrefetch ? (XZ ? nBp[c0 + i] : Xs[kB + 2]) : cp[2 * i + 1], tb[c0 + i]);
                 else
                     bin_dead<MODE>(fB, owner, kRes * (c0 + i));
             }
         }
     });
     // bin N/2, the ninth of residue 0: thread 0 of the frame (its warp tags along)
-    if (kWT < 32 || g.p < 32)
-        bin_emit<N, MODE>(a, fc, owner && g.p == 0, N / 2, (float)(N / 2), Xs[N / 2 + 1], Xs[N / 2], Xs[N / 2 + 2], Sc[0]);
+    if (kWT < 32 || g.p < 32) {
+        if constexpr (XZ)
+            bin_emit<N, MODE>(a, fc, owner && g.p == 0, N / 2, (float)(N / 2), Xs[Cfg<R>::zrow(0) + 8],
+                              Xs[Cfg<R>::zrow(kRes - 1) + 7], Sc[3], Sc[0]);
+        else
+            bin_emit<N, MODE>(a, fc, owner && g.p == 0, N / 2, (float)(N / 2), Xs[N / 2 + 1], Xs[N / 2], Xs[N / 2 + 2], Sc[0]);
+    }
 }
 
 // ---------------------------------------------------------------- in-kernel post-pass (fused mode)
@@ -706,13 +739,12 @@ __device__ __noinline__ void fused_post_block(void* acc, unsigned char* flags, c
 }
 
 // ---------------------------------------------------------------- n_fft = 256 .. 4096
-#ifndef EMS_R16_LB
-#define EMS_R16_LB kThreads      // (register-budget experiments compile with a larger bound)
-#endif
 template <int R, int MODE>
-__global__ void __launch_bounds__(EMS_R16_LB, 1)
+__global__ void __launch_bounds__(Cfg<R>::kCta, 1)
 stft_reassign_r16(const StftArgs a_in, const int tile_T) {
     using C = Cfg<R>;
+    constexpr int kThreads = C::kCta;          // (shadows the namespace constant: 512 in the four-worker build of R = 16)
+    constexpr bool kW4 = C::kW4;
     constexpr int N = C::N, kWT = C::kWT, kWorkers = C::kWorkers, kZBuf = C::kZBuf,
                   kXBuf = C::kXBuf, kZtab = C::kZtab, kTileFloats = C::kTileFloats, kSI = C::kSI,
                   kS16 = C::kS16, kU = C::kU, kG = C::kG, kSlot = C::kSlot, kWTh = C::kWorkerThreads;
@@ -723,7 +755,8 @@ stft_reassign_r16(const StftArgs a_in, const int tile_T) {
     float2* Ztab = sm;                         // [log2 R][256]: rows i = 1, 2, 4, ..
     float2* T2 = Ztab + kZtab;                 // [16][16]
     float2* wbuf = T2 + kT2;                   // per worker: Z, X, scratch
-    float* tile0 = reinterpret_cast<float*>(wbuf + kWorkers * kG * kSlot);   // 2 x kTileFloats
+    float* thwS = reinterpret_cast<float*>(wbuf + kWorkers * kG * kSlot);    // kW4: th'[n] table
+    float* tile0 = thwS + (kW4 ? N : 0);                                     // 2 x kTileFloats
 
     const int tid = threadIdx.x;
     const int w = tid / kWTh;                  // worker
@@ -733,8 +766,8 @@ stft_reassign_r16(const StftArgs a_in, const int tile_T) {
     // carrying the self-paired bins lands on a different scheduler in each worker
     const int p = kG > 1 ? wl % kWT : (tid + 32 * w) & (kWT - 1);
     float2* Zb = wbuf + (w * kG + gs) * kSlot;
-    float2* Xs = Zb + kZBuf;                   // 2 X[k] at Xs[k + 1]
-    float2* Sc = Xs + kXBuf;
+    float2* Xs = kW4 ? Zb : Zb + kZBuf;        // 2 X[k] at Xs[k + 1] (kW4: in place in the Z buffer, at zrow(k & 255) + (k >> 8))
+    float2* Sc = Zb + kZBuf + kXBuf;
 
     // ---- twiddle tables (once per CTA)
     for (int e = tid; e < kZtab; e += kThreads) { const int i = 1 << (e / 256), b = e % 256; Ztab[e] = __ldg(&a.tw[b * i]); }
@@ -744,10 +777,14 @@ stft_reassign_r16(const StftArgs a_in, const int tile_T) {
     // th'[n] at this thread's 32 pass-1 samples n = p + kWT u + 256 j: frame-independent, so they
     // live in registers for the whole persistent loop
     float thw[kU][R];
+    if constexpr (kW4) {
+        for (int e = tid; e < N; e += kThreads) thwS[e] = __ldg(&a.thw[e]);
+    } else {
 #pragma unroll
-    for (int u = 0; u < kU; ++u)
+        for (int u = 0; u < kU; ++u)
 #pragma unroll
-        for (int j = 0; j < R; ++j) thw[u][j] = __ldg(&a.thw[p + kWT * u + 256 * j]);
+            for (int j = 0; j < R; ++j) thw[u][j] = __ldg(&a.thw[p + kWT * u + 256 * j]);
+    }
     const Geom g = make_geom<R, kSI, kS16>(p);
 
     const long long per_ch = a.f_end - a.f_begin;
@@ -947,12 +984,15 @@ stft_reassign_r16(const StftArgs a_in, const int tile_T) {
             for (int u = 0; u < kU; ++u)
 #pragma unroll
                 for (int j = 0; j < R; ++j) xr[u][j] = xs[p + kWT * u + 256 * j];   // n = b + 256 j
+            // kW4: the Z buffer still holds the previous frame's X until every warp of the worker has left its epilogue
+            if constexpr (kW4) worker_bar<kWT>(w);
             static_for<kU>([&](auto uc) {
                 constexpr int u = decltype(uc)::value;
                 const int b = p + kWT * u;
                 float2 v[R];
 #pragma unroll
-                for (int j = 0; j < R; ++j) v[j] = make_float2(xr[u][j], xr[u][j] * thw[u][j]);
+                for (int j = 0; j < R; ++j)
+                    v[j] = make_float2(xr[u][j], xr[u][j] * (kW4 ? thwS[p + kWT * u + 256 * j] : thw[u][j]));
                 dftR(v);
                 twiddle_store_rows<R, kSI>(v, Ztab, b, Zb + b + (b >> 4) * (kS16 - 16));
             });
@@ -964,10 +1004,10 @@ stft_reassign_r16(const StftArgs a_in, const int tile_T) {
             if (last_frame && refill[w]) refill_tile(buf, ti + 2);
 
             float2 xa[8], xb[8], ta[8], tb[8];     // bins tA + kRes c and tB + kRes c, c = 0..7
-            pass3_untangle<R>(Zb, Xs, Sc, g, xa, xb, ta, tb);
+            pass3_untangle<R, kW4>(Zb, Xs, Sc, g, xa, xb, ta, tb);
             worker_bar<kWT>(w);      // X visible; the Z buffer is free for the next frame's pass 1
 
-            epilogue<R, MODE>(a, ch, f, Xs, Sc, g, xa, xb, ta, tb, active);
+            epilogue<R, MODE, kW4>(a, ch, f, Xs, Sc, g, xa, xb, ta, tb, active);
             }
         }
         if (fused) tile_done(tl, ti, ch);
