@@ -937,6 +937,41 @@ ems_status ems_process_grid(ems_handle* h, const float* pcm, size_t S, float* gr
             return finish(h);
         }
     }
+    if (h->prm.flags & EMS_FLAG_BOUNDED_SCRATCH) {
+        // The same result in O(chunk) device memory: frame chunks deposit into an accumulator ring of
+        // 2^n >= chunk + 2R columns and the post-pass shapes, into the caller's buffers, the columns no
+        // later frame can reach.  A chunk is a whole number of rounds of the persistent grid
+        // (sm_count x 36 frames), so the per-chunk tail is small: about 2-6 % slower than one launch.
+        const int N = h->prm.n_fft, H = h->prm.hop;
+        const long long Rc = (N / 2 + H - 1) / H;
+        long long chunk = 24LL * h->sm_count * 36;
+        if (chunk * C > (1LL << 20)) chunk = std::max<long long>((1LL << 20) / C, 4 * Rc + 1024);
+        if (chunk > F) chunk = F;
+        long long ring = 1;
+        while (ring < chunk + 2 * Rc + 2) ring *= 2;
+        ems_status s = prepare_acc(h, (size_t)C * ring * R, (size_t)C * ring, R);
+        if (s != EMS_OK) return s;
+        if ((s = reset_carry(h)) != EMS_OK) return s;
+        stage_begin(h, EMS_STAGE_POINTS);      // (the stages interleave: both brackets span the whole call)
+        long long cols_done = 0;
+        for (long long f0 = 0; f0 < F; f0 += chunk) {
+            const long long f1 = std::min(F, f0 + chunk);
+            StftArgs a = make_args(h, pcm, S, F);
+            a.f_begin = f0; a.f_end = f1;
+            a.acc = h->acc.p; a.flags = (unsigned char*)h->flags.p; a.mode = det ? kDepositU64 : kDepositF32;
+            a.ring = (int)ring;
+            if ((s = launch_stft(h, a)) != EMS_OK) { stage_abort(); return s; }
+            const long long col_end = (f1 == F) ? F : std::max(cols_done, f1 - Rc);
+            PostArgs p = make_post(h, F, grid, index);
+            p.col_begin = cols_done; p.col_end = col_end;
+            p.acc_cols = ring; p.acc_mask = ring - 1;
+            if ((s = run_post(h, p)) != EMS_OK) { stage_abort(); return s; }
+            cols_done = col_end;
+        }
+        stage_end(h, EMS_STAGE_POINTS);
+        h->acc_clean = true;
+        return finish(h);
+    }
     const size_t cells = (size_t)C * F * R;
     ems_status s = prepare_acc(h, cells, (size_t)C * F, R);
     if (s != EMS_OK) return s;

@@ -52,6 +52,10 @@ typedef enum ems_status {
                                      bit-exact across runs; 0: fp32 red.global.add fast mode.
                                      PCM is expected in [-1, 1] (full scale 1.0). */
 #define EMS_FLAG_SYNC          4u /* offline calls synchronise the stream before returning */
+#define EMS_FLAG_BOUNDED_SCRATCH 8u /* ems_process_grid works in frame chunks on an accumulator ring instead of an
+                                     accumulator the size of the call (22 GB for an hour of mono at 4096/128
+                                     becomes 2 GB); same bits out, a few per cent slower.  ems_process_host*
+                                     always work that way. */
 
 /* Parameter surface = the README settings glossary (/root/reference/README.md:41-51);
  * defaults in comments are the "Default" preset of assets/settings.png. */

@@ -801,3 +801,34 @@ def test_schedule_perturbation_is_bit_exact(emspec, n_fft, hop, monkeypatch):
         b = eng.process_points(x)
         assert all(torch.equal(u, v) for u, v in zip(a, b))
         eng.close()
+
+
+def test_process_grid_bounded_scratch(emspec):
+    """EMS_FLAG_BOUNDED_SCRATCH: ems_process_grid in frame chunks on an accumulator ring gives the same bits
+    as the one-launch path (deterministic mode), with smoothing + AGC carried across chunks, for one and for
+    several channels, and holds a fraction of the memory."""
+    fl = emspec.FLAG_REASSIGN | emspec.FLAG_DETERMINISTIC | emspec.FLAG_SYNC
+    S = 600 * SR
+    g = torch.Generator(device="cuda").manual_seed(5)
+    t = torch.arange(S, device="cuda", dtype=torch.float64) / SR
+    x = (0.3 * torch.sin(2 * np.pi * (300.0 * t + 10.0 * t * t)) + 0.1 * torch.sin(2 * np.pi * 2500.0 * t)).float()
+    x += 2e-3 * torch.randn(S, device="cuda", generator=g)
+    for kw in (dict(), dict(smoothing=0.5, agc_strength=0.6)):
+        a = emspec.Engine(n_fft=4096, hop=128, flags=fl, **kw)
+        b = emspec.Engine(n_fft=4096, hop=128, flags=fl | emspec.FLAG_BOUNDED_SCRATCH, **kw)
+        ga, ia = a.process_grid(x)
+        gb, ib = b.process_grid(x)
+        assert ia.shape[1] > 24 * 148 * 36                      # really more than one chunk
+        assert torch.equal(ga, gb)
+        d = (ia.int() - ib.int()).abs()
+        assert d.max() <= (1 if kw else 0) and (d > 0).float().mean() < 1e-4
+        assert b.scratch_bytes() < 0.7 * a.scratch_bytes() and b.scratch_bytes() < 2.5 * 2 ** 30     # constant in the stream length
+        a.close(); b.close()
+    del ga, gb, ia, ib
+    xs = torch.stack([x[: 20 * SR], x[20 * SR: 40 * SR], x[40 * SR: 60 * SR]]).contiguous()
+    a = emspec.Engine(n_fft=2048, hop=64, channels=3, flags=fl)
+    b = emspec.Engine(n_fft=2048, hop=64, channels=3, flags=fl | emspec.FLAG_BOUNDED_SCRATCH)
+    ga, ia = a.process_grid(xs)
+    gb, ib = b.process_grid(xs)
+    assert torch.equal(ga, gb) and torch.equal(ia, ib)
+    a.close(); b.close()
