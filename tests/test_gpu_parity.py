@@ -832,3 +832,35 @@ def test_process_grid_bounded_scratch(emspec):
     gb, ib = b.process_grid(xs)
     assert torch.equal(ga, gb) and torch.equal(ia, ib)
     a.close(); b.close()
+
+
+def test_handle_lifecycle_releases_device_memory(emspec):
+    """Create / use / destroy many handles along every path (points, grid, bounded scratch, host formats,
+    streaming with checkpoint): the device memory in use returns to where it started."""
+    torch.cuda.synchronize()
+    x = torch.from_numpy(orc.synth_signal(2 * SR, SR, seed=90)).cuda()
+    xh = x.cpu().pin_memory()
+    q = (x.cpu() * 32768.0).round().clamp_(-32768, 32767).to(torch.int16)[:, None].contiguous().pin_memory()
+    free0 = torch.cuda.mem_get_info()[0]
+    for it in range(12):
+        n_fft, hop = ((4096, 128), (1024, 100), (8192, 512), (256, 64))[it % 4]
+        fl = emspec.FLAG_REASSIGN | emspec.FLAG_SYNC | (emspec.FLAG_DETERMINISTIC if it % 2 else 0) | \
+            (emspec.FLAG_BOUNDED_SCRATCH if it % 3 == 0 else 0)
+        eng = emspec.Engine(n_fft=n_fft, hop=hop, flags=fl, smoothing=0.3 * (it % 2), agc_strength=0.5 * ((it // 2) % 2),
+                            display_rows=(0, 200)[it % 2])
+        pts = eng.process_points(x)
+        g, i = eng.process_grid(x)
+        eng.process_host(xh, want_grid=(it % 2 == 0))
+        eng.process_host_i16(q)
+        col = torch.empty((1, eng.n_rows), dtype=torch.uint8).pin_memory()
+        for k in range(2 * n_fft // hop + 3):
+            eng.stream_push(xh[k * hop:(k + 1) * hop].contiguous(), col)
+        blob = eng.stream_save()
+        eng.stream_load(blob)
+        eng.stream_push(xh[:hop].contiguous(), col)
+        del pts, g, i
+        eng.close()
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
+    free1 = torch.cuda.mem_get_info()[0]
+    assert free0 - free1 < 64 * 2 ** 20, (free0, free1)
