@@ -68,6 +68,10 @@ struct ems_handle {
         float* agc = nullptr;            // [2][channels]
         float* in_pin = nullptr;         // pinned staging
         uint8_t* out_pin = nullptr;
+        uint32_t* lut = nullptr;         // device colour map of ems_stream_set_colormap (null: off)
+        uint32_t* rgba_pin = nullptr;    // pinned [channels][B] pixels of the final column, and its device alias
+        uint32_t* rgba_dev = nullptr;
+        bool lut_on = false, last_ready = false;
         int M = 0, Lr = 0, R = 0, ring_cols = 0;
         int in_i16 = 0;                  // format of the hop the captured graph reads (0: fp32, 1: int16)
         long long pushes = 0;            // host mirror of the device counter
@@ -582,10 +586,11 @@ static ems_status finish(ems_handle* h) {
 static void stream_free(ems_handle* h) {
     auto& st = h->st;
     if (st.graph) cudaGraphExecDestroy(st.graph);
-    for (void* p : {(void*)st.sstate, (void*)st.ring, st.acc, (void*)st.carry, (void*)st.etmp, (void*)st.agc})
+    for (void* p : {(void*)st.sstate, (void*)st.ring, st.acc, (void*)st.carry, (void*)st.etmp, (void*)st.agc, (void*)st.lut})
         if (p) cudaFree(p);
     if (st.in_pin) cudaFreeHost(st.in_pin);
     if (st.out_pin) cudaFreeHost(st.out_pin);
+    if (st.rgba_pin) cudaFreeHost(st.rgba_pin);
     st = ems_handle::Stream{};
 }
 
@@ -599,6 +604,7 @@ static ems_status stream_zero(ems_handle* h) {
     EMS_CUDA(h, cudaMemsetAsync(st.agc, 0, sizeof(float) * 2 * C, h->stream));
     EMS_CUDA(h, cudaStreamSynchronize(h->stream));
     st.pushes = 0;
+    st.last_ready = false;
     return EMS_OK;
 }
 
@@ -649,6 +655,7 @@ static ems_status stream_capture(ems_handle* h) {
     sa.gate_db = h->prm.noise_gate_db;
     sa.etmp = st.etmp; sa.agc = st.agc; sa.agc_strength = h->prm.agc_strength; sa.agc_target = agc_target(h->prm);
     sa.in_i16 = st.in_i16;
+    sa.lut = st.lut_on ? st.lut : nullptr; sa.out_rgba = st.rgba_dev;
     sa.agc_lambda = std::exp(-(float)H / (h->prm.sample_rate * kAgcReleaseSeconds));
     StftArgs a = make_args(h, st.ring, (size_t)2 * st.Lr, /*F=*/(long long)1 << 60);
     a.f_begin = 0; a.f_end = 1;                       // grid sizing; the kernel decodes the real frame
@@ -1232,8 +1239,43 @@ static ems_status stream_push_impl(ems_handle* h, const void* pcm_host, int is_i
     const long long cf = st.pushes + 1 - st.M - st.R;   // column finalised by this push
     ++st.pushes;
     *column_ready = cf >= 0;
+    st.last_ready = cf >= 0;
     if (column_index) *column_index = cf;
     if (cf >= 0) memcpy(column_host, st.out_pin, (size_t)C * B);
+    return EMS_OK;
+}
+
+ems_status ems_stream_set_colormap(ems_handle* h, const uint32_t* lut_rgba_host) {
+    if (!h) return EMS_ERR_INVALID_ARG;
+    auto& st = h->st;
+    ems_status s;
+    if (!st.ready && (s = stream_init(h)) != EMS_OK) return s;
+    EMS_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (lut_rgba_host) {
+        const size_t px = (size_t)h->prm.channels * rows_of(h->prm);
+        if (!st.lut) EMS_CUDA(h, cudaMalloc(&st.lut, 256 * sizeof(uint32_t)));
+        if (!st.rgba_pin) {
+            EMS_CUDA(h, cudaHostAlloc(&st.rgba_pin, px * sizeof(uint32_t), cudaHostAllocMapped));
+            EMS_CUDA(h, cudaHostGetDevicePointer((void**)&st.rgba_dev, st.rgba_pin, 0));
+        }
+        EMS_CUDA(h, cudaMemcpy(st.lut, lut_rgba_host, 256 * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    }
+    const bool on = lut_rgba_host != nullptr;
+    if (on != st.lut_on && st.graph) {              // the finish kernel of the graph has the table pointer baked in
+        cudaGraphExecDestroy(st.graph);
+        st.graph = nullptr;
+    }
+    st.lut_on = on;
+    st.last_ready = false;
+    return EMS_OK;
+}
+
+ems_status ems_stream_column_rgba(ems_handle* h, uint32_t* rgba_host) {
+    if (!h || !rgba_host) return EMS_ERR_INVALID_ARG;
+    auto& st = h->st;
+    if (!st.ready || !st.lut_on) return fail(h, EMS_ERR_STATE, "no colour map set (ems_stream_set_colormap)");
+    if (!st.last_ready) return fail(h, EMS_ERR_STATE, "the last push delivered no column");
+    memcpy(rgba_host, st.rgba_pin, (size_t)h->prm.channels * rows_of(h->prm) * sizeof(uint32_t));
     return EMS_OK;
 }
 
@@ -1323,6 +1365,7 @@ ems_status ems_stream_load(ems_handle* h, const void* blob, size_t bytes) {
     EMS_CUDA(h, cudaMemcpy(st.carry, p, b.carry_bytes, cudaMemcpyHostToDevice)); p += b.carry_bytes;
     EMS_CUDA(h, cudaMemcpy(st.agc, p, b.agc_bytes, cudaMemcpyHostToDevice));
     st.pushes = pushes;
+    st.last_ready = false;
     return EMS_OK;
 }
 

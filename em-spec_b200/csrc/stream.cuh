@@ -22,6 +22,8 @@ struct StreamArgs {
     int hop, channels, M, Lr, R, ring_cols, B, acc_is_u64;
     float smoothing, db_floor, inv_range, gate_db, agc_strength, agc_lambda, agc_target;
     int in_i16;              // the hop is int16 (full scale 32768) instead of fp32
+    const uint32_t* lut;     // [256] RGBA colour map (ems_stream_set_colormap), or null
+    uint32_t*    out_rgba;   // [channels][B] pixels of the final column (mapped pinned host memory)
 };
 
 // De-interleaves the hop and writes it twice (pos and pos + Lr) so that any n_fft-long
@@ -92,7 +94,9 @@ stream_finish_kernel(const StreamArgs s) {
         pa.db_floor = s.db_floor; pa.inv_range = s.inv_range; pa.gate_db = s.gate_db;
         for (int k = k0; k < s.B; k += kstep) {
             const int e = ch * s.B + k;
-            s.out[e] = s.agc_strength > 0.f ? colour_index(s.etmp[e], scale, pa) : colour_index(s.etmp[e], pa);
+            const uint8_t ci = s.agc_strength > 0.f ? colour_index(s.etmp[e], scale, pa) : colour_index(s.etmp[e], pa);
+            s.out[e] = ci;
+            if (s.lut) s.out_rgba[e] = __ldg(s.lut + ci);
         }
     }
     __syncthreads();

@@ -69,6 +69,8 @@ _SIG = {
     "ems_launch_count": (C.c_int, [_VP, C.POINTER(C.c_uint64)]),
     "ems_stream_push": (C.c_int, [_VP, _FP, _U8P, C.POINTER(C.c_int), C.POINTER(C.c_int64)]),
     "ems_stream_push_i16": (C.c_int, [_VP, _VP, _U8P, C.POINTER(C.c_int), C.POINTER(C.c_int64)]),
+    "ems_stream_set_colormap": (C.c_int, [_VP, _VP]),
+    "ems_stream_column_rgba": (C.c_int, [_VP, _VP]),
     "ems_stream_reset": (C.c_int, [_VP]),
     "ems_stream_state_size": (C.c_int, [_VP, C.POINTER(C.c_size_t)]),
     "ems_stream_save": (C.c_int, [_VP, _VP, C.c_size_t]),
@@ -325,6 +327,21 @@ class Engine:
 
     def stream_load(self, blob: bytes):
         self._check(self.lib.ems_stream_load(self.h, blob, len(blob)))
+
+    def stream_set_colormap(self, lut_rgba):
+        """lut_rgba: 256 uint32 (0xAABBGGRR) or None to switch the streaming colour map off."""
+        import numpy as np
+        if lut_rgba is None:
+            self._check(self.lib.ems_stream_set_colormap(self.h, None))
+            return
+        lut = np.ascontiguousarray(np.asarray(lut_rgba, dtype=np.uint32))
+        assert lut.size == 256
+        self._check(self.lib.ems_stream_set_colormap(self.h, C.c_void_p(lut.ctypes.data)))
+
+    def stream_column_rgba(self, rgba_host):
+        """rgba_host: CPU int32 [channels][n_rows]; receives the pixels of the column the last push delivered."""
+        self._check(self.lib.ems_stream_column_rgba(self.h, _ptr(rgba_host)))
+        return rgba_host
 
     def stream_push(self, pcm_host, column_host):
         """pcm_host: CPU fp32 (or int16, capture format) [hop*channels] interleaved; column_host: CPU u8 [channels][n_rows].

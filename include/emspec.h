@@ -200,6 +200,15 @@ ems_status ems_stream_push(ems_handle* h, const float* pcm_host, uint8_t* column
  * 32768.  A stream may switch formats between pushes. */
 ems_status ems_stream_push_i16(ems_handle* h, const int16_t* pcm_host, uint8_t* column_host,
                                int* column_ready, int64_t* column_index);
+/* Colour map on the streaming path ("ready-to-blit columns for a scrolling
+ * renderer", /root/reference/README.md:15,45).  lut_rgba_host: 256 packed pixels as in
+ * ems_colorize, copied; NULL switches the map off.  While a map is set the kernel that finishes a
+ * push also writes the final column as pixels, and ems_stream_column_rgba copies the pixels
+ * (u32 [channels][R]) of the column the last push delivered; EMS_ERR_STATE when no map is set or
+ * that push had column_ready = 0.  The map is configuration, not stream state: it is not part
+ * of a checkpoint and survives ems_stream_reset. */
+ems_status ems_stream_set_colormap(ems_handle* h, const uint32_t* lut_rgba_host);
+ems_status ems_stream_column_rgba(ems_handle* h, uint32_t* rgba_host);
 /* Clears the ring, the rolling grid and the smoothing state. */
 ems_status ems_stream_reset(ems_handle* h);
 

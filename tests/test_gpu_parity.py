@@ -649,6 +649,57 @@ def test_stream_push_int16(emspec):
     a.close(); b.close()
 
 
+def test_stream_colormap_columns(emspec):
+    """SURVEY §8f-3 on the streaming path: with a colour map set a push also yields the final column as
+    RGBA pixels = lut[colour index]; the map can be replaced and switched off between pushes, survives a
+    reset, and the pixels are refused when there is no map or no column."""
+    hop, n_fft, ch = 256, 2048, 2
+    x = np.stack([orc.synth_signal(SR // 2, SR, seed=43), orc.synth_signal(SR // 2, SR, seed=44)], 1).astype(np.float32)
+    rng = np.random.default_rng(5)
+    lut1 = rng.integers(0, 2 ** 32, 256, dtype=np.uint64).astype(np.uint32)
+    lut2 = rng.integers(0, 2 ** 32, 256, dtype=np.uint64).astype(np.uint32)
+    eng = emspec.Engine(n_fft=n_fft, hop=hop, channels=ch, agc_strength=0.5, smoothing=0.3)
+    ref = emspec.Engine(n_fft=n_fft, hop=hop, channels=ch, agc_strength=0.5, smoothing=0.3)
+    col = torch.empty((ch, eng.n_rows), dtype=torch.uint8).pin_memory()
+    cref = torch.empty((ch, eng.n_rows), dtype=torch.uint8).pin_memory()
+    px = torch.empty((ch, eng.n_rows), dtype=torch.int32)
+    with pytest.raises(emspec.EmspecError):
+        eng.stream_column_rgba(px)                       # no map
+    eng.stream_set_colormap(lut1)
+    n = {1: 0, 2: 0, 0: 0}
+    for i in range(len(x) // hop):
+        hopbuf = torch.from_numpy(x[i * hop:(i + 1) * hop].reshape(-1)).contiguous()
+        which = (1, 2, 0)[(i // 12) % 3]
+        if i % 12 == 0:
+            eng.stream_set_colormap({1: lut1, 2: lut2, 0: None}[which])
+        r, ci = eng.stream_push(hopbuf, col)
+        r2, ci2 = ref.stream_push(hopbuf, cref)
+        assert (r, ci) == (r2, ci2)
+        if not r or which == 0:
+            with pytest.raises(emspec.EmspecError):
+                eng.stream_column_rgba(px)               # no column yet / map off
+            if r:
+                assert (col.numpy() == cref.numpy()).all()
+                n[0] += 1
+            continue
+        assert (col.numpy() == cref.numpy()).all()       # the index column is unchanged by the map
+        eng.stream_column_rgba(px)
+        lut = lut1 if which == 1 else lut2
+        assert (px.numpy().view(np.uint32) == lut[col.numpy()]).all()
+        n[which] += 1
+    assert min(n.values()) > 10, n
+    eng.stream_set_colormap(lut1)
+    eng.stream_reset()
+    with pytest.raises(emspec.EmspecError):
+        eng.stream_column_rgba(px)                       # reset: no column delivered
+    for i in range(2 * n_fft // hop):
+        r, _ = eng.stream_push(torch.from_numpy(x[i * hop:(i + 1) * hop].reshape(-1)).contiguous(), col)
+    assert r
+    eng.stream_column_rgba(px)
+    assert (px.numpy().view(np.uint32) == lut1[col.numpy()]).all()
+    eng.close(); ref.close()
+
+
 def test_process_host_scratch_is_bounded(emspec):
     """ems_process_host keeps O(chunk) device memory — the scratch of a 10-minute stream
     equals that of a 1-minute one (beyond the AGC-free minimum nothing scales with the stream), stays
