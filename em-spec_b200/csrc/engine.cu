@@ -68,15 +68,16 @@ struct ems_handle {
         float* agc = nullptr;            // [2][channels]
         float* in_pin = nullptr;         // pinned staging
         uint8_t* out_pin = nullptr;
-        uint32_t* lut = nullptr;         // device colour map of ems_stream_set_colormap (null: off)
         uint32_t* rgba_pin = nullptr;    // pinned [channels][B] pixels of the final column, and its device alias
         uint32_t* rgba_dev = nullptr;
-        bool lut_on = false, last_ready = false;
+        bool last_ready = false;         // the last push delivered a column
         int M = 0, Lr = 0, R = 0, ring_cols = 0;
         int in_i16 = 0;                  // format of the hop the captured graph reads (0: fp32, 1: int16)
         long long pushes = 0;            // host mirror of the device counter
         size_t acc_bytes = 0;
     } st;
+    ems::DevBuf stream_lut;             // ems_stream_set_colormap: configuration, outlives the stream state
+    bool stream_lut_on = false;
     struct FusedState {                 // in-kernel post-pass of ems_process_grid (common.cuh FusedPost)
         ems::DevBuf ready, done;        // per-tile arrival counters (self-resetting) and epoch stamps
         int epoch = 0;
@@ -586,7 +587,7 @@ static ems_status finish(ems_handle* h) {
 static void stream_free(ems_handle* h) {
     auto& st = h->st;
     if (st.graph) cudaGraphExecDestroy(st.graph);
-    for (void* p : {(void*)st.sstate, (void*)st.ring, st.acc, (void*)st.carry, (void*)st.etmp, (void*)st.agc, (void*)st.lut})
+    for (void* p : {(void*)st.sstate, (void*)st.ring, st.acc, (void*)st.carry, (void*)st.etmp, (void*)st.agc})
         if (p) cudaFree(p);
     if (st.in_pin) cudaFreeHost(st.in_pin);
     if (st.out_pin) cudaFreeHost(st.out_pin);
@@ -655,7 +656,11 @@ static ems_status stream_capture(ems_handle* h) {
     sa.gate_db = h->prm.noise_gate_db;
     sa.etmp = st.etmp; sa.agc = st.agc; sa.agc_strength = h->prm.agc_strength; sa.agc_target = agc_target(h->prm);
     sa.in_i16 = st.in_i16;
-    sa.lut = st.lut_on ? st.lut : nullptr; sa.out_rgba = st.rgba_dev;
+    if (h->stream_lut_on && !st.rgba_pin) {
+        EMS_CUDA(h, cudaHostAlloc(&st.rgba_pin, (size_t)C * B * sizeof(uint32_t), cudaHostAllocMapped));
+        EMS_CUDA(h, cudaHostGetDevicePointer((void**)&st.rgba_dev, st.rgba_pin, 0));
+    }
+    sa.lut = h->stream_lut_on ? (const uint32_t*)h->stream_lut.p : nullptr; sa.out_rgba = st.rgba_dev;
     sa.agc_lambda = std::exp(-(float)H / (h->prm.sample_rate * kAgcReleaseSeconds));
     StftArgs a = make_args(h, st.ring, (size_t)2 * st.Lr, /*F=*/(long long)1 << 60);
     a.f_begin = 0; a.f_end = 1;                       // grid sizing; the kernel decodes the real frame
@@ -777,7 +782,7 @@ ems_status ems_create(const ems_params* params, ems_handle** out) {
 ems_status ems_destroy(ems_handle* h) {
     if (!h) return EMS_ERR_INVALID_ARG;
     if (h->stream) cudaStreamSynchronize(h->stream);
-    for (DevBuf* b : {&h->acc, &h->flags, &h->carry, &h->ema_local, &h->ema_carry, &h->lut, &h->colscale, &h->agc_level,
+    for (DevBuf* b : {&h->acc, &h->flags, &h->carry, &h->ema_local, &h->ema_carry, &h->lut, &h->stream_lut, &h->colscale, &h->agc_level,
                       &h->big_scratch, &h->post_mode, &h->fz.ready, &h->fz.done, &h->hp.pcm[0], &h->hp.pcm[1], &h->hp.raw[0], &h->hp.raw[1], &h->hp.idx[0], &h->hp.idx[1],
                       &h->hp.grid[0], &h->hp.grid[1]})
         if (b->p) cudaFree(b->p);
@@ -1164,7 +1169,7 @@ ems_status ems_process_host_i24(ems_handle* h, const uint8_t* pcm_host, size_t S
 ems_status ems_scratch_bytes(const ems_handle* h, size_t* bytes) {
     if (!h || !bytes) return EMS_ERR_INVALID_ARG;
     size_t n = 0;
-    for (const DevBuf* b : {&h->acc, &h->flags, &h->carry, &h->ema_local, &h->ema_carry, &h->big_scratch, &h->lut,
+    for (const DevBuf* b : {&h->acc, &h->flags, &h->carry, &h->ema_local, &h->ema_carry, &h->big_scratch, &h->lut, &h->stream_lut,
                             &h->colscale, &h->agc_level, &h->hp.pcm[0], &h->hp.pcm[1], &h->hp.raw[0], &h->hp.raw[1],
                             &h->hp.idx[0], &h->hp.idx[1], &h->hp.grid[0], &h->hp.grid[1]})
         n += b->bytes;
@@ -1248,24 +1253,18 @@ static ems_status stream_push_impl(ems_handle* h, const void* pcm_host, int is_i
 ems_status ems_stream_set_colormap(ems_handle* h, const uint32_t* lut_rgba_host) {
     if (!h) return EMS_ERR_INVALID_ARG;
     auto& st = h->st;
-    ems_status s;
-    if (!st.ready && (s = stream_init(h)) != EMS_OK) return s;
     EMS_CUDA(h, cudaStreamSynchronize(h->stream));
     if (lut_rgba_host) {
-        const size_t px = (size_t)h->prm.channels * rows_of(h->prm);
-        if (!st.lut) EMS_CUDA(h, cudaMalloc(&st.lut, 256 * sizeof(uint32_t)));
-        if (!st.rgba_pin) {
-            EMS_CUDA(h, cudaHostAlloc(&st.rgba_pin, px * sizeof(uint32_t), cudaHostAllocMapped));
-            EMS_CUDA(h, cudaHostGetDevicePointer((void**)&st.rgba_dev, st.rgba_pin, 0));
-        }
-        EMS_CUDA(h, cudaMemcpy(st.lut, lut_rgba_host, 256 * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        ems_status s = ensure(h, h->stream_lut, 256 * sizeof(uint32_t));
+        if (s != EMS_OK) return s;
+        EMS_CUDA(h, cudaMemcpy(h->stream_lut.p, lut_rgba_host, 256 * sizeof(uint32_t), cudaMemcpyHostToDevice));
     }
     const bool on = lut_rgba_host != nullptr;
-    if (on != st.lut_on && st.graph) {              // the finish kernel of the graph has the table pointer baked in
+    if (on != h->stream_lut_on && st.graph) {       // the finish kernel of the graph has the table pointer baked in
         cudaGraphExecDestroy(st.graph);
         st.graph = nullptr;
     }
-    st.lut_on = on;
+    h->stream_lut_on = on;
     st.last_ready = false;
     return EMS_OK;
 }
@@ -1273,8 +1272,8 @@ ems_status ems_stream_set_colormap(ems_handle* h, const uint32_t* lut_rgba_host)
 ems_status ems_stream_column_rgba(ems_handle* h, uint32_t* rgba_host) {
     if (!h || !rgba_host) return EMS_ERR_INVALID_ARG;
     auto& st = h->st;
-    if (!st.ready || !st.lut_on) return fail(h, EMS_ERR_STATE, "no colour map set (ems_stream_set_colormap)");
-    if (!st.last_ready) return fail(h, EMS_ERR_STATE, "the last push delivered no column");
+    if (!h->stream_lut_on) return fail(h, EMS_ERR_STATE, "no colour map set (ems_stream_set_colormap)");
+    if (!st.ready || !st.last_ready || !st.rgba_pin) return fail(h, EMS_ERR_STATE, "the last push delivered no column");
     memcpy(rgba_host, st.rgba_pin, (size_t)h->prm.channels * rows_of(h->prm) * sizeof(uint32_t));
     return EMS_OK;
 }

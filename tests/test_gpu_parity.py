@@ -915,3 +915,77 @@ def test_handle_lifecycle_releases_device_memory(emspec):
     torch.cuda.empty_cache()
     free1 = torch.cuda.mem_get_info()[0]
     assert free0 - free1 < 64 * 2 ** 20, (free0, free1)
+
+
+def test_error_behaviour_with_a_live_handle(emspec):
+    """The C-ABI never throws or aborts: wrong calls on a live handle return the documented status,
+    leave a message in ems_last_error, and the handle keeps working afterwards."""
+    import ctypes as C
+    lib = emspec.load()
+    fl = emspec.FLAG_REASSIGN | emspec.FLAG_DETERMINISTIC | emspec.FLAG_SYNC
+    eng = emspec.Engine(n_fft=1024, hop=256, flags=fl)
+    h = eng.h
+    x = torch.from_numpy(orc.synth_signal(SR // 4, SR, seed=95)).cuda()
+    ref_idx = eng.process_grid(x, want_grid=False)[1].clone()
+    F, B = ref_idx.shape[1], eng.n_bins
+    nf = C.c_size_t()
+    buf = torch.empty((1, F, B), dtype=torch.float32, device="cuda")
+    u8 = torch.empty((1, F, B), dtype=torch.uint8, device="cuda")
+    p = lambda t: C.c_void_p(t.data_ptr())
+    INV, STATE = emspec.ERR_INVALID_ARG, emspec.ERR_STATE
+
+    def err():
+        return lib.ems_last_error(h).decode()
+
+    # null buffers
+    assert lib.ems_process_points(h, None, x.numel(), p(buf), p(buf), p(buf), C.byref(nf)) == INV and err()
+    assert lib.ems_process_points(h, p(x), x.numel(), None, p(buf), p(buf), C.byref(nf)) == INV
+    assert lib.ems_process_grid(h, p(x), x.numel(), None, None, C.byref(nf)) == INV and "NULL" in err().upper()
+    assert lib.ems_colorize(h, p(u8), 16, None, p(buf)) == INV
+    assert lib.ems_image_summary(h, None, F, p(buf)) == INV
+    assert lib.ems_stream_column_rgba(h, None) == INV
+    # a stream shorter than one frame is zero frames, not an error
+    assert lib.ems_process_points(h, p(x), 1000, p(buf), p(buf), p(buf), C.byref(nf)) == emspec.OK and nf.value == 0
+    assert eng.frame_count(1023) == 0 and eng.frame_count(1024) == 1
+    # geometry cannot change on a live handle; display controls can
+    for bad in (dict(n_fft=2048), dict(hop=128), dict(channels=2), dict(display_rows=100), dict(freq_scale=3.0)):
+        q = emspec.Params.from_buffer_copy(eng.params)
+        for k, v in bad.items():
+            setattr(q, k, v)
+        assert lib.ems_update_display(h, C.byref(q)) == INV and "new handle" in err(), bad
+    q = emspec.Params.from_buffer_copy(eng.params)
+    q.smoothing = 1.5
+    assert lib.ems_update_display(h, C.byref(q)) == INV
+    # state errors
+    ms = C.c_float()
+    fresh = emspec.Engine(n_fft=1024, hop=256, flags=fl)
+    assert lib.ems_stage_ms(fresh.h, emspec.STAGE_POINTS, C.byref(ms)) == STATE
+    assert lib.ems_stage_ms(fresh.h, 99, C.byref(ms)) == INV
+    px = torch.empty((1, B), dtype=torch.int32)
+    assert lib.ems_stream_column_rgba(fresh.h, p(px)) == STATE and "colour map" in lib.ems_last_error(fresh.h).decode()
+    # a checkpoint from another geometry, a truncated one and garbage are refused
+    col = torch.empty((1, B), dtype=torch.uint8).pin_memory()
+    hopbuf = torch.zeros(256, dtype=torch.float32)
+    eng.stream_push(hopbuf, col)
+    blob = eng.stream_save()
+    other = emspec.Engine(n_fft=2048, hop=256, flags=fl)
+    other.stream_push(hopbuf, torch.empty((1, 1025), dtype=torch.uint8).pin_memory())
+    assert lib.ems_stream_load(other.h, blob, len(blob)) == INV
+    assert lib.ems_stream_load(h, blob, len(blob) - 8) == INV
+    assert lib.ems_stream_load(h, b"\0" * len(blob), len(blob)) == INV
+    assert lib.ems_stream_load(h, blob, len(blob)) == emspec.OK
+    # the colour map is configuration: it survives the accumulator-type change that rebuilds the stream state
+    lut = np.arange(256, dtype=np.uint32) * 0x01010101
+    eng.stream_set_colormap(lut)
+    eng.update_display(flags=fl & ~emspec.FLAG_DETERMINISTIC)
+    xs = x.cpu()
+    for i in range(12):
+        r, _ = eng.stream_push(xs[i * 256:(i + 1) * 256].contiguous(), col)
+    assert r
+    eng.stream_column_rgba(px)
+    assert (px.numpy().view(np.uint32) == lut[col.numpy()]).all()
+    eng.update_display(flags=fl)
+    # after all of that the handle still computes the same image
+    assert torch.equal(eng.process_grid(x, want_grid=False)[1], ref_idx)
+    for e in (eng, fresh, other):
+        e.close()
