@@ -10,7 +10,8 @@ per GPU (clip-sharded, weak scaling, NCCL only for the final gather of per-rank 
                  algorithmic bytes per frame, CUDA events inside the library.
   e2e          : frames/s of ems_process_host — pinned HOST PCM in, u8 colour-index image
                  out to pinned HOST memory (the whole a1-a5 path, copies inside the region).
-  cpu_baseline : the float64 NumPy stand-in oracle (whole a1-a5 path) on the host cores.
+  cpu_baseline : the float64 C stand-in oracle (whole a1-a5 path, oracle/reassign_oracle.c) on every host
+                 thread; the NumPy restatement is timed beside it (cpu_baseline.numpy_oracle).
 
   batch        : configs[3] — 4096 clips x 60 s, n_fft=4096 hop=256, clip-sharded over the ranks
                  (strong scaling: the same 4096 clips at every N), clips fed to the engine as planar
@@ -53,6 +54,13 @@ def frame_count(S, n_fft, hop):
 
 
 # ------------------------------------------------------------------ CPU arm (oracle port)
+def host_cores() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def _cpu_slice(args):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import reassign_oracle as orc
@@ -62,23 +70,40 @@ def _cpu_slice(args):
     return idx.shape[0], int(idx.sum())
 
 
-def cpu_frames_per_s(seconds_audio: float, cores: int, repeats: int = 1, seed: int = 0):
-    """Oracle a1-a5 on `seconds_audio` of the workload signal, frames split over `cores`
-    processes (each slice carries its n_fft - hop halo).  -> (frames/s, frames, wall)."""
-    import multiprocessing as mp
+def _slices(F: int, per: int):
+    """Frame ranges of at most `per` frames; each slice carries its n_fft - hop halo of samples."""
+    return [(f0, min(F, f0 + per)) for f0 in range(0, F, per)]
+
+
+def cpu_frames_per_s(seconds_audio: float, cores: int, repeats: int = 1, seed: int = 0, impl: str = "c"):
+    """Oracle a1-a5 on `seconds_audio` of the workload signal with `cores` host threads.
+    impl "c": oracle/reassign_oracle.c (float64, pthreads), the stream cut into slices of <= 10 s so
+    that the float64 intermediates stay near 0.4 GB and are reused from slice to slice; impl "numpy": oracle/reassign_oracle.py, frames
+    split over one process per core.  -> (frames/s, frames, wall)."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import reassign_oracle as orc
     S = int(seconds_audio * SR)
     x = orc.synth_signal(S, SR, seed=seed)
     F = frame_count(S, N_FFT, HOP)
-    n_slices = max(1, cores)
-    per = (F + n_slices - 1) // n_slices
-    jobs = []
-    for s in range(n_slices):
-        f0, f1 = s * per, min(F, (s + 1) * per)
-        if f1 > f0:
-            jobs.append((x[f0 * HOP:(f1 - 1) * HOP + N_FFT], N_FFT, HOP))
     best = float("inf")
+    if impl == "c":
+        import c_oracle
+        prm = orc.Params(n_fft=N_FFT, hop=HOP)
+        parts = [x[f0 * HOP:(f1 - 1) * HOP + N_FFT] for f0, f1 in _slices(F, frame_count(10 * SR, N_FFT, HOP))]
+        import numpy as np
+        fmax = frame_count(len(parts[0]), N_FFT, HOP)
+        out = (np.empty((fmax, prm.n_rows), np.float64), np.empty((fmax, prm.n_rows), np.uint8))
+        c_oracle.process(parts[0], prm, threads=cores, out=out)      # load the library, touch the buffers
+        for _ in range(repeats):
+            t0 = time.perf_counter()
+            frames = 0
+            for part in parts:
+                _, idx = c_oracle.process(part, prm, threads=cores, out=out)
+                frames += idx.shape[0]
+            best = min(best, time.perf_counter() - t0)
+        return frames / best, frames, best
+    import multiprocessing as mp
+    jobs = [(x[f0 * HOP:(f1 - 1) * HOP + N_FFT], N_FFT, HOP) for f0, f1 in _slices(F, (F + cores - 1) // max(1, cores))]
     ctx = mp.get_context("fork")
     with ctx.Pool(cores) as pool:
         pool.map(_cpu_slice, jobs[:cores])            # warm the workers (imports, FFT plans)
@@ -88,6 +113,10 @@ def cpu_frames_per_s(seconds_audio: float, cores: int, repeats: int = 1, seed: i
             best = min(best, time.perf_counter() - t0)
     frames = sum(r[0] for r in res)
     return frames / best, frames, best
+
+
+CPU_WHAT = {"c": "float64 C stand-in oracle a1-a5 (oracle/reassign_oracle.c, pthreads, one thread per core)",
+            "numpy": "float64 NumPy/SciPy stand-in oracle a1-a5, one process per core"}
 
 
 # ------------------------------------------------------------------ clocks sampler
@@ -317,11 +346,11 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    cores = os.cpu_count() or 1
+    cores = host_cores()
     sample_s = args.cpu_seconds
     vals = []
     for i in range(args.warmup + args.steps):
-        fps, frames, wall = cpu_frames_per_s(sample_s, cores, repeats=1)
+        fps, frames, wall = cpu_frames_per_s(sample_s, cores, repeats=1, impl=args.cpu_impl)
         if i >= args.warmup:
             vals.append((fps, wall))
     fps = statistics.mean(v[0] for v in vals)
@@ -336,7 +365,7 @@ def run_reference(args):
         "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"first {sample_s:g} s of the stream "
                                    f"({frame_count(int(sample_s * SR), N_FFT, HOP)} frames) per step, "
-                                   "float64 NumPy/SciPy stand-in oracle a1-a5, one process per core"},
+                                   + CPU_WHAT[args.cpu_impl]},
         "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "stand-in: EM-Spec ships no runnable source; this is the oracle port",
     }
@@ -685,11 +714,14 @@ def run_ours(args):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        cores = os.cpu_count() or 1
-        fps, frames, wall = cpu_frames_per_s(args.cpu_seconds, cores, repeats=2)
+        cores = host_cores()
+        fps, frames, wall = cpu_frames_per_s(args.cpu_seconds, cores, repeats=2, impl=args.cpu_impl)
         cpu = {"value": fps, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"first {args.cpu_seconds:g} s of the stream ({frames} frames), float64 "
-                         "NumPy/SciPy stand-in oracle a1-a5, one process per core, best of 2"}
+               "sample": f"first {args.cpu_seconds:g} s of the stream ({frames} frames), "
+                         + CPU_WHAT[args.cpu_impl] + ", best of 2"}
+        if args.cpu_impl == "c":                       # the NumPy restatement beside it, on a tenth of the sample
+            nfps, nframes, _ = cpu_frames_per_s(max(2.0, args.cpu_seconds / 10), cores, repeats=1, impl="numpy")
+            cpu["numpy_oracle"] = {"value": nfps, "frames": nframes, "what": CPU_WHAT["numpy"]}
 
     if rank == 0:
         roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -741,7 +773,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--seconds", type=float, default=3600.0, help="stream length per GPU")
-    ap.add_argument("--cpu-seconds", type=float, default=60.0, help="audio seconds of the CPU sample")
+    ap.add_argument("--cpu-seconds", type=float, default=600.0, help="audio seconds of the CPU sample")
+    ap.add_argument("--cpu-impl", choices=("c", "numpy"), default="c",
+                    help="which restatement of the oracle the CPU arm times (default: the C one, all host threads)")
     ap.add_argument("--gate-db", type=float, default=-65.0,
                     help="noise gate; -200 keeps every bin (worst case for the epilogue)")
     ap.add_argument("--no-e2e", action="store_true")

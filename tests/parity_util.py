@@ -23,10 +23,12 @@ def rel_l2(a, b) -> float:
     return float(np.linalg.norm((a - b).ravel()) / den) if den > 0 else float(np.linalg.norm(a.ravel()))
 
 
-def check_points(gpu_pts, x: np.ndarray, prm: orc.Params, p99_tol: float = COORD_TOL):
-    """gpu_pts: (dt, dk, e) numpy arrays [F][B] from the CUDA path for the same float32 x."""
+def check_points(gpu_pts, x: np.ndarray, prm: orc.Params, p99_tol: float = COORD_TOL, ref_points=None):
+    """gpu_pts: (dt, dk, e) numpy arrays [F][B] from the CUDA path for the same float32 x.
+    ref_points: the oracle's (dt, dk, e, raw) when the caller already has them (e.g. from the C
+    restatement on a long stream); by default the NumPy oracle is run here."""
     dt_g, dk_g, e_g = (np.asarray(a, np.float64) for a in gpu_pts)
-    dt_o, dk_o, e_o, raw = orc.reassign_points(x, prm, return_raw=True)
+    dt_o, dk_o, e_o, raw = ref_points if ref_points is not None else orc.reassign_points(x, prm, return_raw=True)
     assert dt_g.shape == dt_o.shape, (dt_g.shape, dt_o.shape)
     assert np.isfinite(dt_g).all() and np.isfinite(dk_g).all() and np.isfinite(e_g).all()
     both = (e_g > 0) & (e_o > 0)

@@ -989,3 +989,26 @@ def test_error_behaviour_with_a_live_handle(emspec):
     assert torch.equal(eng.process_grid(x, want_grid=False)[1], ref_idx)
     for e in (eng, fresh, other):
         e.close()
+
+
+@pytest.mark.parametrize("n_fft,hop,secs,music", [(4096, 128, 30, False), (4096, 128, 10, True), (8192, 256, 20, False),
+                                                   (1024, 64, 10, True)])
+def test_points_vs_c_oracle_long(emspec, n_fft, hop, secs, music):
+    """Parity at sizes the NumPy oracle is too slow for: tens of seconds of audio (up to 11 k frames,
+    23 M points) against the multi-threaded C restatement of the oracle (oracle/reassign_oracle.c, which
+    tests/test_c_oracle.py pins to the NumPy one), with the same banded tolerances as the short cases."""
+    import c_oracle as co
+    x = orc.synth_music(secs * SR, SR, seed=secs) if music else orc.synth_signal(secs * SR, SR, seed=secs)
+    prm = orc.Params(n_fft=n_fft, hop=hop)
+    ref = co.reassign_points(x, prm, return_raw=True)
+    stats = check_points(run_points(emspec, x, prm), x, prm, ref_points=ref)
+    assert stats["n_valid"] > 1000 * secs
+    # and the image of the same stream: C oracle grid / index vs the GPU
+    grid_o = co.scatter_grid(*ref[:3], prm)
+    g, i = run_grid(emspec, x, prm)
+    if music:
+        from parity_util import check_grid_dense
+        check_grid_dense(g, x, prm)
+    else:
+        assert rel_l2(g, grid_o) <= 1e-4
+        check_index(i, grid_o, prm, x)
