@@ -37,6 +37,11 @@
 #include <type_traits>
 #include <utility>
 
+#ifndef EMS_LARGE_PREFETCH
+#define EMS_LARGE_PREFETCH 1    // samples and pass-A twiddles of a worker's NEXT frame are fetched with cp.async during the epilogue, into
+                                // the Z slots the fetching warp itself overwrites in pass A.  1: n_fft = 16384 only (one worker per SM: +6.5 %);
+                                // 2: 8192 too (two workers already hide each other's loads: -1..-4 %); 0: off
+#endif
 #ifndef EMS_LARGE_R32
 #define EMS_LARGE_R32 0         // experiment, n_fft = 8192: pass 1 as one radix-32 butterfly per thread (one exchange and one
                                 // barrier fewer than 2 x 16): correct, 30.9 against 33.2 M frames/s (32 loads and 64 live
@@ -1074,7 +1079,38 @@ stft_reassign_r16_large(const StftArgs a_in) {
 
     const long long per_ch = a.f_end - a.f_begin;
     const long long total = per_ch * a.channels;
-    for (long long it = blockIdx.x + (long long)gridDim.x * w; it < total; it += (long long)gridDim.x * kWorkers) {
+    constexpr bool kPF = (EMS_LARGE_PREFETCH == 2 || (EMS_LARGE_PREFETCH == 1 && R0 == 4)) && !kR32;
+    // Prefetch (kPF): the warp that owns butterflies b0..b0+31 of step u owns the 32 consecutive Z slots of rows
+    // R0 (b0 >> 8) + j, j < R0 (256 bytes each), and is the only one to write them in pass A.  The next frame's
+    // samples (4 bytes per lane and j, packed: two j per row block) and W_N^b (8 bytes per lane, row block R0/2)
+    // are copied there while the epilogue runs; every lane reads back what it copied, and after a __syncwarp
+    // the butterflies overwrite the block.  No barrier is added and pass A no longer waits on L2.
+    const int lane = p & 31;
+    auto stage = [&](int u) -> float* {
+        const int b0 = (p & ~31) + kWT * u;
+        return reinterpret_cast<float*>(Zb + kSI * (R0 * (b0 >> 8)) + (b0 & 255));
+    };
+    auto frame_ptr = [&](long long it) -> const float* {
+        const int ch = (int)(it / per_ch);
+        const long long f = a.f_begin + (it - (long long)ch * per_ch);
+        return a.pcm + (long long)ch * a.S + f * a.hop + a.samp_off;
+    };
+    auto prefetch = [&](const float* xs) {
+#pragma unroll
+        for (int u = 0; u < kUA; ++u) {
+            const unsigned sb = (unsigned)__cvta_generic_to_shared(stage(u));
+#pragma unroll
+            for (int j = 0; j < R0; ++j)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sb + 4u * (2 * kSI * (j >> 1) + lane + 32 * (j & 1))),
+                             "l"(xs + p + kWT * u + 4096 * j) : "memory");
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sb + 4u * (2 * kSI * (R0 / 2) + 2 * lane)),
+                         "l"(a.tw + p + kWT * u) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    const long long it0 = blockIdx.x + (long long)gridDim.x * w, it_step = (long long)gridDim.x * kWorkers;
+    if constexpr (kPF) { if (it0 < total) prefetch(frame_ptr(it0)); }
+    for (long long it = it0; it < total; it += it_step) {
         const int ch = (int)(it / per_ch);
         const long long f = a.f_begin + (it - (long long)ch * per_ch);
         const float* xs = a.pcm + (long long)ch * a.S + f * a.hop + a.samp_off;
@@ -1128,11 +1164,23 @@ stft_reassign_r16_large(const StftArgs a_in) {
         {
             float xr[kUA][R0];
             float2 w1s[kUA];                                   // W_N^b = (cos, -sin)(2 pi b / N)
+            if constexpr (kPF) {
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+#pragma unroll
+                for (int u = 0; u < kUA; ++u) {
+                    const float* sb = stage(u);
+#pragma unroll
+                    for (int j = 0; j < R0; ++j) xr[u][j] = sb[2 * kSI * (j >> 1) + lane + 32 * (j & 1)];
+                    w1s[u] = *reinterpret_cast<const float2*>(sb + 2 * kSI * (R0 / 2) + 2 * lane);
+                }
+                __syncwarp();                                  // every lane has its values before the block is overwritten
+            } else {
 #pragma unroll
             for (int u = 0; u < kUA; ++u) {
 #pragma unroll
                 for (int j = 0; j < R0; ++j) xr[u][j] = __ldg(xs + p + kWT * u + 4096 * j);
                 w1s[u] = __ldg(&a.tw[p + kWT * u]);
+            }
             }
             static_for<kUA>([&](auto uc) {
                 constexpr int u = decltype(uc)::value;
@@ -1186,7 +1234,8 @@ stft_reassign_r16_large(const StftArgs a_in) {
 
         float2 xa[8], xb[8], ta[8], tb[8];
         pass3_untangle<R>(Zb, Xs, Sc, g, xa, xb, ta, tb);
-        worker_bar<kWT>(w);
+        worker_bar<kWT>(w);      // X visible; nobody reads Z any more
+        if constexpr (kPF) { if (it + it_step < total) prefetch(frame_ptr(it + it_step)); }
 
         epilogue<R, MODE>(a, ch, f, Xs, Sc, g, xa, xb, ta, tb);
     }
