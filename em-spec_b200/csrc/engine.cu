@@ -18,6 +18,7 @@
 #include "stft_generic.cuh"
 #include "stft_r16.cuh"
 #include "stft_r64.cuh"
+#include "stft_r32.cuh"
 #include "stream.cuh"
 
 namespace ems {
@@ -317,6 +318,24 @@ static ems_status launch_r16_large(ems_handle* h, const StftArgs& a) {
     return EMS_OK;
 }
 
+// Experiment (EMS_KERNEL_VARIANT=32): n_fft = 8192 with three workers of 128 threads, radix-32 first pass, X in place.
+static ems_status launch_8192_w3(ems_handle* h, const StftArgs& a) {
+    using C = r16::Cfg8kW3;
+    void (*kern)(const StftArgs) =
+        a.mode == kStorePoints ? r16::stft_reassign_8192_w3<kStorePoints>
+        : a.mode == kDepositU64 ? r16::stft_reassign_8192_w3<kDepositU64>
+                                : r16::stft_reassign_8192_w3<kDepositF32>;
+    EMS_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+    const long long total = (a.f_end - a.f_begin) * a.channels;
+    long long grid = h->max_ctas > 0 ? std::min(h->max_ctas, h->sm_count) : h->sm_count;
+    if (grid > total) grid = total;
+    if (grid < 1) return EMS_OK;
+    kern<<<(unsigned)grid, C::kThreads, C::kSmemBytes, h->stream>>>(a);
+    ++h->launches;
+    EMS_CUDA(h, cudaGetLastError());
+    return EMS_OK;
+}
+
 // n_fft = 32768: two sequential 16384-point complex FFTs per frame, 2 X parked in an L2-resident scratch.
 static ems_status launch_r16_32k(ems_handle* h, const StftArgs& a) {
     using C = r16::CfgL<4>;
@@ -350,7 +369,7 @@ static ems_status launch_stft(ems_handle* h, const StftArgs& a) {
             case 1024: s = launch_r16<4>(h, a); break;
             case 2048: s = launch_r16<8>(h, a); break;
             case 4096: s = h->kernel_variant == 64 ? launch_r64(h, a) : launch_r16<16>(h, a); break;
-            case 8192: s = launch_r16_large<2>(h, a); break;
+            case 8192: s = h->kernel_variant == 32 ? launch_8192_w3(h, a) : launch_r16_large<2>(h, a); break;
             case 16384: s = launch_r16_large<4>(h, a); break;
             case 32768: s = launch_r16_32k(h, a); break;
             default: break;

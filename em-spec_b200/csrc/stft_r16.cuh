@@ -414,6 +414,12 @@ struct Geom {
     int i1, q2;         // pass-2 butterflies (i1, q2) and (i1, q2 + 8)
     float tAf, tBf;
 };
+// X in place (XZ): start of the Z row that holds the pass-3 inputs, and afterwards 2 X[t + 16 R c] at slot c, of residue t
+template <int R>
+__host__ __device__ constexpr int zrow_xz(int t) {
+    static_assert(R >= 16, "classic 257 / 16 strides");
+    return 257 * (t & (R - 1)) + 16 * (t / R);
+}
 template <int R, int kSI, int kS16>
 __device__ __forceinline__ Geom make_geom(int p) {
     constexpr int kRes = 16 * R;
@@ -551,11 +557,10 @@ __device__ __forceinline__ void epilogue(const StftArgs& a, int ch, long long f,
     // neighbour is residue 255 one c down, residue 255's upper neighbour is residue 0 one c up)
     const float2* nAm = Xs; const float2* nAp = Xs; const float2* nBm = Xs; const float2* nBp = Xs;
     if constexpr (XZ) {
-        using C = Cfg<R>;
-        nAm = Xs + (g.tA ? C::zrow(g.tA - 1) : C::zrow(kRes - 1) - 1);
-        nAp = Xs + C::zrow(g.tA + 1);
-        nBm = Xs + C::zrow(g.tB - 1);
-        nBp = Xs + (g.tB < kRes - 1 ? C::zrow(g.tB + 1) : C::zrow(0) + 1);
+        nAm = Xs + (g.tA ? zrow_xz<R>(g.tA - 1) : zrow_xz<R>(kRes - 1) - 1);
+        nAp = Xs + zrow_xz<R>(g.tA + 1);
+        nBm = Xs + zrow_xz<R>(g.tB - 1);
+        nBp = Xs + (g.tB < kRes - 1 ? zrow_xz<R>(g.tB + 1) : zrow_xz<R>(0) + 1);
     }
     const bool owner = active;
     FrameCtx fc;
@@ -643,8 +648,8 @@ __device__ __forceinline__ void epilogue(const StftArgs& a, int ch, long long f,
     // bin N/2, the ninth of residue 0: thread 0 of the frame (its warp tags along)
     if (kWT < 32 || g.p < 32) {
         if constexpr (XZ)
-            bin_emit<N, MODE>(a, fc, owner && g.p == 0, N / 2, (float)(N / 2), Xs[Cfg<R>::zrow(0) + 8],
-                              Xs[Cfg<R>::zrow(kRes - 1) + 7], Sc[3], Sc[0]);
+            bin_emit<N, MODE>(a, fc, owner && g.p == 0, N / 2, (float)(N / 2), Xs[zrow_xz<R>(0) + 8],
+                              Xs[zrow_xz<R>(kRes - 1) + 7], Sc[3], Sc[0]);
         else
             bin_emit<N, MODE>(a, fc, owner && g.p == 0, N / 2, (float)(N / 2), Xs[N / 2 + 1], Xs[N / 2], Xs[N / 2 + 2], Sc[0]);
     }
