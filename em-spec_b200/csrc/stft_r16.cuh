@@ -65,7 +65,9 @@ namespace r16 {
 
 constexpr int kMaxSmem = 232448;       // 227 KB
 constexpr int kSyncBytes = 192;        // 2 mbarriers, 2 release counters, kWorkers refill flags; fused mode: 4 finish counters, kWorkers go flags
-constexpr int kT2 = 16 * 16;           // W_256^{p2 i} as [p2][i]: a butterfly's 16 twiddles are contiguous
+constexpr int kT2S = 18;               // row stride of T2: 144 bytes, so that the 8 rows a quarter-warp of the narrow kernels
+                                       // (n_fft <= 1024: up to 8 different p2 among 8 lanes) reads with one LDS.128 sit on different banks
+constexpr int kT2 = 16 * kT2S;         // W_256^{p2 i} as [p2][i]: a butterfly's 16 twiddles are contiguous
 constexpr int kScratch = 20;           // 2 X_th' of bin N/2 (and padding: the slot size stays 8 mod 16)
 constexpr int kThreads = 384;
 
@@ -483,7 +485,7 @@ __device__ __forceinline__ void pass2(float2* Zb, const float2* T2, const Geom& 
     // warp reads two addresses: one wavefront per load); loaded before the butterfly they belong
     // to, so that their latency hides behind its arithmetic
     auto twiddle_load = [&](float4 (&t)[8], int p2) {
-        const float4* t4 = reinterpret_cast<const float4*>(T2 + 16 * p2);
+        const float4* t4 = reinterpret_cast<const float4*>(T2 + kT2S * p2);
 #pragma unroll
         for (int h = 0; h < 8; ++h) t[h] = t4[h];
     };
@@ -781,7 +783,7 @@ stft_reassign_r16(const StftArgs a_in, const int tile_T) {
 
     // ---- twiddle tables (once per CTA)
     for (int e = tid; e < kZtab; e += kThreads) { const int i = 1 << (e / 256), b = e % 256; Ztab[e] = __ldg(&a.tw[b * i]); }
-    for (int e = tid; e < kT2; e += kThreads) { const int q = e / 16, i = e % 16; T2[e] = __ldg(&a.tw[R * q * i]); }
+    for (int e = tid; e < 256; e += kThreads) { const int q = e / 16, i = e % 16; T2[kT2S * q + i] = __ldg(&a.tw[R * q * i]); }
 
     // ---- per-thread constants
     // th'[n] at this thread's 32 pass-1 samples n = p + kWT u + 256 j: frame-independent, so they
@@ -1071,7 +1073,7 @@ stft_reassign_r16_large(const StftArgs a_in) {
     float2* Sc = Xs + kXBuf;
 
     for (int e = tid; e < kZtab; e += kThreads) { const int i = 1 << (e / 256), b = e % 256; Ztab[e] = __ldg(&a.tw[R0 * b * i]); }
-    for (int e = tid; e < kT2; e += kThreads) { const int q = e / 16, i = e % 16; T2[e] = __ldg(&a.tw[R * q * i]); }
+    for (int e = tid; e < 256; e += kThreads) { const int q = e / 16, i = e % 16; T2[kT2S * q + i] = __ldg(&a.tw[R * q * i]); }
     __syncthreads();
     const Geom g = make_geom<R, kSI, kS16>(p);
     constexpr bool kR32 = R0 == 2 && EMS_LARGE_R32;
@@ -1276,7 +1278,7 @@ stft_reassign_r16_32k(const StftArgs a_in, float2* __restrict__ scratch_all) {
 
     const int tid = threadIdx.x, p = tid;
     for (int e = tid; e < kZtab; e += kThreads) { const int i = 1 << (e / 256), b = e % 256; Ztab[e] = __ldg(&a.tw[8 * b * i]); }
-    for (int e = tid; e < kT2; e += kThreads) { const int q = e / 16, i = e % 16; T2[e] = __ldg(&a.tw[128 * q * i]); }
+    for (int e = tid; e < 256; e += kThreads) { const int q = e / 16, i = e % 16; T2[kT2S * q + i] = __ldg(&a.tw[128 * q * i]); }
     __syncthreads();
     const Geom g = make_geom<R, kSI, kS16>(p);
     const int tA = g.tA, tB = g.tB;

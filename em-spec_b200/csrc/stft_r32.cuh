@@ -99,7 +99,7 @@ stft_reassign_8192_w3(const StftArgs a_in) {
     const int p = (tid + 32 * w) & (kWT - 1);                   // warp roles rotate across the workers
     float2* Zb = Ztab + C::kZtab + w * C::kSlot;
     float2* Sc = Zb + C::kZBuf;
-    for (int e = tid; e < kT2; e += kThreads) { const int q = e / 16, i = e % 16; T2[e] = __ldg(&a.tw[R * q * i]); }
+    for (int e = tid; e < 256; e += kThreads) { const int q = e / 16, i = e % 16; T2[kT2S * q + i] = __ldg(&a.tw[R * q * i]); }
     for (int e = tid; e < C::kZtab; e += kThreads) { const int l = e / 256, b = e % 256; Ztab[e] = __ldg(&a.tw[(b << l) & (C::N - 1)]); }
     __syncthreads();
     const Geom g0 = make_geom<R, kSI, kS16>(p), g1 = make_geom<R, kSI, kS16>(p + kWT);
