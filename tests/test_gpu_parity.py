@@ -1012,3 +1012,22 @@ def test_points_vs_c_oracle_long(emspec, n_fft, hop, secs, music):
     else:
         assert rel_l2(g, grid_o) <= 1e-4
         check_index(i, grid_o, prm, x)
+
+
+@pytest.mark.parametrize("variant,n_fft,hop", [(64, 4096, 128), (64, 4096, 333), (32, 8192, 2048), (32, 8192, 256), (32, 8192, 1000)])
+def test_experimental_kernel_variants_keep_parity(emspec, monkeypatch, variant, n_fft, hop):
+    """The kernels kept in the tree as measured experiments (EMS_KERNEL_VARIANT=64: single-exchange 64 x 64 at
+    n_fft 4096; =32: three workers, radix-32 first pass, X in place at 8192 — DESIGN.md §4.8) meet the same
+    tolerances as the default kernels, points and image, on the sparse and on the music-like signal."""
+    monkeypatch.setenv("EMS_KERNEL_VARIANT", str(variant))
+    for music in (False, True):
+        x = orc.synth_music(2 * SR, SR, seed=variant) if music else orc.synth_signal(2 * SR, SR, seed=variant)
+        prm = orc.Params(n_fft=n_fft, hop=hop)
+        stats = check_points(run_points(emspec, x, prm), x, prm)
+        assert stats["n_valid"] > 0
+        g, i = run_grid(emspec, x, prm)
+        if music:
+            check_grid_dense(g, x, prm)
+        else:
+            _, grid_o, _ = check_grid(g, x, prm)
+            check_index(i, grid_o, prm, x)
