@@ -73,7 +73,7 @@ struct ems_handle {
         uint32_t* rgba_dev = nullptr;
         bool last_ready = false;         // the last push delivered a column
         int M = 0, Lr = 0, R = 0, ring_cols = 0;
-        int in_i16 = 0;                  // format of the hop the captured graph reads (0: fp32, 1: int16)
+        int in_i16 = 0;                  // format of the hop the captured graph reads (0: fp32, 1: int16, 2: packed int24)
         long long pushes = 0;            // host mirror of the device counter
         size_t acc_bytes = 0;
     } st;
@@ -1256,7 +1256,7 @@ static ems_status stream_push_impl(ems_handle* h, const void* pcm_host, int is_i
     st.in_i16 = is_i16;
     if (!st.graph && (s = stream_capture(h)) != EMS_OK) return s;
     const int H = h->prm.hop, C = h->prm.channels, B = rows_of(h->prm);
-    memcpy(st.in_pin, pcm_host, (is_i16 ? sizeof(int16_t) : sizeof(float)) * H * C);
+    memcpy(st.in_pin, pcm_host, (is_i16 == 2 ? 3 : is_i16 ? sizeof(int16_t) : sizeof(float)) * (size_t)H * C);
     EMS_CUDA(h, cudaGraphLaunch(st.graph, h->stream));
     h->launches += 3;
     EMS_CUDA(h, cudaStreamSynchronize(h->stream));
@@ -1267,6 +1267,11 @@ static ems_status stream_push_impl(ems_handle* h, const void* pcm_host, int is_i
     if (column_index) *column_index = cf;
     if (cf >= 0) memcpy(column_host, st.out_pin, (size_t)C * B);
     return EMS_OK;
+}
+
+ems_status ems_stream_push_i24(ems_handle* h, const uint8_t* pcm_host, uint8_t* column_host,
+                               int* column_ready, int64_t* column_index) {
+    return stream_push_impl(h, pcm_host, 2, column_host, column_ready, column_index);
 }
 
 ems_status ems_stream_set_colormap(ems_handle* h, const uint32_t* lut_rgba_host) {

@@ -21,7 +21,7 @@ struct StreamArgs {
     float*       agc;        // [2][channels]: (unused), running level
     int hop, channels, M, Lr, R, ring_cols, B, acc_is_u64;
     float smoothing, db_floor, inv_range, gate_db, agc_strength, agc_lambda, agc_target;
-    int in_i16;              // the hop is int16 (full scale 32768) instead of fp32
+    int in_i16;              // format of the hop: 0 fp32, 1 int16 (full scale 32768), 2 packed little-endian int24 (full scale 2^23)
     const uint32_t* lut;     // [256] RGBA colour map (ems_stream_set_colormap), or null
     uint32_t*    out_rgba;   // [channels][B] pixels of the final column (mapped pinned host memory)
 };
@@ -34,7 +34,13 @@ __global__ void stream_ingest_kernel(const StreamArgs s) {
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < s.hop * s.channels;
          e += gridDim.x * blockDim.x) {
         const int smp = e / s.channels, ch = e - smp * s.channels;
-        const float v = s.in_i16 ? (float)reinterpret_cast<const int16_t*>(s.in)[e] * (1.0f / 32768.0f) : s.in[e];
+        float v;
+        if (s.in_i16 == 2) {
+            const unsigned char* b = reinterpret_cast<const unsigned char*>(s.in) + 3 * e;
+            v = (float)((int)(((uint32_t)b[0] | ((uint32_t)b[1] << 8) | ((uint32_t)b[2] << 16)) << 8) >> 8) * (1.0f / 8388608.0f);
+        } else {
+            v = s.in_i16 ? (float)reinterpret_cast<const int16_t*>(s.in)[e] * (1.0f / 32768.0f) : s.in[e];
+        }
         float* r = s.ring + (long long)ch * 2 * s.Lr + wp + smp;
         r[0] = v;
         r[s.Lr] = v;

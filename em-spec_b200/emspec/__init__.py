@@ -69,6 +69,7 @@ _SIG = {
     "ems_launch_count": (C.c_int, [_VP, C.POINTER(C.c_uint64)]),
     "ems_stream_push": (C.c_int, [_VP, _FP, _U8P, C.POINTER(C.c_int), C.POINTER(C.c_int64)]),
     "ems_stream_push_i16": (C.c_int, [_VP, _VP, _U8P, C.POINTER(C.c_int), C.POINTER(C.c_int64)]),
+    "ems_stream_push_i24": (C.c_int, [_VP, _VP, _U8P, C.POINTER(C.c_int), C.POINTER(C.c_int64)]),
     "ems_stream_set_colormap": (C.c_int, [_VP, _VP]),
     "ems_stream_column_rgba": (C.c_int, [_VP, _VP]),
     "ems_stream_reset": (C.c_int, [_VP]),
@@ -344,10 +345,12 @@ class Engine:
         return rgba_host
 
     def stream_push(self, pcm_host, column_host):
-        """pcm_host: CPU fp32 (or int16, capture format) [hop*channels] interleaved; column_host: CPU u8 [channels][n_rows].
-        -> (ready: bool, column_index: int)"""
+        """pcm_host: CPU fp32, int16 or uint8 (packed int24: 3 bytes per sample) [hop*channels] interleaved, capture
+        formats; column_host: CPU u8 [channels][n_rows].  -> (ready: bool, column_index: int)"""
         import torch
         ready, idx = C.c_int(0), C.c_int64(-1)
-        fn = self.lib.ems_stream_push_i16 if pcm_host.dtype == torch.int16 else self.lib.ems_stream_push
+        fn = {torch.int16: self.lib.ems_stream_push_i16, torch.uint8: self.lib.ems_stream_push_i24}.get(pcm_host.dtype, self.lib.ems_stream_push)
+        if pcm_host.dtype == torch.uint8:
+            assert pcm_host.numel() == 3 * self.params.hop * self.params.channels
         self._check(fn(self.h, _ptr(pcm_host), _ptr(column_host), C.byref(ready), C.byref(idx)))
         return bool(ready.value), idx.value

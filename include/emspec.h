@@ -200,6 +200,10 @@ ems_status ems_stream_push(ems_handle* h, const float* pcm_host, uint8_t* column
  * 32768.  A stream may switch formats between pushes. */
 ems_status ems_stream_push_i16(ems_handle* h, const int16_t* pcm_host, uint8_t* column_host,
                                int* column_ready, int64_t* column_index);
+/* ... or packed little-endian int24, three bytes per sample, interleaved [hop][channels], full scale 2^23
+ * (as ems_process_host_i24). */
+ems_status ems_stream_push_i24(ems_handle* h, const uint8_t* pcm_host, uint8_t* column_host,
+                               int* column_ready, int64_t* column_index);
 /* Colour map on the streaming path ("ready-to-blit columns for a scrolling
  * renderer", /root/reference/README.md:15,45).  lut_rgba_host: 256 packed pixels as in
  * ems_colorize, copied; NULL switches the map off.  While a map is set the kernel that finishes a

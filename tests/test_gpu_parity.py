@@ -1031,3 +1031,36 @@ def test_experimental_kernel_variants_keep_parity(emspec, monkeypatch, variant, 
         else:
             _, grid_o, _ = check_grid(g, x, prm)
             check_index(i, grid_o, prm, x)
+
+
+def test_stream_push_int24(emspec):
+    """The capture-side push also takes packed little-endian int24 hops (three bytes per sample, interleaved,
+    full scale 2^23): columns equal the fp32 pushes of the same quantised samples, stereo, and the three
+    formats may alternate within one stream."""
+    hop, n_fft, ch = 256, 2048, 2
+    x = np.stack([orc.synth_signal(SR // 2, SR, seed=61), orc.synth_music(SR // 2, SR, seed=62)], 1)
+    q24 = np.clip(np.rint(x.astype(np.float64) * 8388608.0), -8388608, 8388607).astype(np.int32)
+    xf = (q24.astype(np.float64) / 8388608.0).astype(np.float32)            # exact: 24 bits fit the fp32 mantissa
+    packed = np.stack([(q24 & 0xFF), ((q24 >> 8) & 0xFF), ((q24 >> 16) & 0xFF)], -1).astype(np.uint8)   # [S][ch][3]
+    q16 = np.clip(np.rint(x.astype(np.float64) * 32768.0), -32768, 32767).astype(np.int16)
+    a = emspec.Engine(n_fft=n_fft, hop=hop, channels=ch)
+    b = emspec.Engine(n_fft=n_fft, hop=hop, channels=ch)
+    ca = torch.empty((ch, n_fft // 2 + 1), dtype=torch.uint8).pin_memory()
+    cb = torch.empty((ch, n_fft // 2 + 1), dtype=torch.uint8).pin_memory()
+    n = 0
+    for i in range(len(x) // hop):
+        sl = slice(i * hop, (i + 1) * hop)
+        kind = (i // 7) % 3                    # int24, fp32 of the same samples, int16 (its own quantisation: fed to both)
+        if kind == 2:
+            src_a = src_b = torch.from_numpy(q16[sl].reshape(-1)).contiguous()
+        else:
+            src_a = torch.from_numpy(xf[sl].reshape(-1)).contiguous()
+            src_b = torch.from_numpy(packed[sl].reshape(-1)).contiguous() if kind == 0 else src_a
+        ra, ia = a.stream_push(src_a, ca)
+        rb, ib = b.stream_push(src_b, cb)
+        assert (ra, ia) == (rb, ib)
+        if ra:
+            assert (ca.numpy() == cb.numpy()).all(), i
+            n += 1
+    assert n > 50
+    a.close(); b.close()
