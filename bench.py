@@ -115,6 +115,21 @@ def cpu_frames_per_s(seconds_audio: float, cores: int, repeats: int = 1, seed: i
     return frames / best, frames, best
 
 
+def cpu_impl_available(impl: str) -> str:
+    """The C restatement needs its shared library (prebuilt in oracle/_build/, else gcc): fall back to the NumPy one
+    rather than lose the CPU arm."""
+    if impl != "c":
+        return impl
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import c_oracle
+        c_oracle.load()
+        return "c"
+    except Exception as e:                                   # noqa: BLE001
+        print(f"bench: C oracle unavailable ({e}); timing the NumPy oracle instead", file=sys.stderr)
+        return "numpy"
+
+
 CPU_WHAT = {"c": "float64 C stand-in oracle a1-a5 (oracle/reassign_oracle.c, pthreads, one thread per core)",
             "numpy": "float64 NumPy/SciPy stand-in oracle a1-a5, one process per core"}
 
@@ -347,6 +362,7 @@ def run_reference(args):
     if rank != 0:
         return 0
     cores = host_cores()
+    args.cpu_impl = cpu_impl_available(args.cpu_impl)
     sample_s = args.cpu_seconds
     vals = []
     for i in range(args.warmup + args.steps):
@@ -715,6 +731,7 @@ def run_ours(args):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cores = host_cores()
+        args.cpu_impl = cpu_impl_available(args.cpu_impl)
         fps, frames, wall = cpu_frames_per_s(args.cpu_seconds, cores, repeats=2, impl=args.cpu_impl)
         cpu = {"value": fps, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": f"first {args.cpu_seconds:g} s of the stream ({frames} frames), "
