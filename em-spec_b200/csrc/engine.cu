@@ -873,6 +873,73 @@ ems_status ems_frame_count(const ems_handle* h, size_t S, size_t* F) {
     return EMS_OK;
 }
 
+// Frequency [Hz] of a (fractional) output row: the inverse of out_row (common.cuh) / upload_display's
+// row centres.
+static double row_to_hz(const ems_params& p, double row) {
+    const int R = rows_of(p);
+    row = std::min(std::max(row, 0.0), (double)(R - 1));
+    if (p.display_rows <= 0) return row * (double)p.sample_rate / (double)p.n_fft;
+    const double nyq = 0.5 * (double)p.sample_rate, a = warp_a_of(p);
+    const double u = R > 1 ? row / (double)(R - 1) : 0.0;
+    return nyq * (a > 1e-6 ? std::expm1(u * std::log1p(a)) / a : u);
+}
+
+// "note and frequency information" under the cursor (/root/reference/README.md:39).
+ems_status ems_cursor_info(const ems_handle* h, double column, double row, ems_cursor* out) {
+    if (!h || !out || !(column == column) || !(row == row)) return EMS_ERR_INVALID_ARG;
+    static const char* const kNames[12] = {"C", "C#", "D", "D#", "E", "F", "F#", "G", "G#", "A", "A#", "B"};
+    const ems_params& p = h->prm;
+    std::memset(out, 0, sizeof(*out));
+    out->time_s = (column * (double)p.hop + 0.5 * (double)p.n_fft) / (double)p.sample_rate;
+    out->freq_hz = row_to_hz(p, row);
+    out->midi_note = -1;
+    if (out->freq_hz >= 1.0) {
+        const double pitch = 69.0 + 12.0 * std::log2(out->freq_hz / 440.0);
+        const double note = std::floor(pitch + 0.5);
+        out->midi_note = (int32_t)note;
+        out->cents = (float)(100.0 * (pitch - note));
+        const int pc = ((out->midi_note % 12) + 12) % 12;
+        const int octave = (out->midi_note - pc) / 12 - 1;
+        std::snprintf(out->name, sizeof(out->name), "%s%d", kNames[pc], octave);
+    }
+    return EMS_OK;
+}
+
+// Built-in colour maps ("Multiple Color Maps", /root/reference/README.md:15,45): stand-in tables,
+// piecewise linear through 8-bit control colours in integer arithmetic (oracle: builtin_colormap).
+namespace {
+struct ColourStop { int pos; int r, g, b; };
+struct ColourMap { const char* name; int n; ColourStop stop[5]; };
+const ColourMap kColourMaps[] = {
+    {"gray",    2, {{0, 0, 0, 0}, {255, 255, 255, 255}}},
+    {"heat",    4, {{0, 0, 0, 0}, {85, 200, 0, 0}, {170, 255, 200, 0}, {255, 255, 255, 255}}},
+    {"magma",   5, {{0, 0, 0, 4}, {64, 81, 18, 124}, {128, 183, 55, 121}, {192, 252, 137, 97}, {255, 252, 253, 191}}},
+    {"viridis", 5, {{0, 68, 1, 84}, {64, 59, 82, 139}, {128, 33, 145, 140}, {192, 94, 201, 98}, {255, 253, 231, 37}}},
+    {"ice",     4, {{0, 0, 0, 0}, {96, 0, 60, 160}, {192, 80, 200, 255}, {255, 255, 255, 255}}},
+};
+constexpr int kColourMapCount = (int)(sizeof(kColourMaps) / sizeof(kColourMaps[0]));
+}  // namespace
+
+int ems_colormap_count(void) { return kColourMapCount; }
+const char* ems_colormap_name(int id) { return id >= 0 && id < kColourMapCount ? kColourMaps[id].name : nullptr; }
+
+ems_status ems_colormap_builtin(int id, uint32_t lut[256]) {
+    if (!lut || id < 0 || id >= kColourMapCount) return EMS_ERR_INVALID_ARG;
+    const ColourMap& m = kColourMaps[id];
+    for (int s = 0; s + 1 < m.n; ++s) {
+        const ColourStop &a = m.stop[s], &b = m.stop[s + 1];
+        const int d = b.pos - a.pos;
+        for (int i = a.pos; i <= b.pos; ++i) {
+            const int t = i - a.pos;
+            const uint32_t r = (uint32_t)((a.r * (d - t) + b.r * t + d / 2) / d);
+            const uint32_t g = (uint32_t)((a.g * (d - t) + b.g * t + d / 2) / d);
+            const uint32_t bl = (uint32_t)((a.b * (d - t) + b.b * t + d / 2) / d);
+            lut[i] = 0xFF000000u | (bl << 16) | (g << 8) | r;
+        }
+    }
+    return EMS_OK;
+}
+
 ems_status ems_process_points(ems_handle* h, const float* pcm, size_t S, float* dt_cols,
                               float* dk_bins, float* energy, size_t* n_frames) {
     if (!h) return EMS_ERR_INVALID_ARG;

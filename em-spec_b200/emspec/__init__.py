@@ -41,6 +41,12 @@ class Params(C.Structure):
     ]
 
 
+class Cursor(C.Structure):
+    """ems_cursor (include/emspec.h): what lies under an output cell."""
+    _fields_ = [("time_s", C.c_double), ("freq_hz", C.c_double), ("midi_note", C.c_int32),
+                ("cents", C.c_float), ("name", C.c_char * 8)]
+
+
 # name -> (restype, argtypes); every symbol include/emspec.h declares.
 _VP, _FP, _U8P = C.c_void_p, C.c_void_p, C.c_void_p
 _SIG = {
@@ -56,6 +62,10 @@ _SIG = {
     "ems_synchronize": (C.c_int, [_VP]),
     "ems_output_rows": (C.c_int, [_VP, C.POINTER(C.c_size_t)]),
     "ems_frame_count": (C.c_int, [_VP, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "ems_cursor_info": (C.c_int, [_VP, C.c_double, C.c_double, C.POINTER(Cursor)]),
+    "ems_colormap_count": (C.c_int, []),
+    "ems_colormap_name": (C.c_char_p, [C.c_int]),
+    "ems_colormap_builtin": (C.c_int, [C.c_int, _VP]),
     "ems_process_points": (C.c_int, [_VP, _FP, C.c_size_t, _FP, _FP, _FP, C.POINTER(C.c_size_t)]),
     "ems_process_grid": (C.c_int, [_VP, _FP, C.c_size_t, _FP, _U8P, C.POINTER(C.c_size_t)]),
     "ems_scatter_points": (C.c_int, [_VP, _FP, _FP, _FP, C.c_size_t, _FP, _U8P]),
@@ -108,6 +118,24 @@ def _ptr(t):
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
+def colormap_names() -> list:
+    """Names of the built-in colour maps, by id."""
+    lib = load()
+    return [lib.ems_colormap_name(i).decode() for i in range(lib.ems_colormap_count())]
+
+
+def builtin_colormap(which):
+    """256 uint32 pixels (0xAABBGGRR) of a built-in colour map, by id or name."""
+    import numpy as np
+    lib = load()
+    idx = colormap_names().index(which) if isinstance(which, str) else int(which)
+    lut = np.zeros(256, np.uint32)
+    st = lib.ems_colormap_builtin(idx, C.c_void_p(lut.ctypes.data))
+    if st != OK:
+        raise EmspecError(st, lib.ems_status_str(st).decode())
+    return lut
+
+
 class Engine:
     """One ems_handle.  Tensors in / out are torch CUDA tensors (device memory only)."""
 
@@ -156,6 +184,13 @@ class Engine:
         n = C.c_size_t()
         self._check(self.lib.ems_frame_count(self.h, n_samples, C.byref(n)))
         return n.value
+
+    def cursor_info(self, column: float, row: float) -> dict:
+        """Time, frequency and nearest note under output cell (column, row)."""
+        c = Cursor()
+        self._check(self.lib.ems_cursor_info(self.h, float(column), float(row), C.byref(c)))
+        return {"time_s": c.time_s, "freq_hz": c.freq_hz, "midi_note": c.midi_note,
+                "cents": c.cents, "name": c.name.decode()}
 
     def use_torch_stream(self):
         """Run on torch's current stream so torch.cuda.Event timing and ordering apply."""

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define EMS_ABI_VERSION 4
+#define EMS_ABI_VERSION 5
 
 typedef enum ems_status {
     EMS_OK = 0,
@@ -125,6 +125,29 @@ ems_status ems_output_rows(const ems_handle* h, size_t* rows);
 
 /* F for n_samples_per_ch samples with this handle's n_fft / hop. */
 ems_status ems_frame_count(const ems_handle* h, size_t n_samples_per_ch, size_t* n_frames);
+
+/* Cursor readout (/root/reference/README.md:39 "Hold Shift and hover over the spectrogram to see note
+ * and frequency information"): what lies under output cell (column, row) of this handle's pictures.
+ * Pure host arithmetic on the handle's geometry — the inverse of the row mapping the scatter uses
+ * (row -> frequency; fractional rows follow the axis between row centres, rows are clamped to
+ * [0, R-1]) and the frame clock (column f is centred on sample f*H + N/2). */
+typedef struct ems_cursor {
+    double  time_s;    /* centre of the column [s] */
+    double  freq_hz;   /* frequency of the row [Hz] */
+    int32_t midi_note; /* nearest equal-tempered note, A4 = 440 Hz = 69; -1 when freq_hz < 1 Hz */
+    float   cents;     /* freq_hz relative to that note, in [-50, 50] */
+    char    name[8];   /* "A4", "C#3", "D-1"; "" when midi_note = -1 */
+} ems_cursor;
+ems_status ems_cursor_info(const ems_handle* h, double column, double row, ems_cursor* out);
+
+/* Built-in colour maps ("Multiple Color Maps", /root/reference/README.md:15,45): 256 packed
+ * 0xAABBGGRR pixels for ems_colorize / ems_stream_set_colormap.  The maps are stand-ins (EM-Spec's own
+ * tables are not published): piecewise-linear ramps through a few 8-bit control colours, evaluated in
+ * integer arithmetic (exactly reproducible).  ids 0..ems_colormap_count()-1; ems_colormap_name
+ * returns NULL for any other id. */
+int         ems_colormap_count(void);
+const char* ems_colormap_name(int id);
+ems_status  ems_colormap_builtin(int id, uint32_t lut_rgba_host[256]);
 
 /* a1-a3, "reassignment method" (/root/reference/README.md:3,11).
  * pcm_dev: fp32 planar [channels][n_samples_per_ch].

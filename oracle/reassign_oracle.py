@@ -199,6 +199,55 @@ def row_frequencies(prm: Params) -> np.ndarray:
     return x * prm.sample_rate / 2
 
 
+NOTE_NAMES = ("C", "C#", "D", "D#", "E", "F", "F#", "G", "G#", "A", "A#", "B")
+
+
+def cursor_info(column: float, row: float, prm: Params) -> dict:
+    """Time, frequency and nearest equal-tempered note under output cell (column, row)
+    (README.md:39 "note and frequency information"; include/emspec.h::ems_cursor_info).  Fractional
+    rows follow the axis between the row centres of `row_frequencies`; A4 = 440 Hz = MIDI 69."""
+    R = prm.n_rows
+    r = min(max(float(row), 0.0), R - 1.0)
+    if prm.display_rows <= 0:
+        f = r * prm.sample_rate / prm.n_fft
+    else:
+        u = r / (R - 1) if R > 1 else 0.0
+        a = prm.warp_a
+        f = (math.expm1(u * math.log1p(a)) / a if a > 1e-6 else u) * prm.sample_rate / 2
+    out = {"time_s": (column * prm.hop + prm.n_fft / 2) / prm.sample_rate, "freq_hz": f,
+           "midi_note": -1, "cents": 0.0, "name": ""}
+    if f >= 1.0:
+        pitch = 69.0 + 12.0 * math.log2(f / 440.0)
+        note = math.floor(pitch + 0.5)
+        out.update(midi_note=int(note), cents=100.0 * (pitch - note),
+                   name=f"{NOTE_NAMES[int(note) % 12]}{int(note) // 12 - 1}")
+    return out
+
+
+# Stand-in colour maps (README.md:15,45 "Multiple Color Maps"): (position, r, g, b) control colours.
+COLORMAPS = {
+    "gray": ((0, 0, 0, 0), (255, 255, 255, 255)),
+    "heat": ((0, 0, 0, 0), (85, 200, 0, 0), (170, 255, 200, 0), (255, 255, 255, 255)),
+    "magma": ((0, 0, 0, 4), (64, 81, 18, 124), (128, 183, 55, 121), (192, 252, 137, 97), (255, 252, 253, 191)),
+    "viridis": ((0, 68, 1, 84), (64, 59, 82, 139), (128, 33, 145, 140), (192, 94, 201, 98), (255, 253, 231, 37)),
+    "ice": ((0, 0, 0, 0), (96, 0, 60, 160), (192, 80, 200, 255), (255, 255, 255, 255)),
+}
+
+
+def builtin_colormap(name: str) -> np.ndarray:
+    """256 packed 0xAABBGGRR pixels: linear ramps between the control colours, rounded to nearest in
+    integer arithmetic ((c0 (d - t) + c1 t + d // 2) // d), alpha 255."""
+    lut = np.zeros(256, np.uint32)
+    stops = COLORMAPS[name]
+    for (p0, *c0), (p1, *c1) in zip(stops[:-1], stops[1:]):
+        d = p1 - p0
+        for i in range(p0, p1 + 1):
+            t = i - p0
+            r, g, b = ((a * (d - t) + z * t + d // 2) // d for a, z in zip(c0, c1))
+            lut[i] = 0xFF000000 | (b << 16) | (g << 8) | r
+    return lut
+
+
 def scatter_grid(dcol, dbin, energy, prm: Params | None = None) -> np.ndarray:
     """a4: G[f + rint(dt_cols), output_row(k + dk_bins)] += e over kept (e > 0) points; fp64 [F][R]."""
     F, B = energy.shape

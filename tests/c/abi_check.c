@@ -27,6 +27,8 @@ _Static_assert(offsetof(ems_params, freq_scale) == 44, "freq_scale");
 _Static_assert(offsetof(ems_params, agc_strength) == 48, "agc_strength");
 _Static_assert(offsetof(ems_params, brightness) == 52, "brightness");
 _Static_assert(sizeof(ems_status) == sizeof(int), "status codes travel as int");
+_Static_assert(sizeof(ems_cursor) == 32 && offsetof(ems_cursor, freq_hz) == 8 && offsetof(ems_cursor, midi_note) == 16 &&
+               offsetof(ems_cursor, cents) == 20 && offsetof(ems_cursor, name) == 24, "ems_cursor layout");
 
 #define OFF(f) printf(#f " %zu\n", offsetof(ems_params, f))
 
@@ -65,6 +67,15 @@ static int run(void) {
         for (size_t r = 1; r < R; ++r) if (img[f * R + r] > img[f * R + best]) best = r;
         if ((int)best != k0 || img[f * R + best] == 0) ++bad;
     }
+    ems_cursor cur;                                      /* the tone's row reads back as its frequency and note */
+    if (ems_cursor_info(h, 8.0, (double)k0, &cur) != EMS_OK) return 9;
+    if (fabs(cur.freq_hz - k0 * 48000.0 / 2048.0) > 1e-9 || strcmp(cur.name, "B5") != 0 || cur.midi_note != 83 ||
+        fabs(cur.time_s - (8 * 256 + 1024) / 48000.0) > 1e-12) {
+        fprintf(stderr, "cursor %g Hz %s %d %+.1f cents %g s\n", cur.freq_hz, cur.name, cur.midi_note, cur.cents, cur.time_s);
+        return 10;
+    }
+    uint32_t lut[256];
+    if (ems_colormap_count() < 1 || !ems_colormap_name(0) || ems_colormap_builtin(0, lut) != EMS_OK || lut[255] != 0xFFFFFFFFu) return 11;
     size_t scratch = 0;
     ems_scratch_bytes(h, &scratch);
     printf("frames %zu rows %zu bad_columns %d scratch_bytes %zu\n", F, R, bad, scratch);

@@ -28,7 +28,7 @@ def test_header_symbols_all_exported(lib_built):
 def test_abi_version_and_status_strings(lib_built):
     import emspec
     lib = emspec.load()
-    assert lib.ems_abi_version() == 4
+    assert lib.ems_abi_version() == 5
     assert lib.ems_status_str(0) == b"ok"
     for s in range(1, 6):
         assert len(lib.ems_status_str(s)) > 0
@@ -122,3 +122,28 @@ def test_c_caller_end_to_end(lib_built, tmp_path):
     res = subprocess.run([exe, "run"], capture_output=True, text=True, timeout=300)
     assert res.returncode == 0, res.stdout + res.stderr
     assert "bad_columns 0" in res.stdout
+
+
+def test_builtin_colour_maps_match_the_oracle_bit_for_bit(lib_built):
+    """"Multiple Color Maps" (README.md:15,45): host-side integer work, callable without a GPU; every
+    built-in table equals the oracle's restatement, is opaque, starts dark and ends bright."""
+    import numpy as np
+    import emspec
+    import reassign_oracle as orc
+    names = emspec.colormap_names()
+    assert names == list(orc.COLORMAPS) and len(names) == emspec.load().ems_colormap_count()
+    for i, name in enumerate(names):
+        lut = emspec.builtin_colormap(i)
+        assert lut.dtype == np.uint32 and lut.shape == (256,)
+        assert (lut == orc.builtin_colormap(name)).all(), name
+        assert (emspec.builtin_colormap(name) == lut).all()
+        assert ((lut >> 24) == 0xFF).all()
+        luma = (lut & 0xFF).astype(int) * 2 + ((lut >> 8) & 0xFF) * 5 + ((lut >> 16) & 0xFF)
+        assert luma[0] < 300 and luma[255] > 1400 and luma[255] == luma.max(), name
+    lib = emspec.load()
+    buf = np.zeros(256, np.uint32)
+    for bad in (-1, len(names)):
+        assert lib.ems_colormap_name(bad) is None
+        assert lib.ems_colormap_builtin(bad, ctypes.c_void_p(buf.ctypes.data)) == emspec.ERR_INVALID_ARG
+    assert lib.ems_colormap_builtin(0, None) == emspec.ERR_INVALID_ARG
+    assert lib.ems_cursor_info(None, 0.0, 0.0, None) == emspec.ERR_INVALID_ARG

@@ -1064,3 +1064,56 @@ def test_stream_push_int24(emspec):
             n += 1
     assert n > 50
     a.close(); b.close()
+
+
+@pytest.mark.parametrize("kw", [dict(n_fft=4096, hop=128), dict(n_fft=2048, hop=512, display_rows=546, freq_scale=1.0),
+                                dict(n_fft=8192, hop=256, display_rows=300, freq_scale=0.0, sample_rate=44100.0)])
+def test_cursor_readout_matches_the_oracle(emspec, kw):
+    """README.md:39 "note and frequency information" under the cursor: ems_cursor_info is the inverse of
+    the row mapping the scatter uses.  Checked against the oracle's cursor_info / row_frequencies on whole and
+    fractional rows, out-of-range rows (clamped), and through the picture itself: the brightest row of a
+    tone's image reads back as the tone's frequency and note."""
+    prm = orc.Params(**kw)
+    eng = emspec.Engine(flags=prm.flags | emspec.FLAG_SYNC, **kw)
+    R = eng.n_rows
+    assert R == prm.n_rows
+    fr = orc.row_frequencies(prm)
+    rng = np.random.default_rng(3)
+    rows = np.concatenate([np.arange(R, dtype=np.float64)[:: max(1, R // 97)], rng.uniform(0, R - 1, 50), [-5.0, R + 3.5, R - 1]])
+    for r in rows:
+        col = float(rng.integers(0, 100000))
+        got, want = eng.cursor_info(col, r), orc.cursor_info(col, r, prm)
+        assert abs(got["freq_hz"] - want["freq_hz"]) <= 1e-9 * max(1.0, want["freq_hz"])
+        assert abs(got["time_s"] - want["time_s"]) <= 1e-12 * max(1.0, want["time_s"])
+        if abs(abs(want["cents"]) - 50.0) > 1e-6:                    # away from the tie between two notes
+            assert got["midi_note"] == want["midi_note"] and got["name"] == want["name"]
+            assert abs(got["cents"] - want["cents"]) < 1e-4
+        if float(r).is_integer() and 0 <= r < R:
+            assert abs(got["freq_hz"] - fr[int(r)]) <= 1e-9 * max(1.0, fr[int(r)])
+    assert eng.cursor_info(0, 0)["midi_note"] == -1 and eng.cursor_info(0, 0)["name"] == ""
+    # A4 through the picture
+    sr = prm.sample_rate
+    t = np.arange(int(sr)) / sr
+    x = (0.5 * np.sin(2 * np.pi * 440.0 * t)).astype(np.float32)
+    _, img = eng.process_grid(torch.from_numpy(x).cuda(), want_grid=False)
+    img = img[0].cpu().numpy()
+    f = img.shape[0] // 2
+    info = eng.cursor_info(f, int(np.argmax(img[f])))
+    assert info["name"] == "A4" and info["midi_note"] == 69
+    row_hz = max(fr[min(R - 1, int(np.argmax(img[f])) + 1)] - fr[int(np.argmax(img[f]))], sr / prm.n_fft)
+    assert abs(info["freq_hz"] - 440.0) <= row_hz
+    assert abs(info["time_s"] - (f * prm.hop + prm.n_fft / 2) / sr) < 1e-12
+    eng.close()
+
+
+def test_builtin_colour_map_through_the_device_lookup(emspec):
+    """A built-in table (ems_colormap_builtin) fed to ems_colorize gives lut[index] on a real image."""
+    eng = emspec.Engine(n_fft=1024, hop=256, flags=emspec.FLAG_REASSIGN | emspec.FLAG_DETERMINISTIC | emspec.FLAG_SYNC)
+    x = torch.from_numpy(orc.synth_signal(SR // 2, SR, seed=21)).cuda()
+    _, img = eng.process_grid(x, want_grid=False)
+    for name in emspec.colormap_names():
+        lut = emspec.builtin_colormap(name)
+        assert (lut == orc.builtin_colormap(name)).all()
+        rgba = eng.colorize(img, lut)
+        assert (rgba.cpu().numpy().view(np.uint32) == lut[img.cpu().numpy()]).all()
+    eng.close()
