@@ -15,6 +15,7 @@
 
 #include "common.cuh"
 #include "scatter_post.cuh"
+#include "scatter_sorted.cuh"
 #include "stft_generic.cuh"
 #include "stft_r16.cuh"
 #include "stft_r64.cuh"
@@ -44,7 +45,7 @@ struct ems_handle {
     float*  thw = nullptr;              // [N] th' window
     float2* tw = nullptr;               // [N]
     float*  weight = nullptr;           // [B]
-    ems::DevBuf acc, flags, carry, ema_local, ema_carry, big_scratch, lut, colscale, agc_level, post_mode;
+    ems::DevBuf acc, flags, carry, ema_local, ema_carry, big_scratch, lut, colscale, agc_level, post_mode, sort_buf;
     bool post_mode_init = false;
     struct HostPipe {                   // ems_process_host*: two of everything, chunk c uses set c & 1
         ems::DevBuf pcm[2], raw[2], idx[2], grid[2];   // fp32 planar chunk, raw int16/int24 chunk, staging images
@@ -802,7 +803,7 @@ ems_status ems_destroy(ems_handle* h) {
     if (!h) return EMS_ERR_INVALID_ARG;
     if (h->stream) cudaStreamSynchronize(h->stream);
     for (DevBuf* b : {&h->acc, &h->flags, &h->carry, &h->ema_local, &h->ema_carry, &h->lut, &h->stream_lut, &h->colscale, &h->agc_level,
-                      &h->big_scratch, &h->post_mode, &h->fz.ready, &h->fz.done, &h->hp.pcm[0], &h->hp.pcm[1], &h->hp.raw[0], &h->hp.raw[1], &h->hp.idx[0], &h->hp.idx[1],
+                      &h->big_scratch, &h->post_mode, &h->sort_buf, &h->fz.ready, &h->fz.done, &h->hp.pcm[0], &h->hp.pcm[1], &h->hp.raw[0], &h->hp.raw[1], &h->hp.idx[0], &h->hp.idx[1],
                       &h->hp.grid[0], &h->hp.grid[1]})
         if (b->p) cudaFree(b->p);
     if (h->hp.events) {
@@ -957,6 +958,47 @@ ems_status ems_process_points(ems_handle* h, const float* pcm, size_t S, float* 
     return finish(h);
 }
 
+// a4 as sort-by-cell + segmented reduce (scatter_sorted.cuh), in chunks of at most 2^25 points so that
+// the scratch (two key and two value buffers, 24 bytes per point) stays below 1 GB.
+static ems_status scatter_sorted(ems_handle* h, const float* dt_cols, const float* dk_bins, const float* energy,
+                                 size_t points, size_t cells, long long F, int B, int R, const StftArgs& wa) {
+    namespace so = ems::sorted;
+    size_t chunk_max = (size_t)1 << 25;
+    if (const char* ev = getenv("EMS_SORT_CHUNK")) { const long long v = atoll(ev); if (v > 0) chunk_max = std::min(chunk_max, (size_t)v); }   // tests: chunk seams on small inputs
+    const size_t chunk = std::min(points, chunk_max);
+    const int G = h->sm_count * 4;
+    const size_t table = (size_t)so::kRadix * G * sizeof(unsigned);
+    ems_status s = ensure(h, h->sort_buf, chunk * 24 + table);
+    if (s != EMS_OK) return s;
+    unsigned long long* keys[2] = {(unsigned long long*)h->sort_buf.p, (unsigned long long*)h->sort_buf.p + chunk};
+    float* vals[2] = {(float*)(keys[1] + chunk), (float*)(keys[1] + chunk) + chunk};
+    unsigned* counts = (unsigned*)(vals[1] + chunk);
+    int bits = 0;
+    while (bits < 64 && ((unsigned long long)cells >> bits) != 0ull) ++bits;     // the sentinel key is `cells` itself
+    const int passes = (bits + 7) / 8;
+    const int kb = (int)std::min<size_t>((chunk + 255) / 256, (size_t)h->sm_count * 16);
+    for (size_t i0 = 0; i0 < points; i0 += chunk) {
+        const long long n = (long long)std::min(chunk, points - i0);
+        long long span = (n + G - 1) / G;
+        span = (span + so::kTile - 1) / so::kTile * so::kTile;
+        so::keys_kernel<<<kb, 256, 0, h->stream>>>(dt_cols, dk_bins, energy, (long long)i0, n, keys[0], vals[0], F, B, R,
+                                                   (unsigned long long)cells, wa.warp_mode, wa.warp_a, wa.warp_c, wa.inv_half);
+        int cur = 0;
+        for (int p = 0; p < passes; ++p, cur ^= 1) {
+            so::histogram_kernel<<<G, so::kThreads, 0, h->stream>>>(keys[cur], n, span, 8 * p, counts);
+            so::scan_kernel<<<1, 1024, 0, h->stream>>>(counts, so::kRadix * G);
+            so::scatter_kernel<<<G, so::kThreads, 0, h->stream>>>(keys[cur], vals[cur], keys[cur ^ 1], vals[cur ^ 1], n, span,
+                                                                    8 * p, counts);
+            h->launches += 3;
+        }
+        so::reduce_kernel<<<kb, 256, 0, h->stream>>>(keys[cur], vals[cur], n, (unsigned long long)cells, (float*)h->acc.p,
+                                                     (unsigned char*)h->flags.p, F, R);
+        h->launches += 2;
+        EMS_CUDA(h, cudaGetLastError());
+    }
+    return EMS_OK;
+}
+
 ems_status ems_scatter_points(ems_handle* h, const float* dt_cols, const float* dk_bins,
                               const float* energy, size_t n_frames, float* grid, uint8_t* index) {
     if (!h) return EMS_ERR_INVALID_ARG;
@@ -976,17 +1018,24 @@ ems_status ems_scatter_points(ems_handle* h, const float* dt_cols, const float* 
     const long long cap = (long long)h->sm_count * 32;
     if (blocks > cap) blocks = cap;
     const StftArgs wa = make_args(h, nullptr, 0, F);   // carries the frequency-axis warp
-    scatter_points_kernel<<<(unsigned)blocks, 256, 0, h->stream>>>(
-        dt_cols, dk_bins, energy, h->acc.p, det, (unsigned char*)h->flags.p, F, B, C, R,
-        wa.warp_mode, wa.warp_a, wa.warp_c, wa.inv_half);
-    ++h->launches;
+    const bool sorted = h->prm.flags & EMS_FLAG_SORTED_SCATTER;
+    if (sorted) {
+        if ((s = scatter_sorted(h, dt_cols, dk_bins, energy, points, cells, F, B, R, wa)) != EMS_OK) { stage_abort(); return s; }
+    } else {
+        scatter_points_kernel<<<(unsigned)blocks, 256, 0, h->stream>>>(
+            dt_cols, dk_bins, energy, h->acc.p, det, (unsigned char*)h->flags.p, F, B, C, R,
+            wa.warp_mode, wa.warp_a, wa.warp_c, wa.inv_half);
+        ++h->launches;
+    }
     if (cudaError_t le = cudaGetLastError(); le != cudaSuccess) {
         stage_abort();
         return fail(h, EMS_ERR_CUDA, "scatter_points_kernel: %s", cudaGetErrorString(le));
     }
     stage_end(h, EMS_STAGE_SCATTER);
     stage_begin(h, EMS_STAGE_POST);
-    if ((s = run_post(h, make_post(h, F, grid, index))) != EMS_OK) { stage_abort(); return s; }
+    PostArgs pa = make_post(h, F, grid, index);
+    if (sorted) pa.acc_is_u64 = 0;                      // the sorted scatter sums in fp32
+    if ((s = run_post(h, pa)) != EMS_OK) { stage_abort(); return s; }
     h->acc_clean = true;
     stage_end(h, EMS_STAGE_POST);
     return finish(h);
@@ -1255,7 +1304,7 @@ ems_status ems_process_host_i24(ems_handle* h, const uint8_t* pcm_host, size_t S
 ems_status ems_scratch_bytes(const ems_handle* h, size_t* bytes) {
     if (!h || !bytes) return EMS_ERR_INVALID_ARG;
     size_t n = 0;
-    for (const DevBuf* b : {&h->acc, &h->flags, &h->carry, &h->ema_local, &h->ema_carry, &h->big_scratch, &h->lut, &h->stream_lut,
+    for (const DevBuf* b : {&h->acc, &h->flags, &h->carry, &h->ema_local, &h->ema_carry, &h->big_scratch, &h->sort_buf, &h->lut, &h->stream_lut,
                             &h->colscale, &h->agc_level, &h->hp.pcm[0], &h->hp.pcm[1], &h->hp.raw[0], &h->hp.raw[1],
                             &h->hp.idx[0], &h->hp.idx[1], &h->hp.grid[0], &h->hp.grid[1]})
         n += b->bytes;

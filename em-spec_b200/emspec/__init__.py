@@ -18,6 +18,7 @@ FLAG_REASSIGN = 1
 FLAG_DETERMINISTIC = 2
 FLAG_SYNC = 4
 FLAG_BOUNDED_SCRATCH = 8
+FLAG_SORTED_SCATTER = 16
 STAGE_POINTS, STAGE_SCATTER, STAGE_POST = 0, 1, 2
 
 OK, ERR_INVALID_ARG, ERR_UNSUPPORTED, ERR_CUDA, ERR_NOMEM, ERR_STATE = range(6)

@@ -57,6 +57,13 @@ typedef enum ems_status {
                                      becomes 2 GB); same bits out, a few per cent slower.  ems_process_host*
                                      always work that way. */
 
+#define EMS_FLAG_SORTED_SCATTER 16u /* ems_scatter_points deposits by sort-by-cell + segmented reduce (the scatter
+                                     BASELINE.json's north_star names): a stable radix sort orders the points by
+                                     destination cell, each cell's energies are added in fp32 in ascending point
+                                     order.  Defined by the point order alone (bit-exact across runs), no fixed-point
+                                     quantisation; up to 1 GB of extra scratch; slower than the default
+                                     deterministic mode.  Ignored by the fused ems_process_* paths. */
+
 /* Parameter surface = the README settings glossary (/root/reference/README.md:41-51);
  * defaults in comments are the "Default" preset of assets/settings.png. */
 typedef struct ems_params {

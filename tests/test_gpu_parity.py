@@ -1117,3 +1117,81 @@ def test_builtin_colour_map_through_the_device_lookup(emspec):
         rgba = eng.colorize(img, lut)
         assert (rgba.cpu().numpy().view(np.uint32) == lut[img.cpu().numpy()]).all()
     eng.close()
+
+
+def _sequential_cell_sums(dt, dk, en, F, B, R, chunk):
+    """fp32 grid of the sorted scatter, restated: per chunk of `chunk` points (in point order) every cell's
+    energies are added left to right in fp32, then the chunk's sum is added to the cell."""
+    col = (np.arange(F)[:, None] + np.rint(dt)).astype(np.int64)
+    row = (np.arange(B)[None, :] + np.rint(dk)).astype(np.int64)
+    ok = (en > 0) & (col >= 0) & (col < F) & (row >= 0) & (row < R)
+    key = np.where(ok, col * R + row, -1).reshape(-1)
+    e = en.reshape(-1).astype(np.float32)
+    acc = np.zeros(F * R, np.float32)
+    for i0 in range(0, key.size, chunk):
+        k, v = key[i0:i0 + chunk], e[i0:i0 + chunk]
+        order = np.argsort(k, kind="stable")
+        k, v = k[order], v[order]
+        start = np.flatnonzero(np.r_[True, k[1:] != k[:-1]])
+        end = np.r_[start[1:], k.size]
+        for a, b in zip(start, end):
+            if k[a] < 0:
+                continue
+            s = np.float32(v[a])
+            for j in range(a + 1, b):
+                s = np.float32(s + v[j])
+            acc[k[a]] = np.float32(acc[k[a]] + s)
+    return acc.reshape(F, R)
+
+
+@pytest.mark.parametrize("chunk", [0, 5000, 2048, 777])
+def test_sorted_scatter_is_the_ordered_fp32_sum(emspec, chunk, monkeypatch):
+    """EMS_FLAG_SORTED_SCATTER (north_star's sort-by-bin + segmented reduce): the grid is, bit for bit, the
+    fp32 sum of each cell's energies in ascending point order — also across chunk seams — and agrees with
+    the fixed-point deterministic mode to fp32 round-off."""
+    if chunk:
+        monkeypatch.setenv("EMS_SORT_CHUNK", str(chunk))
+    n_fft, hop = 1024, 256
+    x = orc.synth_signal(SR // 4, SR, seed=31)
+    det = emspec.Engine(n_fft=n_fft, hop=hop, noise_gate_db=-200.0, flags=emspec.FLAG_REASSIGN | emspec.FLAG_DETERMINISTIC | emspec.FLAG_SYNC)
+    srt = emspec.Engine(n_fft=n_fft, hop=hop, noise_gate_db=-200.0,
+                        flags=emspec.FLAG_REASSIGN | emspec.FLAG_DETERMINISTIC | emspec.FLAG_SORTED_SCATTER | emspec.FLAG_SYNC)
+    pts = det.process_points(torch.from_numpy(x).cuda())
+    gd, idd = det.scatter_points(*pts)
+    gs, ids = srt.scatter_points(*pts)
+    gs2, ids2 = srt.scatter_points(*pts)
+    assert torch.equal(gs, gs2) and torch.equal(ids, ids2)
+    dt, dk, en = (p[0].cpu().numpy() for p in pts)
+    F, B = en.shape
+    assert (en > 0).mean() > 0.9                                               # dense: cells collide
+    want = _sequential_cell_sums(dt, dk, en, F, B, B, chunk or dt.size)
+    got = gs[0].cpu().numpy()
+    assert (got.view(np.uint32) == want.view(np.uint32)).all()
+    assert rel_l2(got, gd[0].cpu().numpy()) < 1e-6
+    assert (np.abs(ids[0].cpu().numpy().astype(int) - idd[0].cpu().numpy().astype(int)) <= 1).all()
+    det.close(); srt.close()
+
+
+@pytest.mark.parametrize("kw", [dict(n_fft=4096, hop=128), dict(n_fft=2048, hop=512, channels=2),
+                                dict(n_fft=2048, hop=256, display_rows=546, freq_scale=1.0, smoothing=0.4, agc_strength=0.5)])
+def test_sorted_scatter_matches_the_default_modes(emspec, kw, monkeypatch):
+    """Sorted scatter against the fixed-point mode on sparse and multi-channel input, the warped display
+    axis with smoothing and AGC behind it, several chunks, and a handle that alternates between calls."""
+    monkeypatch.setenv("EMS_SORT_CHUNK", str(300000))
+    ch = kw.get("channels", 1)
+    x = np.stack([orc.synth_signal(SR, SR, seed=50 + c) for c in range(ch)])
+    base = emspec.FLAG_REASSIGN | emspec.FLAG_DETERMINISTIC | emspec.FLAG_SYNC
+    det = emspec.Engine(flags=base, **kw)
+    srt = emspec.Engine(flags=base | emspec.FLAG_SORTED_SCATTER, **kw)
+    xd = torch.from_numpy(x).cuda()
+    pts = det.process_points(xd)
+    gd, idd = det.scatter_points(*pts)
+    for _ in range(2):
+        gs, ids = srt.scatter_points(*pts)
+        assert rel_l2(gs.cpu().numpy(), gd.cpu().numpy()) < 1e-6
+        d = np.abs(ids.cpu().numpy().astype(int) - idd.cpu().numpy().astype(int))
+        assert d.max() <= 1 and (d > 0).mean() < 1e-3
+        g2, i2 = srt.process_grid(xd)                                          # the fused path ignores the flag
+        g3, i3 = det.process_grid(xd)
+        assert torch.equal(g2, g3) and torch.equal(i2, i3)
+    det.close(); srt.close()
