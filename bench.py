@@ -616,6 +616,37 @@ def run_ours(args):
     out = None
     torch.cuda.empty_cache()
 
+    # ---- a4 from stored points in its three modes (north_star names sort-by-bin + segmented reduce as the
+    # deterministic scatter; the engine's default is 64-bit fixed-point reductions): ems_scatter_points on the
+    # points of the first 300 s of the stream, sparse (default gate) and with every bin kept
+    scat = None
+    if rank == 0 and not args.no_dense:
+        scat = {"what": "ems_scatter_points (points in HBM -> u8 image in HBM) on the first 300 s of the stream: "
+                        "frames/s of the whole call; scatter_ms = the library's own events around the deposit stage",
+                "sample_s": 300}
+        S3 = min(S, 300 * SR)
+        F3 = frame_count(S3, N_FFT, HOP)
+        idx3 = torch.empty((1, F3, B), dtype=torch.uint8, device=dev)
+        for sig, gate in (("sparse", args.gate_db), ("dense", -200.0)):
+            src = emspec.Engine(n_fft=N_FFT, hop=HOP, noise_gate_db=gate)
+            src.use_torch_stream()
+            pts = src.process_points(pcm[:S3])
+            src.close()
+            for mode, fl in (("u64_reds", emspec.FLAG_DETERMINISTIC), ("f32_reds", 0),
+                             ("sorted", emspec.FLAG_DETERMINISTIC | emspec.FLAG_SORTED_SCATTER)):
+                e3 = emspec.Engine(n_fft=N_FFT, hop=HOP, noise_gate_db=gate, flags=emspec.FLAG_REASSIGN | fl)
+                e3.use_torch_stream()
+                fn = lambda: e3.lib.ems_scatter_points(e3.h, pts[0].data_ptr(), pts[1].data_ptr(), pts[2].data_ptr(), F3,
+                                                       None, idx3.data_ptr())
+                ms = time_calls(fn, 3, 1)
+                scat[f"{sig}_{mode}"] = {"value": F3 / (ms * 1e-3), "unit": UNIT, "ms_per_call": ms,
+                                         "scatter_ms": e3.stage_ms(emspec.STAGE_SCATTER),
+                                         "scratch_bytes": int(e3.scratch_bytes())}
+                e3.close()
+            del pts
+        del idx3
+        torch.cuda.empty_cache()
+
     # ---- end to end: pinned host PCM -> pinned host u8 image through ems_process_host
     e2e = None
     if not args.no_e2e:
@@ -772,7 +803,7 @@ def run_ours(args):
                        "parallelism": f"one stream per GPU x{world} (replicas, no data-path collective); the clip-sharded "
                                       "multi-GPU workload is the `batch` key"},
             "roofline": roof,
-            "cpu_baseline": cpu, "e2e": e2e, "pipeline_u8": pipe, "worst_case": worst or None, "batch": batch,
+            "cpu_baseline": cpu, "e2e": e2e, "pipeline_u8": pipe, "worst_case": worst or None, "scatter_modes": scat, "batch": batch,
             "e2e_display_rows": e2e_display, "stream_latency": stream, "nfft_sweep": sweep, "gpu_launches": int(launches),
             "clocks": clocks,
         }
