@@ -967,7 +967,7 @@ static ems_status scatter_sorted(ems_handle* h, const float* dt_cols, const floa
     if (const char* ev = getenv("EMS_SORT_CHUNK")) { const long long v = atoll(ev); if (v > 0) chunk_max = std::min(chunk_max, (size_t)v); }   // tests: chunk seams on small inputs
     const size_t chunk = std::min(points, chunk_max);
     const int G = h->sm_count * 4;
-    const size_t table = (size_t)so::kRadix * G * sizeof(unsigned);
+    const size_t table = (size_t)so::kRadix * (G + 1) * sizeof(unsigned);   // digit-major counts + 256 digit totals
     ems_status s = ensure(h, h->sort_buf, chunk * 24 + table);
     if (s != EMS_OK) return s;
     unsigned long long* keys[2] = {(unsigned long long*)h->sort_buf.p, (unsigned long long*)h->sort_buf.p + chunk};
@@ -986,9 +986,9 @@ static ems_status scatter_sorted(ems_handle* h, const float* dt_cols, const floa
         int cur = 0;
         for (int p = 0; p < passes; ++p, cur ^= 1) {
             so::histogram_kernel<<<G, so::kThreads, 0, h->stream>>>(keys[cur], n, span, 8 * p, counts);
-            so::scan_kernel<<<1, 1024, 0, h->stream>>>(counts, so::kRadix * G);
+            so::scan_kernel<<<so::kRadix, 256, 0, h->stream>>>(counts, counts + (size_t)so::kRadix * G, G);
             so::scatter_kernel<<<G, so::kThreads, 0, h->stream>>>(keys[cur], vals[cur], keys[cur ^ 1], vals[cur ^ 1], n, span,
-                                                                    8 * p, counts);
+                                                                    8 * p, counts, counts + (size_t)so::kRadix * G);
             h->launches += 3;
         }
         so::reduce_kernel<<<kb, 256, 0, h->stream>>>(keys[cur], vals[cur], n, (unsigned long long)cells, (float*)h->acc.p,

@@ -65,25 +65,30 @@ histogram_kernel(const unsigned long long* __restrict__ keys, long long n, long 
     counts[(size_t)threadIdx.x * gridDim.x + blockIdx.x] = hist[threadIdx.x];
 }
 
-// Radix pass, part 2: exclusive scan of the digit-major count table (one block; the table has
-// 256 x grid entries, a few hundred thousand).
-__global__ void __launch_bounds__(1024)
-scan_kernel(unsigned* __restrict__ counts, int total) {
-    __shared__ unsigned part[1024];
-    const int per = (total + 1023) / 1024;
-    const int a = min(total, (int)threadIdx.x * per), b = min(total, a + per);
-    unsigned s = 0;
-    for (int i = a; i < b; ++i) s += counts[i];
-    part[threadIdx.x] = s;
-    __syncthreads();
-    for (int d = 1; d < 1024; d <<= 1) {
-        const unsigned v = threadIdx.x >= (unsigned)d ? part[threadIdx.x - d] : 0u;
+// Radix pass, part 2: one block per digit turns its row of the digit-major count table into exclusive
+// offsets within the digit and writes the digit's total; the scatter kernel adds the totals of the
+// smaller digits itself (256 values).
+__global__ void __launch_bounds__(256)
+scan_kernel(unsigned* __restrict__ counts, unsigned* __restrict__ totals, int G) {
+    __shared__ unsigned part[256];
+    unsigned* row = counts + (size_t)blockIdx.x * G;
+    unsigned carry = 0;
+    for (int i0 = 0; i0 < G; i0 += 256) {
+        const int i = i0 + threadIdx.x;
+        const unsigned c = i < G ? row[i] : 0u;
+        part[threadIdx.x] = c;
         __syncthreads();
-        part[threadIdx.x] += v;
+        for (int d = 1; d < 256; d <<= 1) {
+            const unsigned v = threadIdx.x >= (unsigned)d ? part[threadIdx.x - d] : 0u;
+            __syncthreads();
+            part[threadIdx.x] += v;
+            __syncthreads();
+        }
+        if (i < G) row[i] = carry + part[threadIdx.x] - c;
+        carry += part[255];
         __syncthreads();
     }
-    unsigned run = part[threadIdx.x] - s;
-    for (int i = a; i < b; ++i) { const unsigned c = counts[i]; counts[i] = run; run += c; }
+    if (threadIdx.x == 0) totals[blockIdx.x] = carry;
 }
 
 // Radix pass, part 3: stable scatter.  A block walks its span in sub-tiles; inside a sub-tile the
@@ -93,11 +98,23 @@ scan_kernel(unsigned* __restrict__ counts, int total) {
 __global__ void __launch_bounds__(kThreads)
 scatter_kernel(const unsigned long long* __restrict__ keys_in, const float* __restrict__ vals_in,
                unsigned long long* __restrict__ keys_out, float* __restrict__ vals_out,
-               long long n, long long span, int shift, const unsigned* __restrict__ offsets) {
+               long long n, long long span, int shift, const unsigned* __restrict__ offsets,
+               const unsigned* __restrict__ totals) {
     __shared__ unsigned wcount[kWarps][kRadix];
     __shared__ unsigned base[kRadix];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    base[threadIdx.x] = offsets[(size_t)threadIdx.x * gridDim.x + blockIdx.x];
+    {   // exclusive prefix of the digit totals (256 values) + this block's offset within its digit
+        const unsigned t = totals[threadIdx.x];
+        base[threadIdx.x] = t;
+        __syncthreads();
+        for (int d = 1; d < kRadix; d <<= 1) {
+            const unsigned v = threadIdx.x >= (unsigned)d ? base[threadIdx.x - d] : 0u;
+            __syncthreads();
+            base[threadIdx.x] += v;
+            __syncthreads();
+        }
+        base[threadIdx.x] += offsets[(size_t)threadIdx.x * gridDim.x + blockIdx.x] - t;
+    }
     const long long b0 = (long long)blockIdx.x * span, b1 = min(n, b0 + span);
     for (long long t0 = b0; t0 < b1; t0 += kTile) {
 #pragma unroll
