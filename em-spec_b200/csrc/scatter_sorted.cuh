@@ -123,14 +123,18 @@ scatter_kernel(const unsigned long long* __restrict__ keys_in, const float* __re
         unsigned long long key[kItems];
         float val[kItems];
         unsigned rank[kItems];
+        // all loads of the sub-tile are in flight before the first rank is computed
+#pragma unroll
+        for (int j = 0; j < kItems; ++j) {
+            const long long i = t0 + (long long)warp * (32 * kItems) + j * 32 + lane;
+            if (i < b1) { key[j] = keys_in[i]; val[j] = vals_in[i]; }
+        }
 #pragma unroll
         for (int j = 0; j < kItems; ++j) {
             const long long i = t0 + (long long)warp * (32 * kItems) + j * 32 + lane;
             const bool on = i < b1;
             const unsigned active = __ballot_sync(0xffffffffu, on);
             if (on) {
-                key[j] = keys_in[i];
-                val[j] = vals_in[i];
                 const unsigned d = (unsigned)(key[j] >> shift) & 255u;
                 const unsigned peers = __match_any_sync(active, d);
                 const int leader = __ffs(peers) - 1;
