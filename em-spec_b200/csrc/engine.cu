@@ -967,31 +967,35 @@ static ems_status scatter_sorted(ems_handle* h, const float* dt_cols, const floa
     if (const char* ev = getenv("EMS_SORT_CHUNK")) { const long long v = atoll(ev); if (v > 0) chunk_max = std::min(chunk_max, (size_t)v); }   // tests: chunk seams on small inputs
     const size_t chunk = std::min(points, chunk_max);
     const int G = h->sm_count * 4;
-    const size_t table = (size_t)so::kRadix * (G + 1) * sizeof(unsigned);   // digit-major counts + 256 digit totals
+    const size_t table = ((size_t)so::kRadix * (G + 1) + 4) * sizeof(unsigned);   // digit-major counts + 256 digit totals + kept count
     ems_status s = ensure(h, h->sort_buf, chunk * 24 + table);
     if (s != EMS_OK) return s;
     unsigned long long* keys[2] = {(unsigned long long*)h->sort_buf.p, (unsigned long long*)h->sort_buf.p + chunk};
     float* vals[2] = {(float*)(keys[1] + chunk), (float*)(keys[1] + chunk) + chunk};
     unsigned* counts = (unsigned*)(vals[1] + chunk);
+    unsigned* totals = counts + (size_t)so::kRadix * G;
+    unsigned* nkept = totals + so::kRadix;
     int bits = 0;
     while (bits < 64 && ((unsigned long long)cells >> bits) != 0ull) ++bits;     // the sentinel key is `cells` itself
     const int passes = (bits + 7) / 8;
     const int kb = (int)std::min<size_t>((chunk + 255) / 256, (size_t)h->sm_count * 16);
     for (size_t i0 = 0; i0 < points; i0 += chunk) {
         const long long n = (long long)std::min(chunk, points - i0);
-        long long span = (n + G - 1) / G;
-        span = (span + so::kTile - 1) / so::kTile * so::kTile;
         so::keys_kernel<<<kb, 256, 0, h->stream>>>(dt_cols, dk_bins, energy, (long long)i0, n, keys[0], vals[0], F, B, R,
                                                    (unsigned long long)cells, wa.warp_mode, wa.warp_a, wa.warp_c, wa.inv_half);
+        // pass -1: stable partition kept | dropped over all n points; passes 0..: radix passes over the kept ones
         int cur = 0;
-        for (int p = 0; p < passes; ++p, cur ^= 1) {
-            so::histogram_kernel<<<G, so::kThreads, 0, h->stream>>>(keys[cur], n, span, 8 * p, counts);
-            so::scan_kernel<<<so::kRadix, 256, 0, h->stream>>>(counts, counts + (size_t)so::kRadix * G, G);
-            so::scatter_kernel<<<G, so::kThreads, 0, h->stream>>>(keys[cur], vals[cur], keys[cur ^ 1], vals[cur ^ 1], n, span,
-                                                                    8 * p, counts, counts + (size_t)so::kRadix * G);
+        for (int p = -1; p < passes; ++p, cur ^= 1) {
+            const unsigned* n_dev = p < 0 ? nullptr : nkept;
+            const unsigned long long part = p < 0 ? (unsigned long long)cells : 0ull;
+            const int shift = p < 0 ? 0 : 8 * p;
+            so::histogram_kernel<<<G, so::kThreads, 0, h->stream>>>(keys[cur], n, n_dev, shift, part, counts);
+            so::scan_kernel<<<so::kRadix, 256, 0, h->stream>>>(counts, totals, G, p < 0 ? nkept : nullptr);
+            so::scatter_kernel<<<G, so::kThreads, 0, h->stream>>>(keys[cur], vals[cur], keys[cur ^ 1], vals[cur ^ 1], n, n_dev,
+                                                                    shift, part, counts, totals);
             h->launches += 3;
         }
-        so::reduce_kernel<<<kb, 256, 0, h->stream>>>(keys[cur], vals[cur], n, (unsigned long long)cells, (float*)h->acc.p,
+        so::reduce_kernel<<<kb, 256, 0, h->stream>>>(keys[cur], vals[cur], nkept, (unsigned long long)cells, (float*)h->acc.p,
                                                      (unsigned char*)h->flags.p, F, R);
         h->launches += 2;
         EMS_CUDA(h, cudaGetLastError());

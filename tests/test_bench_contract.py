@@ -50,4 +50,7 @@ def test_our_arm_line():
     assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
     assert d["batch"]["clips"] == 128 and len(d["batch"]["clip_checksums_sha16"]) == 16
     assert {"value_dense", "value_broadband", "pipeline_u8_dense", "pipeline_u8_broadband"} <= set(d["worst_case"])
+    sm = d["scatter_modes"]
+    assert {f"{a}_{b}" for a in ("sparse", "dense") for b in ("u64_reds", "f32_reds", "sorted")} <= set(sm)
+    assert all(sm[k]["value"] > 0 and sm[k]["scatter_ms"] > 0 for k in sm if isinstance(sm[k], dict))
     assert len(d["nfft_sweep"]) == 8 and d["stream_latency"]["p50_us"] < 1000.0     # the < 1 ms target of north_star
