@@ -314,11 +314,23 @@ __device__ __forceinline__ float gate_power(const StftArgs& a) { return a.gate_l
 // `off` is the bin's index relative to the row pointers of fc (k itself, or a compile-time
 // multiple of the residue stride when fc points at the thread's residue: the stores then take
 // immediate offsets from six live base pointers instead of a 64-bit address computation each).
+#ifndef EMS_STORE_POLICY
+#define EMS_STORE_POLICY 0      // trial: 1 = st.global.cs (evict-first) for the point stores, 2 = st.global.wt
+#endif
+__device__ __forceinline__ void st_point(float* p, float v) {
+#if EMS_STORE_POLICY == 1
+    __stcs(p, v);
+#elif EMS_STORE_POLICY == 2
+    __stwt(p, v);
+#else
+    __stwb(p, v);
+#endif
+}
 template <int MODE>
 __device__ __forceinline__ void bin_dead(const FrameCtx& fc, bool owner, int off) {
     // __stwb = st.global.wb, the default policy spelled out: the row pointers went through an
     // opaque asm and would otherwise be stored through as generic addresses
-    if (MODE == kStorePoints && owner) { __stwb(fc.pd + off, 0.f); __stwb(fc.pk + off, 0.f); __stwb(fc.pe + off, 0.f); }
+    if (MODE == kStorePoints && owner) { st_point(fc.pd + off, 0.f); st_point(fc.pk + off, 0.f); st_point(fc.pe + off, 0.f); }
 }
 template <int N, int MODE>
 __device__ __forceinline__ void bin_tail(const StftArgs& a, const FrameCtx& fc, bool owner, bool live, int k, int off,
@@ -347,7 +359,7 @@ __device__ __forceinline__ void bin_tail(const StftArgs& a, const FrameCtx& fc, 
         dk = ok ? dk : 0.f;
     }
     if (MODE == kStorePoints) {
-        if (owner) { __stwb(fc.pd + off, dtc); __stwb(fc.pk + off, dk); __stwb(fc.pe + off, ok ? e : 0.f); }
+        if (owner) { st_point(fc.pd + off, dtc); st_point(fc.pk + off, dk); st_point(fc.pe + off, ok ? e : 0.f); }
     } else {
 #if EMS_DEPOSIT_AGG
         // Experiment: warp-level pre-aggregation.  Lanes hold adjacent bins of one frame, so
