@@ -885,6 +885,21 @@ static double row_to_hz(const ems_params& p, double row) {
     return nyq * (a > 1e-6 ? std::expm1(u * std::log1p(a)) / a : u);
 }
 
+ems_status ems_hz_to_row(const ems_handle* h, double freq_hz, double* row) {
+    if (!h || !row || !(freq_hz == freq_hz)) return EMS_ERR_INVALID_ARG;
+    const ems_params& p = h->prm;
+    const int R = rows_of(p);
+    double r;
+    if (p.display_rows <= 0) {
+        r = freq_hz * (double)p.n_fft / (double)p.sample_rate;
+    } else {
+        const double x = std::min(std::max(freq_hz / (0.5 * (double)p.sample_rate), 0.0), 1.0), a = warp_a_of(p);
+        r = (double)(R - 1) * (a > 1e-6 ? std::log1p(a * x) / std::log1p(a) : x);
+    }
+    *row = std::min(std::max(r, 0.0), (double)(R - 1));
+    return EMS_OK;
+}
+
 // "note and frequency information" under the cursor (/root/reference/README.md:39).
 ems_status ems_cursor_info(const ems_handle* h, double column, double row, ems_cursor* out) {
     if (!h || !out || !(column == column) || !(row == row)) return EMS_ERR_INVALID_ARG;
@@ -912,6 +927,7 @@ namespace {
 struct ColourStop { int pos; int r, g, b; };
 struct ColourMap { const char* name; int n; ColourStop stop[5]; };
 const ColourMap kColourMaps[] = {
+    {"inferno", 5, {{0, 0, 0, 4}, {64, 87, 16, 110}, {128, 188, 55, 84}, {192, 249, 142, 9}, {255, 252, 255, 164}}},   // settings.png "Default" preset
     {"gray",    2, {{0, 0, 0, 0}, {255, 255, 255, 255}}},
     {"heat",    4, {{0, 0, 0, 0}, {85, 200, 0, 0}, {170, 255, 200, 0}, {255, 255, 255, 255}}},
     {"magma",   5, {{0, 0, 0, 4}, {64, 81, 18, 124}, {128, 183, 55, 121}, {192, 252, 137, 97}, {255, 252, 253, 191}}},

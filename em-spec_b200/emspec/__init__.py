@@ -64,6 +64,7 @@ _SIG = {
     "ems_output_rows": (C.c_int, [_VP, C.POINTER(C.c_size_t)]),
     "ems_frame_count": (C.c_int, [_VP, C.c_size_t, C.POINTER(C.c_size_t)]),
     "ems_cursor_info": (C.c_int, [_VP, C.c_double, C.c_double, C.POINTER(Cursor)]),
+    "ems_hz_to_row": (C.c_int, [_VP, C.c_double, C.POINTER(C.c_double)]),
     "ems_colormap_count": (C.c_int, []),
     "ems_colormap_name": (C.c_char_p, [C.c_int]),
     "ems_colormap_builtin": (C.c_int, [C.c_int, _VP]),
@@ -192,6 +193,12 @@ class Engine:
         self._check(self.lib.ems_cursor_info(self.h, float(column), float(row), C.byref(c)))
         return {"time_s": c.time_s, "freq_hz": c.freq_hz, "midi_note": c.midi_note,
                 "cents": c.cents, "name": c.name.decode()}
+
+    def hz_to_row(self, freq_hz: float) -> float:
+        """Fractional output row of a frequency (axis ticks, note grid lines)."""
+        r = C.c_double()
+        self._check(self.lib.ems_hz_to_row(self.h, float(freq_hz), C.byref(r)))
+        return r.value
 
     def use_torch_stream(self):
         """Run on torch's current stream so torch.cuda.Event timing and ordering apply."""

@@ -146,11 +146,16 @@ typedef struct ems_cursor {
     char    name[8];   /* "A4", "C#3", "D-1"; "" when midi_note = -1 */
 } ems_cursor;
 ems_status ems_cursor_info(const ems_handle* h, double column, double row, ems_cursor* out);
+/* The other direction, for axis ticks and note grid lines over the picture: the (fractional) output row
+ * of a frequency — exactly the mapping the scatter rounds to place a point (bin axis: f n_fft / sample_rate;
+ * warped display axis: (R-1) log1p(a x) / log1p(a)), clamped to [0, R-1]. */
+ems_status ems_hz_to_row(const ems_handle* h, double freq_hz, double* row);
 
 /* Built-in colour maps ("Multiple Color Maps", /root/reference/README.md:15,45): 256 packed
  * 0xAABBGGRR pixels for ems_colorize / ems_stream_set_colormap.  The maps are stand-ins (EM-Spec's own
  * tables are not published): piecewise-linear ramps through a few 8-bit control colours, evaluated in
- * integer arithmetic (exactly reproducible).  ids 0..ems_colormap_count()-1; ems_colormap_name
+ * integer arithmetic (exactly reproducible).  id 0 is "inferno", the map of the settings.png "Default"
+ * preset.  ids 0..ems_colormap_count()-1; ems_colormap_name
  * returns NULL for any other id. */
 int         ems_colormap_count(void);
 const char* ems_colormap_name(int id);

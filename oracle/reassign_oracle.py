@@ -199,6 +199,18 @@ def row_frequencies(prm: Params) -> np.ndarray:
     return x * prm.sample_rate / 2
 
 
+def hz_to_row(freq_hz: float, prm: Params) -> float:
+    """Fractional output row of a frequency: the mapping `output_row` rounds (include/emspec.h::ems_hz_to_row)."""
+    R = prm.n_rows
+    if prm.display_rows <= 0:
+        r = freq_hz * prm.n_fft / prm.sample_rate
+    else:
+        x = min(max(freq_hz / (prm.sample_rate / 2), 0.0), 1.0)
+        a = prm.warp_a
+        r = (R - 1) * (math.log1p(a * x) / math.log1p(a) if a > 1e-6 else x)
+    return min(max(r, 0.0), R - 1.0)
+
+
 NOTE_NAMES = ("C", "C#", "D", "D#", "E", "F", "F#", "G", "G#", "A", "A#", "B")
 
 
@@ -226,6 +238,7 @@ def cursor_info(column: float, row: float, prm: Params) -> dict:
 
 # Stand-in colour maps (README.md:15,45 "Multiple Color Maps"): (position, r, g, b) control colours.
 COLORMAPS = {
+    "inferno": ((0, 0, 0, 4), (64, 87, 16, 110), (128, 188, 55, 84), (192, 249, 142, 9), (255, 252, 255, 164)),  # settings.png default
     "gray": ((0, 0, 0, 0), (255, 255, 255, 255)),
     "heat": ((0, 0, 0, 0), (85, 200, 0, 0), (170, 255, 200, 0), (255, 255, 255, 255)),
     "magma": ((0, 0, 0, 4), (64, 81, 18, 124), (128, 183, 55, 121), (192, 252, 137, 97), (255, 252, 253, 191)),

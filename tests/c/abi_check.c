@@ -74,8 +74,11 @@ static int run(void) {
         fprintf(stderr, "cursor %g Hz %s %d %+.1f cents %g s\n", cur.freq_hz, cur.name, cur.midi_note, cur.cents, cur.time_s);
         return 10;
     }
+    double row = -1.0;
+    if (ems_hz_to_row(h, cur.freq_hz, &row) != EMS_OK || fabs(row - k0) > 1e-9) return 12;
     uint32_t lut[256];
-    if (ems_colormap_count() < 1 || !ems_colormap_name(0) || ems_colormap_builtin(0, lut) != EMS_OK || lut[255] != 0xFFFFFFFFu) return 11;
+    if (ems_colormap_count() < 2 || strcmp(ems_colormap_name(0), "inferno") != 0 || ems_colormap_builtin(1, lut) != EMS_OK || lut[255] != 0xFFFFFFFFu ||
+        lut[0] != 0xFF000000u || ems_colormap_name(ems_colormap_count()) != NULL) return 11;   /* id 1 = gray: black to white */
     size_t scratch = 0;
     ems_scratch_bytes(h, &scratch);
     printf("frames %zu rows %zu bad_columns %d scratch_bytes %zu\n", F, R, bad, scratch);

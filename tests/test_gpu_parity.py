@@ -1091,6 +1091,14 @@ def test_cursor_readout_matches_the_oracle(emspec, kw):
         if float(r).is_integer() and 0 <= r < R:
             assert abs(got["freq_hz"] - fr[int(r)]) <= 1e-9 * max(1.0, fr[int(r)])
     assert eng.cursor_info(0, 0)["midi_note"] == -1 and eng.cursor_info(0, 0)["name"] == ""
+    # the other direction (axis ticks): equals the oracle, inverts the read-out, and rounds to the row the scatter uses
+    for hz in (0.0, 27.5, 440.0, 1000.0, 9999.9, prm.sample_rate / 2, 1e6, -3.0):
+        r = eng.hz_to_row(hz)
+        assert abs(r - orc.hz_to_row(hz, prm)) <= 1e-9 * max(1.0, r)
+        if 0 < hz < prm.sample_rate / 2:
+            assert abs(eng.cursor_info(0, r)["freq_hz"] - hz) <= 1e-6 * hz
+            k = hz * prm.n_fft / prm.sample_rate
+            assert int(np.rint(r)) == int(orc.output_row(np.floor(k), np.float64(k - np.floor(k)), prm))
     # A4 through the picture
     sr = prm.sample_rate
     t = np.arange(int(sr)) / sr
