@@ -244,3 +244,37 @@ def test_drop_rule_is_decided_on_the_rounded_row():
     en[50, 2047] = 1.0; db[50, 2047] = 1.49
     g = orc.scatter_grid(dc, db, en, prm)
     assert g[50, 2048] == 1.0 and g.sum() == 1.0
+
+
+def test_cursor_readout_known_notes_and_round_trip():
+    """README.md:39 read-out: known pitches, and row -> Hz -> row is the identity on both axes."""
+    for kw in (dict(n_fft=4096, hop=128), dict(n_fft=2048, hop=512, display_rows=546, freq_scale=1.0),
+               dict(n_fft=8192, hop=256, display_rows=300, freq_scale=0.0)):
+        prm = orc.Params(**kw)
+        for hz, midi, name in ((440.0, 69, "A4"), (261.6256, 60, "C4"), (27.5, 21, "A0"), (4186.009, 108, "C8"),
+                               (466.1638, 70, "A#4"), (8.1758, 0, "C-1")):
+            r = orc.hz_to_row(hz, prm)
+            c = orc.cursor_info(3, r, prm)
+            assert abs(c["freq_hz"] - hz) < 1e-9 * hz and c["midi_note"] == midi and c["name"] == name
+            assert abs(c["cents"]) < 0.01
+            assert abs(c["time_s"] - (3 * prm.hop + prm.n_fft / 2) / prm.sample_rate) < 1e-15
+        rows = np.linspace(0, prm.n_rows - 1, 257)
+        back = [orc.hz_to_row(orc.cursor_info(0, r, prm)["freq_hz"], prm) for r in rows]
+        assert np.abs(np.array(back) - rows).max() < 1e-8
+        fr = orc.row_frequencies(prm)
+        assert np.allclose([orc.cursor_info(0, r, prm)["freq_hz"] for r in range(0, prm.n_rows, 37)], fr[::37], rtol=1e-12, atol=1e-12)
+    assert orc.cursor_info(0, 0, orc.Params())["midi_note"] == -1          # DC: no note
+
+
+def test_builtin_colour_maps_are_ramps_through_their_control_colours():
+    for name, stops in orc.COLORMAPS.items():
+        lut = orc.builtin_colormap(name)
+        assert lut.shape == (256,) and ((lut >> 24) == 0xFF).all()
+        for pos, r, g, b in stops:
+            assert lut[pos] == (0xFF000000 | (b << 16) | (g << 8) | r), (name, pos)
+        for ch in (0, 8, 16):                                              # piecewise monotone between stops
+            v = ((lut >> ch) & 0xFF).astype(int)
+            for (p0, *_), (p1, *_) in zip(stops[:-1], stops[1:]):
+                d = np.diff(v[p0:p1 + 1])
+                assert (d >= 0).all() or (d <= 0).all(), (name, ch, p0)
+    assert list(orc.COLORMAPS)[0] == "inferno"                             # the Default preset's map (settings.png)
