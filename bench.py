@@ -608,6 +608,13 @@ def run_ours(args):
                                           "what": "ems_process_grid with the gate at -200 dB: 2,049 deposits per frame, every "
                                                   "64-row block of the image dirty"}
             dense.close()
+            dense = emspec.Engine(n_fft=N_FFT, hop=HOP, noise_gate_db=-200.0, flags=emspec.FLAG_REASSIGN)
+            dense.use_torch_stream()
+            ms = allmax(time_calls(lambda: dense.process_grid(pcm, out=(None, idx)), max(3, args.steps // 4), 2, barrier))
+            worst["pipeline_u8_dense_fast"] = {"value": frames_all / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms,
+                                               "what": "the same with the fp32 fast mode (red.global.add.f32 instead of the "
+                                                       "64-bit fixed-point reductions; not bit-exact across runs)"}
+            dense.close()
             ms = allmax(time_calls(lambda: eng.process_grid(pcm_bb, out=(None, idx)), max(3, args.steps // 4), 2, barrier))
             worst["pipeline_u8_broadband"] = {"value": frames_all / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms,
                                               "what": "ems_process_grid at the default gate on the broadband signal"}

@@ -49,7 +49,7 @@ def test_our_arm_line():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] > 0
     assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
     assert d["batch"]["clips"] == 128 and len(d["batch"]["clip_checksums_sha16"]) == 16
-    assert {"value_dense", "value_broadband", "pipeline_u8_dense", "pipeline_u8_broadband"} <= set(d["worst_case"])
+    assert {"value_dense", "value_broadband", "pipeline_u8_dense", "pipeline_u8_dense_fast", "pipeline_u8_broadband"} <= set(d["worst_case"])
     sm = d["scatter_modes"]
     assert {f"{a}_{b}" for a in ("sparse", "dense") for b in ("u64_reds", "f32_reds", "sorted")} <= set(sm)
     assert all(sm[k]["value"] > 0 and sm[k]["scatter_ms"] > 0 for k in sm if isinstance(sm[k], dict))
